@@ -1,0 +1,417 @@
+/* TEST INFRASTRUCTURE ONLY -- the reference itself, compiled as a CPU oracle.
+ *
+ * This translation unit #includes the reference's own main.cpp (which pulls in
+ * perlin.h, math.h, vec3.h, list.h, timing.h, pp.h, logging.h, render.h) from
+ * where it lies under /root/reference, UNMODIFIED, and links the reference's
+ * own render.cpp.  No reference source is copied into this repository: the
+ * build recipe (oracle/Makefile, target `ref`) passes `-iquote $(REF)` and the
+ * headless SDL/GL stubs in oracle/stubs/.  Output goes to oracle/_ref/ only
+ * (git-ignored, shipped to the GPU box as a prebuilt .so).
+ *
+ * What is the reference's code and what is ours in here:
+ *   - every number returned by a ref_* function is computed by reference code:
+ *     PerlinRandom/PerlinGradient/PerlinNoise3 (perlin.h:38-88), PerlinfBm /
+ *     PerlinRidged (main.cpp:689-734), CreateHeightMapGenerator<F>'s
+ *     GetHeightAt / GenerateHeightMap (main.cpp:113-158), QuadID helpers
+ *     (main.cpp:19-65), InitPlanet's vertex/index build (main.cpp:391-481),
+ *     ProcessQuad / RenderPlanet (main.cpp:537-683), and main() itself;
+ *   - ours: the recording fake OpenGL below, and `OracleHeight`, a functor that
+ *     restates the 6-line body of `Perlin::operator()` (main.cpp:823-833) with
+ *     its constants lifted into a config struct.  `Perlin` is a local struct
+ *     inside the reference's main() and cannot be named from outside; to pin
+ *     the restated functor, ref_run_reference_main() runs the reference's real
+ *     main() for one headless frame and captures the height maps its real
+ *     local functor produced (oracle/gen_golden.py asserts both agree bit for
+ *     bit).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * `--impl reference` legs may load this library.  The product never does.
+ */
+#include <vector>
+#include <string>
+#include <thread>
+#include <unistd.h>
+
+#define main planet_reference_main
+#include "main.cpp"
+#undef main
+
+/* ------------------------------------------------------------------------- */
+/* recording fake OpenGL                                                      */
+/* ------------------------------------------------------------------------- */
+namespace fakegl {
+
+struct Buffer { GLenum target; std::vector<unsigned char> bytes; };
+struct HeightMap { int w, h; std::vector<float> texels; };
+struct DrawRecord {
+    float P[12], N[12], skirt_size, corners[4], pixel_size[2];
+    GLuint texture; int count;
+};
+
+static GLuint next_id = 1;
+static std::vector<Buffer> buffers;
+static std::vector<HeightMap> height_maps;      /* index = texture id order */
+static std::vector<GLuint> height_map_ids;
+static std::vector<DrawRecord> draws;
+static std::vector<std::string> uniform_names;  /* location = index */
+static float uni_P[12], uni_N[12], uni_skirt, uni_corners[4], uni_pixel[2];
+static GLuint bound_texture = 0;
+static bool recording = true;
+
+static void reset_frame() { height_maps.clear(); height_map_ids.clear(); draws.clear(); }
+
+} // namespace fakegl
+
+GLboolean glewExperimental = 0;
+GLenum glewInit() { return GLEW_OK; }
+const unsigned char *glewGetErrorString(GLenum) { return (const unsigned char *)"stub"; }
+
+void glActiveTexture(GLenum) {}
+void glAttachShader(GLuint, GLuint) {}
+void glBindAttribLocation(GLuint, GLuint, const GLchar *) {}
+void glBindBuffer(GLenum, GLuint) {}
+void glBindTexture(GLenum, GLuint t) { fakegl::bound_texture = t; }
+void glBindVertexArray(GLuint) {}
+void glBufferData(GLenum target, GLsizeiptr size, const void *data, GLenum)
+{
+    fakegl::Buffer b; b.target = target;
+    b.bytes.assign((const unsigned char *)data, (const unsigned char *)data + size);
+    fakegl::buffers.push_back(b);
+}
+void glClear(GLbitfield) {}
+void glCompileShader(GLuint) {}
+GLuint glCreateProgram() { return fakegl::next_id++; }
+GLuint glCreateShader(GLenum) { return fakegl::next_id++; }
+void glCullFace(GLenum) {}
+void glDeleteProgram(GLuint) {}
+void glDeleteShader(GLuint) {}
+void glDeleteTextures(GLsizei, const GLuint *) {}
+void glDepthFunc(GLenum) {}
+void glDetachShader(GLuint, GLuint) {}
+void glDrawArrays(GLenum, GLint, GLsizei) {}
+void glDrawElements(GLenum, GLsizei count, GLenum, const void *)
+{
+    if (!fakegl::recording) return;
+    fakegl::DrawRecord d;
+    memcpy(d.P, fakegl::uni_P, sizeof d.P);
+    memcpy(d.N, fakegl::uni_N, sizeof d.N);
+    d.skirt_size = fakegl::uni_skirt;
+    memcpy(d.corners, fakegl::uni_corners, sizeof d.corners);
+    memcpy(d.pixel_size, fakegl::uni_pixel, sizeof d.pixel_size);
+    d.texture = fakegl::bound_texture;
+    d.count = count;
+    fakegl::draws.push_back(d);
+}
+void glEnable(GLenum) {}
+void glEnableVertexAttribArray(GLuint) {}
+void glFrontFace(GLenum) {}
+void glGenBuffers(GLsizei n, GLuint *o) { for (int i = 0; i < n; i++) o[i] = fakegl::next_id++; }
+void glGenTextures(GLsizei n, GLuint *o) { for (int i = 0; i < n; i++) o[i] = fakegl::next_id++; }
+void glGenVertexArrays(GLsizei n, GLuint *o) { for (int i = 0; i < n; i++) o[i] = fakegl::next_id++; }
+GLenum glGetError() { return GL_NO_ERROR; }
+void glGetProgramInfoLog(GLuint, GLsizei, GLsizei *, GLchar *b) { if (b) b[0] = 0; }
+void glGetProgramiv(GLuint, GLenum, GLint *v) { *v = GL_TRUE; }
+void glGetShaderInfoLog(GLuint, GLsizei, GLsizei *, GLchar *b) { if (b) b[0] = 0; }
+void glGetShaderiv(GLuint, GLenum, GLint *v) { *v = GL_TRUE; }
+GLint glGetUniformLocation(GLuint, const GLchar *name)
+{
+    for (size_t i = 0; i < fakegl::uniform_names.size(); i++)
+        if (fakegl::uniform_names[i] == name) return (GLint)i;
+    fakegl::uniform_names.push_back(name);
+    return (GLint)fakegl::uniform_names.size() - 1;
+}
+void glLinkProgram(GLuint) {}
+void glPolygonMode(GLenum, GLenum) {}
+void glShaderSource(GLuint, GLsizei, const GLchar *const *, const GLint *) {}
+void glTexImage2D(GLenum, GLint, GLint, GLsizei w, GLsizei h, GLint, GLenum, GLenum, const void *data)
+{
+    if (!fakegl::recording) return;
+    fakegl::HeightMap m; m.w = w; m.h = h;
+    m.texels.assign((const float *)data, (const float *)data + (size_t)w * h);
+    fakegl::height_maps.push_back(m);
+    fakegl::height_map_ids.push_back(fakegl::bound_texture);
+}
+void glTexParameteri(GLenum, GLenum, GLint) {}
+static const std::string &uname(GLint loc)
+{
+    static const std::string none;
+    return (loc >= 0 && (size_t)loc < fakegl::uniform_names.size()) ? fakegl::uniform_names[loc] : none;
+}
+void glUniform1fv(GLint loc, GLsizei, const GLfloat *v) { if (uname(loc) == "SkirtSize") fakegl::uni_skirt = v[0]; }
+void glUniform1i(GLint, GLint) {}
+void glUniform2fv(GLint loc, GLsizei n, const GLfloat *v)
+{
+    if (uname(loc) == "HeightMap_corners") memcpy(fakegl::uni_corners, v, sizeof(float) * 2 * (n < 2 ? n : 2));
+    if (uname(loc) == "HeightMap_pixel_size") memcpy(fakegl::uni_pixel, v, sizeof(float) * 2);
+}
+void glUniform3fv(GLint loc, GLsizei n, const GLfloat *v)
+{
+    if (uname(loc) == "P") memcpy(fakegl::uni_P, v, sizeof(float) * 3 * (n < 4 ? n : 4));
+    if (uname(loc) == "N") memcpy(fakegl::uni_N, v, sizeof(float) * 3 * (n < 4 ? n : 4));
+}
+void glUniformMatrix4fv(GLint, GLsizei, GLboolean, const GLfloat *) {}
+void glUseProgram(GLuint) {}
+void glVertexAttribPointer(GLuint, GLint, GLenum, GLboolean, GLsizei, const void *) {}
+void glViewport(GLint, GLint, GLsizei, GLsizei) {}
+
+/* ------------------------------------------------------------------------- */
+/* the height functor, constants lifted out (restates main.cpp:823-833)       */
+/* ------------------------------------------------------------------------- */
+enum { ORACLE_RIDGED = 0, ORACLE_FBM = 1, ORACLE_ZERO = 2 };
+
+struct OracleFunctorConfig
+{
+    int kind;            /* main.cpp:829 (ridged) / :830 (fBm, commented out) / :835-841 (zero) */
+    double lacunarity;   /* main.cpp:829: 2.0f widened to the double parameter */
+    float gain;          /* main.cpp:829: 0.55f */
+    int fixed_octaves;   /* <= 0: use main.cpp:827, 6 + 12*depth/max_depth */
+    double coord_scale;  /* main.cpp:828: 0.00001 */
+    float height_scale;  /* main.cpp:831: 8848.0f */
+};
+
+static OracleFunctorConfig g_cfg = { ORACLE_RIDGED, 2.0, 0.55f, 0, 0.00001, 8848.0f };
+
+struct OracleHeight
+{
+    inline float operator()(Vec3d p, int depth, int max_depth)
+    {
+        if (g_cfg.kind == ORACLE_ZERO) return 0.0f;
+        int octaves = (g_cfg.fixed_octaves > 0) ? g_cfg.fixed_octaves
+                                                : 6 + 12 * depth / max_depth;
+        p *= g_cfg.coord_scale;
+        float h = (g_cfg.kind == ORACLE_RIDGED)
+            ? PerlinRidged(p.x, p.y, p.z, g_cfg.lacunarity, g_cfg.gain, octaves)
+            : PerlinfBm(p.x, p.y, p.z, g_cfg.lacunarity, g_cfg.gain, octaves);
+        return h * g_cfg.height_scale;
+    }
+};
+
+static HeightMapGenerator g_gen = CreateHeightMapGenerator<OracleHeight>();
+static Planet g_planet;            /* zero-initialised like main.cpp:846 */
+static bool g_planet_ready = false;
+static size_t g_vertex_buffer = 0, g_index_buffer = 0;
+
+static bool ensure_planet(double radius)
+{
+    if (g_planet_ready && g_planet.radius == radius) return true;
+    size_t first = fakegl::buffers.size();
+    g_planet = Planet{};
+    if (!InitPlanet(g_planet, radius, g_gen)) return false;
+    g_vertex_buffer = first;           /* main.cpp:479 */
+    g_index_buffer = first + 1;        /* main.cpp:480 */
+    g_planet_ready = true;
+    return true;
+}
+
+extern "C" {
+
+/* ---- perlin.h ---- */
+void ref_perlin_tables(unsigned char *table256, float *vectors48)
+{
+    memcpy(table256, perlin_random_table, 256);
+    memcpy(vectors48, perlin_vectors, sizeof(float) * 48);
+}
+int ref_perlin_random(int seed) { return PerlinRandom(seed); }
+float ref_perlin_gradient(float x, float y, float z, int ix, int iy, int iz)
+{
+    return PerlinGradient(x, y, z, ix, iy, iz);
+}
+float ref_perlin_noise3(double x, double y, double z) { return PerlinNoise3(x, y, z); }
+float ref_perlin_fbm(double x, double y, double z, double lac, float gain, int oct)
+{
+    return PerlinfBm(x, y, z, lac, gain, oct);
+}
+float ref_perlin_ridged(double x, double y, double z, double lac, float gain, int oct)
+{
+    return PerlinRidged(x, y, z, lac, gain, oct);
+}
+void ref_noise3_batch(const double *xyz, long n, float *out)
+{
+    for (long i = 0; i < n; i++) out[i] = PerlinNoise3(xyz[3*i], xyz[3*i+1], xyz[3*i+2]);
+}
+void ref_fractal_batch(const double *xyz, long n, int kind, double lac, float gain, int oct, float *out)
+{
+    for (long i = 0; i < n; i++)
+        out[i] = (kind == ORACLE_RIDGED)
+            ? PerlinRidged(xyz[3*i], xyz[3*i+1], xyz[3*i+2], lac, gain, oct)
+            : PerlinfBm(xyz[3*i], xyz[3*i+1], xyz[3*i+2], lac, gain, oct);
+}
+
+/* ---- QuadID (main.cpp:19-65) ---- */
+uint64_t ref_make_root_id(uint64_t root) { return MakeRootID(root).value; }
+uint64_t ref_make_child_id(uint64_t id, uint64_t child) { return MakeChildID(QuadID{id}, child).value; }
+uint64_t ref_get_parent_id(uint64_t id) { return GetParentID(QuadID{id}).value; }
+uint64_t ref_get_root(uint64_t id) { return GetRoot(QuadID{id}); }
+uint64_t ref_get_depth(uint64_t id) { return GetDepth(QuadID{id}); }
+uint64_t ref_get_index(uint64_t id) { return GetIndex(QuadID{id}); }
+uint64_t ref_get_child_index(uint64_t id) { return GetChildIndex(QuadID{id}); }
+int ref_sizeof_quad() { return (int)sizeof(Quad); }
+
+/* ---- height functor seam (main.cpp:107-158) ---- */
+void ref_set_functor(int kind, double lacunarity, float gain, int fixed_octaves,
+                     double coord_scale, float height_scale)
+{
+    g_cfg.kind = kind; g_cfg.lacunarity = lacunarity; g_cfg.gain = gain;
+    g_cfg.fixed_octaves = fixed_octaves; g_cfg.coord_scale = coord_scale;
+    g_cfg.height_scale = height_scale;
+}
+float ref_get_height_at(const double *p, int depth, int max_depth)
+{
+    Vec3d v = V3d(p[0], p[1], p[2]);
+    return g_gen.GetHeightAt(v, depth, max_depth);
+}
+void ref_generate_height_map(float *data, int dim, const void *quad, int max_depth)
+{
+    g_gen.GenerateHeightMap(data, dim, *(const Quad *)quad, max_depth);
+}
+/* the reference is single-threaded; GenerateHeightMap is a pure function of
+ * (quad, dim, max_depth) and read-only tables, so patches are striped over
+ * threads for the all-cores CPU baseline.  nthreads <= 1: the reference as is. */
+void ref_generate_height_maps(const void *quads, long nquads, int dim, int max_depth,
+                              float *out, int nthreads)
+{
+    const Quad *q = (const Quad *)quads;
+    size_t per = (size_t)dim * dim;
+    if (nthreads <= 1) {
+        for (long i = 0; i < nquads; i++) g_gen.GenerateHeightMap(out + i * per, dim, q[i], max_depth);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; t++)
+        pool.emplace_back([=]() {
+            for (long i = t; i < nquads; i += nthreads)
+                g_gen.GenerateHeightMap(out + i * per, dim, q[i], max_depth);
+        });
+    for (auto &th : pool) th.join();
+}
+
+/* ---- InitPlanet: patch vertex grid + strip index buffer (main.cpp:391-501) ---- */
+int ref_init_planet(double radius, int *max_lod, float *max_skirt_size)
+{
+    if (!ensure_planet(radius)) return 0;
+    if (max_lod) *max_lod = g_planet.max_lod;
+    if (max_skirt_size) *max_skirt_size = g_planet.max_skirt_size;
+    return 1;
+}
+long ref_patch_buffer(int which, void *out, long cap)
+{
+    if (!g_planet_ready) return -1;
+    const std::vector<unsigned char> &b = fakegl::buffers[which ? g_index_buffer : g_vertex_buffer].bytes;
+    if (out && cap >= (long)b.size()) memcpy(out, b.data(), b.size());
+    return (long)b.size();
+}
+
+/* ---- subdivision geometry through the reference's own ProcessQuad ---- */
+/* Root quads: RenderPlanet builds them (main.cpp:604-624) and hands each to
+ * ProcessQuad with lod = planet.max_lod; with max_lod forced to 0 ProcessQuad
+ * appends them unsplit (main.cpp:539-544). */
+int ref_root_quads(double radius, void *out6)
+{
+    if (!ensure_planet(radius)) return 0;
+    OracleFunctorConfig saved = g_cfg; g_cfg.kind = ORACLE_ZERO;
+    int saved_lod = g_planet.max_lod; g_planet.max_lod = 0;
+    fakegl::recording = false;
+    CameraInfo cam = {}; cam.rotation = Mat3Identity();
+    InitCameraInfo(cam, DegToRad(50.0f), 800.0f / 600.0f, 1.0f, 20000000.0f);
+    RenderPlanet(g_planet, cam);
+    fakegl::recording = true;
+    g_planet.max_lod = saved_lod; g_cfg = saved;
+    if (g_planet.quads.num != 6) return 0;
+    memcpy(out6, g_planet.quads.data, 6 * sizeof(Quad));
+    return 6;
+}
+/* One split: ProcessQuad(q, cam, lod = 1) with the camera sitting exactly on
+ * corner 0 (zero-height functor, so p[0] == q.p[0] and the distance test at
+ * main.cpp:566-573 fires); the four children come back with lod 0 and are
+ * appended in child order 0..3 (main.cpp:589-592). */
+int ref_split_quad(double radius, const void *quad, void *out4)
+{
+    if (!ensure_planet(radius)) return 0;
+    const Quad &q = *(const Quad *)quad;
+    OracleFunctorConfig saved = g_cfg; g_cfg.kind = ORACLE_ZERO;
+    CameraInfo cam = {}; cam.position = q.p[0];
+    ListResize(g_planet.quads, 0);
+    ProcessQuad(g_planet, q, cam, 1);
+    g_cfg = saved;
+    if (g_planet.quads.num != 4) return 0;
+    memcpy(out4, g_planet.quads.data, 4 * sizeof(Quad));
+    return 4;
+}
+/* all quads of one root face at uniform depth, in the recursion (= QuadID path) order
+ * ProcessQuad would emit them */
+static void uniform_rec(double radius, const Quad &q, int levels, Quad *out, long &n)
+{
+    if (levels == 0) { out[n++] = q; return; }
+    Quad kids[4];
+    ref_split_quad(radius, &q, kids);
+    for (int c = 0; c < 4; c++) uniform_rec(radius, kids[c], levels - 1, out, n);
+}
+long ref_uniform_quads(double radius, int face, int depth, void *out)
+{
+    Quad roots[6];
+    if (!ref_root_quads(radius, roots)) return 0;
+    long n = 0;
+    uniform_rec(radius, roots[face], depth, (Quad *)out, n);
+    return n;
+}
+
+/* ---- one frame of RenderPlanet with our planet + the configurable functor ---- */
+long ref_render_frame(double radius, const double *cam_pos)
+{
+    if (!ensure_planet(radius)) return -1;
+    fakegl::reset_frame();
+    g_planet.cache = HeightMapCache{};   /* cold cache: every leaf generates */
+    CameraInfo cam = {};
+    cam.position = V3d(cam_pos[0], cam_pos[1], cam_pos[2]);
+    cam.rotation = Mat3Identity();
+    InitCameraInfo(cam, DegToRad(50.0f), 800.0f / 600.0f, 1.0f, 20000000.0f);
+    RenderPlanet(g_planet, cam);
+    return g_planet.quads.num;
+}
+long ref_frame_quads(void *out, long cap)
+{
+    long n = g_planet.quads.num;
+    if (out && cap >= n) memcpy(out, g_planet.quads.data, n * sizeof(Quad));
+    return n;
+}
+
+/* ---- the reference's real main(), one headless frame ---- */
+int ref_run_reference_main(const char *scratch_dir)
+{
+    /* main() reads/writes a file called "save" in the cwd (main.cpp:869-888,1118-1138) */
+    if (scratch_dir && chdir(scratch_dir) != 0) return -1;
+    fakegl::reset_frame();
+    return planet_reference_main(0, nullptr);
+}
+
+/* ---- what the fake GL recorded during the last frame ---- */
+long ref_captured_height_map_count() { return (long)fakegl::height_maps.size(); }
+int ref_captured_height_map(long i, float *out, int *w, int *h)
+{
+    if (i < 0 || i >= (long)fakegl::height_maps.size()) return 0;
+    const fakegl::HeightMap &m = fakegl::height_maps[i];
+    if (w) *w = m.w; if (h) *h = m.h;
+    if (out) memcpy(out, m.texels.data(), m.texels.size() * sizeof(float));
+    return 1;
+}
+long ref_captured_draw_count() { return (long)fakegl::draws.size(); }
+/* 32 floats per draw: P[12] N[12] skirt corners[4] pixel_size[2] count */
+int ref_captured_draw(long i, float *out32)
+{
+    if (i < 0 || i >= (long)fakegl::draws.size()) return 0;
+    const fakegl::DrawRecord &d = fakegl::draws[i];
+    memcpy(out32, d.P, 48); memcpy(out32 + 12, d.N, 48);
+    out32[24] = d.skirt_size; memcpy(out32 + 25, d.corners, 16); memcpy(out32 + 29, d.pixel_size, 8);
+    out32[31] = (float)d.count;
+    return 1;
+}
+long ref_captured_buffer_count() { return (long)fakegl::buffers.size(); }
+long ref_captured_buffer(long i, void *out, long cap)
+{
+    if (i < 0 || i >= (long)fakegl::buffers.size()) return -1;
+    const std::vector<unsigned char> &b = fakegl::buffers[i].bytes;
+    if (out && cap >= (long)b.size()) memcpy(out, b.data(), b.size());
+    return (long)b.size();
+}
+
+} /* extern "C" */
