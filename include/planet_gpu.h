@@ -1,0 +1,173 @@
+/* planet_gpu.h -- C-ABI of the B200 terrain hot path of pgcomp/planet.
+ *
+ * Drop-in boundary: the reference's only indirection on this
+ * path is
+ *
+ *     struct HeightMapGenerator {                       // main.cpp:107-111
+ *         float (*GetHeightAt)(const Vec3d &, int, int);
+ *         void  (*GenerateHeightMap)(float *, int, const Quad &, int);
+ *     };
+ *
+ * installed by InitPlanet (main.cpp:280, 495) and called from GetHeightMapForQuad
+ * (main.cpp:244) and ProcessQuad (main.cpp:552, 555).  On the SysV/Itanium ABI a
+ * `const T &` parameter is passed as `const T *`, so planet_gpu_get_height_at and
+ * planet_gpu_generate_height_map below are assignable to those two members (see
+ * INTEGRATION.md and planet_b200/host/planet_host.h for the binding).
+ *
+ * Everything else here is the batched, stream-ordered form of the same
+ * computations (device pointers, caller-owned memory, nothing retained), which
+ * the single-threaded reference lacks.  Plain C types only: no CUDA, torch or
+ * C++ types appear in any signature; `stream` is a cudaStream_t passed as void*
+ * (NULL = the legacy default stream).
+ *
+ * Errors: every entry point that can fail returns 0 on success or a negative
+ * PLANET_E_* code and records a message retrievable with
+ * planet_gpu_last_error().  The two legacy-shaped entry points cannot return a
+ * status (reference signatures); on failure they log "[ERROR] ..." to stderr
+ * (logging.h:7 convention) and produce NaN.  There is NO CPU fallback anywhere:
+ * without a usable CUDA device every compute call fails.
+ */
+#ifndef PLANET_GPU_H
+#define PLANET_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLANET_GPU_ABI_VERSION 1
+
+enum {
+    PLANET_OK = 0,
+    PLANET_E_NO_DEVICE = -1,      /* no CUDA device / driver */
+    PLANET_E_INVALID = -2,        /* precondition violated (dim <= 3, max_depth == 0, depth >= 32, ...) */
+    PLANET_E_CUDA = -3,           /* a CUDA runtime call failed; see planet_gpu_last_error() */
+    PLANET_E_UNSUPPORTED = -4     /* valid in the reference but outside what this build handles */
+};
+
+/* noise kinds: main.cpp:829 (ridged, the reference default), :830 (fBm), :835-841 (ConstantZero) */
+enum { PLANET_NOISE_RIDGED = 0, PLANET_NOISE_FBM = 1, PLANET_NOISE_ZERO = 2 };
+
+/* arithmetic modes of the noise kernel */
+enum {
+    /* bit-exact: fp64 lattice split, fp64 fade, unfused fp32 -- every rounding of
+     * perlin.h:50-88 / main.cpp:689-734 reproduced (IEEE _rn intrinsics, no FMA) */
+    PLANET_PRECISION_EXACT = 0,
+    /* throughput: 64-bit fixed-point lattice split (exact for lacunarity 2.0), fp32
+     * fade with FMA; |dh| <= 1e-5 * height_scale * sum(gain^k) (tests state it) */
+    PLANET_PRECISION_FAST = 1
+};
+
+/* The reference's compile-time constants on this path, as data. */
+typedef struct planet_gpu_params {
+    double radius;          /* main.cpp:821  6371000.0 */
+    int32_t patch_verts;    /* main.cpp:391  30 (height map dim = patch_verts + 2, main.cpp:194) */
+    int32_t noise_kind;     /* PLANET_NOISE_* */
+    double lacunarity;      /* main.cpp:829  2.0f widened to double */
+    float gain;             /* main.cpp:829  0.55f */
+    int32_t fixed_octaves;  /* <= 0: main.cpp:827, 6 + 12*depth/max_depth */
+    double coord_scale;     /* main.cpp:828  0.00001 */
+    float height_scale;     /* main.cpp:831  8848.0f */
+    int32_t precision;      /* PLANET_PRECISION_* */
+    double seed_offset[3];  /* added to the scaled coordinate; {0,0,0} == the reference */
+} planet_gpu_params;
+
+/* main.cpp:68-72: struct Quad { Vec3d p[4]; QuadID id; } -- 104 bytes, same layout */
+typedef struct planet_gpu_quad {
+    double p[4][3];
+    uint64_t id;
+} planet_gpu_quad;
+
+/* ---- lifecycle ------------------------------------------------------------------- */
+int  planet_gpu_abi_version(void);
+void planet_gpu_default_params(planet_gpu_params *out);      /* the reference's defaults, EXACT mode */
+int  planet_gpu_init(int device);                            /* selects the device, uploads tables */
+void planet_gpu_shutdown(void);
+const char *planet_gpu_last_error(void);
+/* name, SM count, boost clock (kHz) and FP32 lanes/SM of the active device: the
+ * denominators bench.py prints beside every roofline fraction */
+int  planet_gpu_device_info(char *name, int name_cap, int *sm_count, int *clock_khz, int *fp32_lanes_per_sm);
+
+/* ---- the reference-shaped seam (main.cpp:107-111) ----------------------------------- */
+/* parameters used by the two legacy-shaped calls below (they have no params argument) */
+int   planet_gpu_set_params(const planet_gpu_params *p);
+/* replaces Gen::GetHeightAt, main.cpp:118-121.  Host pointer; synchronous. */
+float planet_gpu_get_height_at(const double *p, int depth, int max_depth);
+/* replaces Gen::GenerateHeightMap, main.cpp:123-151.  `data` is a caller-owned HOST
+ * buffer of dim*dim floats, fully overwritten, row-major data[y*dim+x]; `quad` points
+ * to a reference-layout Quad (104 bytes).  Synchronous: H2D quad, kernel, D2H heights. */
+void  planet_gpu_generate_height_map(float *data, int dim, const void *quad, int max_depth);
+
+/* ---- batched device API (all pointers are DEVICE pointers, work is stream-ordered) --- */
+/* K2: nquads height maps of dim*dim floats each, out[q*dim*dim + y*dim + x]
+ * (main.cpp:123-151 applied to every quad). */
+int planet_gpu_generate_height_maps(const planet_gpu_params *p, const planet_gpu_quad *d_quads,
+                                    int64_t nquads, int dim, int max_depth, float *d_out,
+                                    void *stream);
+/* batched Gen::GetHeightAt (main.cpp:118-121): n points (xyz doubles), one (depth, max_depth) */
+int planet_gpu_heights_at(const planet_gpu_params *p, const double *d_xyz, int64_t n, int depth,
+                          int max_depth, float *d_out, void *stream);
+/* perlin.h:50-88 / main.cpp:689-734 on n points; kind PLANET_NOISE_FBM or _RIDGED, or
+ * octaves == 0 for a single PerlinNoise3 evaluation.  precision as in params. */
+int planet_gpu_noise(const double *d_xyz, int64_t n, int kind, double lacunarity, float gain,
+                     int octaves, int precision, float *d_out, void *stream);
+
+/* K1: subdivision geometry.  Quads of `nquads` leaves starting at leaf `first` of the
+ * uniform depth-`depth` tree over all six root faces, in the order the reference's
+ * recursion emits them (face-major, then child 0..3 depth-first; main.cpp:589-592,
+ * 619-624).  Corners are bit-identical to the reference's midpoint rule
+ * (main.cpp:546-547, 581-594).  d_indices (may be NULL) receives the triangle-strip
+ * index buffer of main.cpp:427-474 for every quad, rebased to a merged vertex buffer:
+ * d_indices[q*ni + k] = q*nv + strip[k], nv = n*n + 4n, ni = 2n*n + 8n - 4. */
+int planet_gpu_tessellate_uniform(const planet_gpu_params *p, int depth, int64_t first,
+                                  int64_t nquads, planet_gpu_quad *d_quads, uint32_t *d_indices,
+                                  void *stream);
+/* corners of arbitrary quads from their QuadIDs (main.cpp:19-65 encoding) */
+int planet_gpu_quads_from_ids(const planet_gpu_params *p, const uint64_t *d_ids, int64_t n,
+                              planet_gpu_quad *d_quads, void *stream);
+/* the reference's static patch mesh (main.cpp:402-474): nv (u,v,skirt) float triples and
+ * ni uint32 strip indices; either pointer may be NULL */
+int planet_gpu_patch_mesh(int patch_verts, float *d_vertices, uint32_t *d_indices, void *stream);
+int planet_gpu_patch_vertex_count(int patch_verts);   /* n*n + 4n          (main.cpp:393-394) */
+int planet_gpu_patch_index_count(int patch_verts);    /* 2n*n + 8n - 4     (main.cpp:395-400) */
+/* host-side integer closed forms the kernels use (no device needed):
+ *   strip index k of the patch index buffer, main.cpp:427-474;
+ *   QuadID of leaf `leaf` of the uniform depth-`depth` tree in emission order */
+uint32_t planet_gpu_strip_index(int k, int patch_verts);
+uint64_t planet_gpu_uniform_leaf_id(int64_t leaf, int depth);
+int   planet_gpu_max_lod(double radius, int patch_verts);          /* main.cpp:497 */
+float planet_gpu_max_skirt_size(double radius, int patch_verts);   /* main.cpp:500 */
+
+/* K3: the GLSL stage (main.cpp:286-380) for every vertex of every quad, in the patch
+ * vertex order of main.cpp:406-422.  d_heights holds the quads' own height maps
+ * (dim = patch_verts + 2).  Outputs, nv float4 per quad:
+ *   d_pos4 = (v.p + v.n*height, height)           position relative to cam_pos
+ *   d_nrm4 = (Normal, sqrt(0.001 + max(0, N.l)))  world normal + Lambert term
+ * skirt size per quad follows main.cpp:674-677 from max_skirt (pass a negative value
+ * to use planet_gpu_max_skirt_size).  Either output may be NULL. */
+int planet_gpu_shade(const planet_gpu_params *p, const planet_gpu_quad *d_quads, int64_t nquads,
+                     const double *cam_pos /* host, 3 doubles */, const float *d_heights,
+                     float max_skirt, float *d_pos4, float *d_nrm4, void *stream);
+
+/* ---- host-buffer convenience (what a reference-side caller with host memory uses) ---- */
+/* batched GenerateHeightMap with HOST quads and HOST output: H2D quads, K2, D2H heights;
+ * returns after the data is in h_out.  d_mirror (DEVICE pointer, may be NULL) additionally
+ * keeps the height maps resident on the device -- the role the GL texture plays after
+ * main.cpp:245 -- so K3 can consume them without a second upload. */
+int planet_gpu_generate_height_maps_host(const planet_gpu_params *p, const planet_gpu_quad *h_quads,
+                                         int64_t nquads, int dim, int max_depth, float *h_out,
+                                         float *d_mirror);
+
+/* ---- measurement helpers ------------------------------------------------------------- */
+/* dependent-free FFMA loop on every SM for about `ms` milliseconds; returns achieved
+ * FP32 TFLOP/s (2 flop per FFMA) and the elapsed device time; the FP32 roofline
+ * denominator measured on this device under this kernel's own power/clock regime */
+int planet_gpu_measure_fp32_peak(double ms, double *tflops, double *elapsed_ms);
+/* number of kernels this library has launched since planet_gpu_init (bench.py's gpu_launches) */
+int64_t planet_gpu_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLANET_GPU_H */

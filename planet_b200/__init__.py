@@ -1,0 +1,278 @@
+"""planet_b200 -- B200-native terrain hot path of pgcomp/planet behind a C-ABI.
+
+The product is ``libplanet_gpu.so`` (hand-written sm_100a CUDA, include/planet_gpu.h).
+This module is the thin Python host layer the tests and bench.py use: a ctypes binding
+with the reference's vocabulary (quads, height maps, patches).  PyTorch appears only as
+plumbing -- device memory, streams, torch.distributed -- never as the compute path, and
+there is no CPU fallback: if the library or a GPU is missing, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+RIDGED, FBM, ZERO = 0, 1, 2            # PLANET_NOISE_*
+EXACT, FAST = 0, 1                     # PLANET_PRECISION_*
+RADIUS = 6371000.0                     # main.cpp:821
+
+QUAD_DTYPE = np.dtype([("p", np.float64, (4, 3)), ("id", np.uint64)])   # main.cpp:68-72, 104 B
+QUAD_WORDS = 13                        # a Quad as 13 x 8-byte words (torch side: int64[n, 13])
+
+
+class PlanetGpuError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    """planet_gpu_params (include/planet_gpu.h) -- the reference's constants, SURVEY App. D."""
+    _fields_ = [("radius", C.c_double), ("patch_verts", C.c_int32), ("noise_kind", C.c_int32),
+                ("lacunarity", C.c_double), ("gain", C.c_float), ("fixed_octaves", C.c_int32),
+                ("coord_scale", C.c_double), ("height_scale", C.c_float), ("precision", C.c_int32),
+                ("seed_offset", C.c_double * 3)]
+
+
+_lib = None
+
+
+def lib():
+    """Load (building if needed) the C-ABI library.  Raises if it cannot be built/loaded."""
+    global _lib
+    if _lib is None:
+        so = _build.build()
+        L = C.CDLL(so)
+        i, i64, f, d, vp = C.c_int, C.c_int64, C.c_float, C.c_double, C.c_void_p
+        pp = C.POINTER(Params)
+        sig = {
+            "planet_gpu_abi_version": (i, []),
+            "planet_gpu_default_params": (None, [pp]),
+            "planet_gpu_init": (i, [i]),
+            "planet_gpu_shutdown": (None, []),
+            "planet_gpu_last_error": (C.c_char_p, []),
+            "planet_gpu_device_info": (i, [C.c_char_p, i, C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
+            "planet_gpu_set_params": (i, [pp]),
+            "planet_gpu_get_height_at": (f, [vp, i, i]),
+            "planet_gpu_generate_height_map": (None, [vp, i, vp, i]),
+            "planet_gpu_generate_height_maps": (i, [pp, vp, i64, i, i, vp, vp]),
+            "planet_gpu_heights_at": (i, [pp, vp, i64, i, i, vp, vp]),
+            "planet_gpu_noise": (i, [vp, i64, i, d, f, i, i, vp, vp]),
+            "planet_gpu_tessellate_uniform": (i, [pp, i, i64, i64, vp, vp, vp]),
+            "planet_gpu_quads_from_ids": (i, [pp, vp, i64, vp, vp]),
+            "planet_gpu_patch_mesh": (i, [i, vp, vp, vp]),
+            "planet_gpu_patch_vertex_count": (i, [i]),
+            "planet_gpu_patch_index_count": (i, [i]),
+            "planet_gpu_strip_index": (C.c_uint32, [i, i]),
+            "planet_gpu_uniform_leaf_id": (C.c_uint64, [i64, i]),
+            "planet_gpu_max_lod": (i, [d, i]),
+            "planet_gpu_max_skirt_size": (f, [d, i]),
+            "planet_gpu_shade": (i, [pp, vp, i64, vp, vp, f, vp, vp, vp]),
+            "planet_gpu_generate_height_maps_host": (i, [pp, vp, i64, i, i, vp, vp]),
+            "planet_gpu_measure_fp32_peak": (i, [d, C.POINTER(d), C.POINTER(d)]),
+            "planet_gpu_launch_count": (i64, []),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)            # AttributeError here == header/library mismatch
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+EXPORTED_SYMBOLS = [
+    "planet_gpu_abi_version", "planet_gpu_default_params", "planet_gpu_init", "planet_gpu_shutdown",
+    "planet_gpu_last_error", "planet_gpu_device_info", "planet_gpu_set_params",
+    "planet_gpu_get_height_at", "planet_gpu_generate_height_map", "planet_gpu_generate_height_maps",
+    "planet_gpu_heights_at", "planet_gpu_noise", "planet_gpu_tessellate_uniform",
+    "planet_gpu_quads_from_ids", "planet_gpu_patch_mesh", "planet_gpu_patch_vertex_count",
+    "planet_gpu_patch_index_count", "planet_gpu_strip_index", "planet_gpu_uniform_leaf_id",
+    "planet_gpu_max_lod", "planet_gpu_max_skirt_size",
+    "planet_gpu_shade", "planet_gpu_generate_height_maps_host", "planet_gpu_measure_fp32_peak",
+    "planet_gpu_launch_count",
+]
+
+
+def _check(rc):
+    if rc != 0:
+        raise PlanetGpuError(f"planet_gpu error {rc}: {lib().planet_gpu_last_error().decode()}")
+
+
+def default_params(**over):
+    """The reference's defaults (ridged, gain 0.55, octaves 6+12*depth/max_depth, EXACT)."""
+    p = Params()
+    lib().planet_gpu_default_params(C.byref(p))
+    for k, v in over.items():
+        if k == "seed_offset":
+            p.seed_offset = (C.c_double * 3)(*v)
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def fbm_params(octaves=8, gain=0.5, precision=FAST, **over):
+    """BASELINE.json configs 2-5: fBm, fixed octave count, gain 0.5."""
+    return default_params(noise_kind=FBM, gain=gain, fixed_octaves=octaves, precision=precision, **over)
+
+
+def init(device=0):
+    _check(lib().planet_gpu_init(int(device)))
+
+
+def patch_vertex_count(n=30): return lib().planet_gpu_patch_vertex_count(n)
+def patch_index_count(n=30): return lib().planet_gpu_patch_index_count(n)
+def max_lod(radius=RADIUS, n=30): return lib().planet_gpu_max_lod(radius, n)
+def max_skirt_size(radius=RADIUS, n=30): return lib().planet_gpu_max_skirt_size(radius, n)
+def launch_count(): return lib().planet_gpu_launch_count()
+
+
+def device_info():
+    name = C.create_string_buffer(128)
+    sm, khz, lanes = C.c_int(), C.c_int(), C.c_int()
+    _check(lib().planet_gpu_device_info(name, 128, C.byref(sm), C.byref(khz), C.byref(lanes)))
+    return {"name": name.value.decode(), "sm_count": sm.value, "clock_khz": khz.value,
+            "fp32_lanes_per_sm": lanes.value}
+
+
+def measure_fp32_peak(ms=200.0):
+    tf, el = C.c_double(), C.c_double()
+    _check(lib().planet_gpu_measure_fp32_peak(ms, C.byref(tf), C.byref(el)))
+    return tf.value, el.value
+
+
+# ---- torch plumbing -----------------------------------------------------------------------
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise PlanetGpuError("no CUDA device: planet_b200 has no CPU path")
+    return torch
+
+
+def _stream(stream=None):
+    torch = _torch()
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def quads_to_device(quads, device="cuda"):
+    """numpy structured quads (QUAD_DTYPE) -> int64[n, 13] device tensor (same bytes)."""
+    torch = _torch()
+    q = np.ascontiguousarray(quads, QUAD_DTYPE)
+    return torch.from_numpy(q.view(np.int64).reshape(-1, QUAD_WORDS).copy()).to(device)
+
+
+def quads_to_host(t):
+    return t.detach().cpu().numpy().reshape(-1).view(QUAD_DTYPE)
+
+
+def tessellate_uniform(depth, first=0, nquads=None, params=None, with_indices=False, stream=None):
+    """K1: quads [first, first+nquads) of the uniform depth-`depth` tree (+ merged strip indices)."""
+    torch = _torch()
+    params = params or default_params()
+    if nquads is None:
+        nquads = 6 * 4 ** depth - first
+    quads = torch.empty((nquads, QUAD_WORDS), dtype=torch.int64, device="cuda")
+    idx = None
+    if with_indices:
+        idx = torch.empty(nquads * patch_index_count(params.patch_verts), dtype=torch.int32, device="cuda")
+    _check(lib().planet_gpu_tessellate_uniform(C.byref(params), depth, first, nquads, quads.data_ptr(),
+                                               idx.data_ptr() if idx is not None else None, _stream(stream)))
+    return (quads, idx) if with_indices else quads
+
+
+def quads_from_ids(ids, params=None, stream=None):
+    torch = _torch()
+    params = params or default_params()
+    ids = ids if hasattr(ids, "data_ptr") else torch.from_numpy(np.ascontiguousarray(ids, np.uint64).view(np.int64)).cuda()
+    out = torch.empty((ids.numel(), QUAD_WORDS), dtype=torch.int64, device="cuda")
+    _check(lib().planet_gpu_quads_from_ids(C.byref(params), ids.data_ptr(), ids.numel(), out.data_ptr(), _stream(stream)))
+    return out
+
+
+def patch_mesh(n=30, stream=None):
+    torch = _torch()
+    v = torch.empty((patch_vertex_count(n), 3), dtype=torch.float32, device="cuda")
+    i = torch.empty(patch_index_count(n), dtype=torch.int32, device="cuda")
+    _check(lib().planet_gpu_patch_mesh(n, v.data_ptr(), i.data_ptr(), _stream(stream)))
+    return v, i
+
+
+def generate_height_maps(quads, dim, max_depth, params=None, out=None, stream=None):
+    """K2: batched GenerateHeightMap (main.cpp:123-151).  quads: int64[n,13] device tensor."""
+    torch = _torch()
+    params = params or default_params()
+    n = quads.shape[0]
+    if out is None:
+        out = torch.empty((n, dim, dim), dtype=torch.float32, device="cuda")
+    _check(lib().planet_gpu_generate_height_maps(C.byref(params), quads.data_ptr(), n, dim, max_depth,
+                                                 out.data_ptr(), _stream(stream)))
+    return out
+
+
+def heights_at(points, depth, max_depth, params=None, stream=None):
+    """Batched GetHeightAt (main.cpp:118-121).  points: float64[n,3] device tensor."""
+    torch = _torch()
+    params = params or default_params()
+    n = points.shape[0]
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    _check(lib().planet_gpu_heights_at(C.byref(params), points.data_ptr(), n, depth, max_depth,
+                                       out.data_ptr(), _stream(stream)))
+    return out
+
+
+def noise(points, kind=FBM, lacunarity=2.0, gain=0.5, octaves=0, precision=EXACT, stream=None):
+    """PerlinNoise3 (octaves=0) / PerlinfBm / PerlinRidged on float64[n,3] device points."""
+    torch = _torch()
+    n = points.shape[0]
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    _check(lib().planet_gpu_noise(points.data_ptr(), n, kind, lacunarity, gain, octaves, precision,
+                                  out.data_ptr(), _stream(stream)))
+    return out
+
+
+def shade(quads, heights, cam_pos, params=None, max_skirt=-1.0, want_pos=True, want_nrm=True,
+          pos=None, nrm=None, stream=None):
+    """K3: displaced positions + normals/Lambert for every patch vertex (main.cpp:286-380)."""
+    torch = _torch()
+    params = params or default_params()
+    n = quads.shape[0]
+    nv = patch_vertex_count(params.patch_verts)
+    if want_pos and pos is None:
+        pos = torch.empty((n, nv, 4), dtype=torch.float32, device="cuda")
+    if want_nrm and nrm is None:
+        nrm = torch.empty((n, nv, 4), dtype=torch.float32, device="cuda")
+    cam = (C.c_double * 3)(*[float(c) for c in cam_pos])
+    _check(lib().planet_gpu_shade(C.byref(params), quads.data_ptr(), n, cam, heights.data_ptr(), max_skirt,
+                                  pos.data_ptr() if pos is not None else None,
+                                  nrm.data_ptr() if nrm is not None else None, _stream(stream)))
+    return pos, nrm
+
+
+# ---- host-buffer entry points (the reference-facing calls) ----------------------------------
+def generate_height_maps_host(quads_np, dim, max_depth, params=None, out=None, mirror=None):
+    """Host quads in, host height maps out: H2D + K2 + D2H inside the call.  `mirror`: optional
+    device tensor that also keeps the maps resident (the GL texture's role, main.cpp:245)."""
+    params = params or default_params()
+    q = np.ascontiguousarray(quads_np, QUAD_DTYPE)
+    if out is None:
+        out = np.empty((len(q), dim, dim), np.float32)
+    _check(lib().planet_gpu_generate_height_maps_host(C.byref(params), q.ctypes.data, len(q), dim, max_depth,
+                                                      out.ctypes.data,
+                                                      mirror.data_ptr() if mirror is not None else None))
+    return out
+
+
+def set_params(params):
+    _check(lib().planet_gpu_set_params(C.byref(params)))
+
+
+def generate_height_map(quad_np, dim, max_depth):
+    """The reference-shaped call: void GenerateHeightMap(float*, int, const Quad&, int)."""
+    q = np.ascontiguousarray(quad_np, QUAD_DTYPE).reshape(1)
+    out = np.empty((dim, dim), np.float32)
+    lib().planet_gpu_generate_height_map(out.ctypes.data, dim, q.ctypes.data, max_depth)
+    return out
+
+
+def get_height_at(p, depth, max_depth):
+    """The reference-shaped call: float GetHeightAt(const Vec3d&, int, int)."""
+    v = np.ascontiguousarray(p, np.float64)
+    return lib().planet_gpu_get_height_at(v.ctypes.data, depth, max_depth)

@@ -1,0 +1,279 @@
+// k1_tessellate.cu -- K1: subdivision geometry and index buffers, written straight to HBM.
+//
+// Replaces the serial CPU code of the reference:
+//   root faces            RenderPlanet,  main.cpp:604-624
+//   child split           ProcessQuad,   main.cpp:546-547, 581-594
+//   QuadID arithmetic                    main.cpp:19-65
+//   patch vertex grid     InitPlanet,    main.cpp:402-425
+//   strip index buffer    InitPlanet,    main.cpp:427-474
+//
+// The reference reaches a leaf by recursion from its root face; every leaf's corners are
+// a pure function of its QuadID, so here one thread walks one id from the root (depth
+// <= 27 levels of 5 normalisations) with the reference's exact fp64 operation order
+// (IEEE add/mul/div/sqrt, no FMA) -- corners come out bit-identical, and shared edges of
+// neighbouring quads stay bit-identical too because both sides compute Normalize(a+b).
+// The strip index buffer is produced in closed form per output slot (the reference's
+// loop has asymmetric cursor resets), one coalesced 4-byte store per
+// thread, rebased per quad so that all patches index one merged vertex buffer.
+#include "planet_common.cuh"
+
+#include <algorithm>
+
+namespace planet {
+
+// main.cpp:604-624: corner signs of the cube, and the six faces.  QUAD(a,b,c,d) stores
+// {v[a], v[b], v[d], v[c]} (main.cpp:605), applied here to the face table directly.
+__constant__ signed char c_cube[8][3] = {
+    {-1, -1, -1}, { 1, -1, -1}, { 1,  1, -1}, {-1,  1, -1},
+    {-1, -1,  1}, { 1, -1,  1}, { 1,  1,  1}, {-1,  1,  1}
+};
+__constant__ unsigned char c_face[6][4] = {      // stored order p[0], p[1], p[2], p[3]
+    {0, 1, 3, 2}, {1, 5, 2, 6}, {5, 4, 6, 7}, {4, 0, 7, 3}, {3, 2, 7, 6}, {4, 5, 0, 1}
+};
+
+__device__ __forceinline__ d3 cube_corner(int i, double radius)
+{
+    d3 v = { (double)c_cube[i][0], (double)c_cube[i][1], (double)c_cube[i][2] };
+    return exact::mul(exact::normalize(v), radius);                   // main.cpp:607
+}
+
+// descend from the root face along the id's path; child order main.cpp:589-592
+__device__ Quad quad_from_id(uint64_t id, double radius)
+{
+    Quad q;
+    const int root = (int)quad_root(id);
+    const int depth = (int)quad_depth(id);
+#pragma unroll
+    for (int j = 0; j < 4; j++) q.p[j] = cube_corner(c_face[root][j], radius);
+    for (int l = 0; l < depth; l++) {
+        const int child = (int)((id >> (2 * l)) & 3);
+        // main.cpp:546-547: centre; :581 VERT(i,j) = Normalize(p[i]+p[j]) * radius
+        d3 s = exact::add(exact::add(exact::add(q.p[0], q.p[1]), q.p[2]), q.p[3]);
+        d3 mid = exact::mul(exact::normalize(s), radius);
+        // 3x3 grid g0..g8 = p0, V(0,1), p1, V(0,2), mid, V(1,3), p2, V(2,3), p3; child c takes
+        // (0,1,3,4) (1,2,4,5) (3,4,6,7) (4,5,7,8): only the two midpoints it touches are needed
+        d3 n0, n1, n2, n3;
+        if (child == 0) {
+            n0 = q.p[0];
+            n1 = exact::mul(exact::normalize(exact::add(q.p[0], q.p[1])), radius);
+            n2 = exact::mul(exact::normalize(exact::add(q.p[0], q.p[2])), radius);
+            n3 = mid;
+        } else if (child == 1) {
+            n0 = exact::mul(exact::normalize(exact::add(q.p[0], q.p[1])), radius);
+            n1 = q.p[1];
+            n2 = mid;
+            n3 = exact::mul(exact::normalize(exact::add(q.p[1], q.p[3])), radius);
+        } else if (child == 2) {
+            n0 = exact::mul(exact::normalize(exact::add(q.p[0], q.p[2])), radius);
+            n1 = mid;
+            n2 = q.p[2];
+            n3 = exact::mul(exact::normalize(exact::add(q.p[2], q.p[3])), radius);
+        } else {
+            n0 = mid;
+            n1 = exact::mul(exact::normalize(exact::add(q.p[1], q.p[3])), radius);
+            n2 = exact::mul(exact::normalize(exact::add(q.p[2], q.p[3])), radius);
+            n3 = q.p[3];
+        }
+        q.p[0] = n0; q.p[1] = n1; q.p[2] = n2; q.p[3] = n3;
+    }
+    q.id = id;
+    return q;
+}
+
+// id of leaf `leaf` (0 .. 6*4^depth - 1) in the reference's emission order: face-major,
+// then depth-first with child 0..3 -- the first split is the most significant base-4
+// digit of the in-face index, and QuadID stores level l's child at bits 2(l-1).
+__host__ __device__ inline uint64_t uniform_leaf_id(int64_t leaf, int depth)
+{
+    const int64_t per_face = (int64_t)1 << (2 * depth);
+    const uint64_t face = (uint64_t)(leaf / per_face);
+    uint64_t j = (uint64_t)(leaf - (int64_t)face * per_face);
+    uint64_t path = 0;
+    for (int l = 0; l < depth; l++) {
+        uint64_t digit = (j >> (2 * (depth - 1 - l))) & 3;
+        path |= digit << (2 * l);
+    }
+    return (1ull << 63) | (face << 60) | ((uint64_t)depth << 55) | path;
+}
+
+// one Quad is 13 8-byte words; 13 consecutive threads each write one word of a quad so
+// the 104-byte records leave the SM as coalesced 8-byte stores.
+__device__ __forceinline__ void store_quad(Quad *dst, const Quad &q)
+{
+    *dst = q;
+}
+
+__global__ void __launch_bounds__(128)
+k_quads_uniform(int depth, int64_t first, int64_t n, double radius, Quad *__restrict__ out)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        store_quad(out + i, quad_from_id(uniform_leaf_id(first + i, depth), radius));
+}
+
+__global__ void __launch_bounds__(128)
+k_quads_from_ids(const uint64_t *__restrict__ ids, int64_t n, double radius, Quad *__restrict__ out)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t id = ids[i];
+        Quad q;
+        if ((id >> 63) && quad_root(id) < 6) q = quad_from_id(id, radius);
+        else { for (int j = 0; j < 4; j++) q.p[j] = { 0.0, 0.0, 0.0 }; q.id = 0; }   // invalid id (main.cpp:35)
+        store_quad(out + i, q);
+    }
+}
+
+// ---- strip index buffer, closed form of main.cpp:427-474 ---------------------------------
+// n = patch_verts.  Vertex numbering (main.cpp:406-422): n top-skirt verts, then n rows of
+// (skirt, n verts, skirt), then n bottom-skirt verts.
+__host__ __device__ inline uint32_t strip_index(int k, int n)
+{
+    const int w = n + 2;                       // vertices per full row
+    if (k < 2 * n) {                           // top skirt: v0 = x, v1 = n+1+x   (:434-438)
+        int x = k >> 1;
+        return (k & 1) ? (uint32_t)(n + 1 + x) : (uint32_t)x;
+    }
+    k -= 2 * n;
+    if (k < 2) return k == 0 ? (uint32_t)(2 * n) : (uint32_t)n;      // reset (:441-443)
+    k -= 2;
+    const int row_len = 2 * w + 2;             // 2(n+2) strip indices + 2 reset indices
+    const int body = (n - 1) * 2 * w + (n - 2) * 2;
+    if (k < body) {                            // rows y = 0 .. n-2       (:445-457)
+        int y = k / row_len, r = k - y * row_len;
+        int v0 = n + y * w, v1 = 2 * n + 2 + y * w;
+        if (r < 2 * w) {
+            int x = r >> 1;
+            return (r & 1) ? (uint32_t)(v1 + x) : (uint32_t)(v0 + x);
+        }
+        return (r == 2 * w) ? (uint32_t)(v1 + w - 1) : (uint32_t)(v0 + w);
+    }
+    k -= body;
+    const int v0e = n + (n - 1) * w, v1e = 2 * n + 2 + (n - 1) * w;  // cursors after the rows
+    if (k < 2) return k == 0 ? (uint32_t)(v1e - 1) : (uint32_t)(v0e + 1);   // v0++, reset (:459-462)
+    k -= 2;
+    int x = k >> 1;                            // bottom skirt           (:465-469)
+    return (k & 1) ? (uint32_t)(v1e + x) : (uint32_t)(v0e + 1 + x);
+}
+
+// merged index buffer: out[q*ni + k] = q*nv + strip[k].  The strip is staged once per CTA
+// in shared memory; each thread then streams 4 consecutive indices as one 16-byte store.
+__global__ void __launch_bounds__(256)
+k_merged_indices(int n, int nv, int ni, int64_t nquads, uint32_t base_quad, uint32_t *__restrict__ out)
+{
+    extern __shared__ uint32_t s_strip[];
+    for (int k = threadIdx.x; k < ni; k += blockDim.x) s_strip[k] = strip_index(k, n);
+    __syncthreads();
+    const int64_t total = nquads * ni;                 // ni is even; total % 4 may be 0 or 2
+    const int64_t vecs = total >> 2;
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < vecs;
+         v += (int64_t)gridDim.x * blockDim.x) {
+        int64_t e = v << 2;
+        int64_t q = e / ni;
+        int k = (int)(e - q * ni);
+        uint32_t r[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int kk = k + j;
+            int64_t qq = q;
+            if (kk >= ni) { kk -= ni; qq++; }
+            r[j] = (uint32_t)(base_quad + qq) * (uint32_t)nv + s_strip[kk];
+        }
+        reinterpret_cast<uint4 *>(out)[v] = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(total & 3)) {
+        int64_t e = (vecs << 2) + threadIdx.x;
+        int64_t q = e / ni;
+        out[e] = (uint32_t)(base_quad + q) * (uint32_t)nv + s_strip[(int)(e - q * ni)];
+    }
+}
+
+// the reference's static patch: vertices (main.cpp:402-425) and indices (:427-474)
+__global__ void k_patch_mesh(int n, float *__restrict__ verts, uint32_t *__restrict__ indices)
+{
+    const int nv = n * n + 4 * n, ni = 2 * n * n + 8 * n - 4, w = n + 2;
+    const double div = __ddiv_rn(1.0, (double)(n - 1));               // main.cpp:404
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) {
+        if (!verts) break;
+        float u, v, s;
+        if (i < n) {                                      // top skirt (:406-407)
+            u = __double2float_rn(__dmul_rn((double)i, div)); v = 0.0f; s = 1.0f;
+        } else if (i < n + n * w) {
+            int r = i - n, y = r / w, c = r - y * w;
+            v = __double2float_rn(__dmul_rn((double)y, div));
+            if (c == 0)          { u = 0.0f; s = 1.0f; }   // :411
+            else if (c == w - 1) { u = 1.0f; s = 1.0f; }   // :416
+            else { u = __double2float_rn(__dmul_rn((double)(c - 1), div)); s = 0.0f; }   // :414
+        } else {                                          // bottom skirt (:419-420)
+            u = __double2float_rn(__dmul_rn((double)(i - n - n * w), div)); v = 1.0f; s = 1.0f;
+        }
+        verts[3 * i] = u; verts[3 * i + 1] = v; verts[3 * i + 2] = s;
+    }
+    if (indices)
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < ni; k += gridDim.x * blockDim.x)
+            indices[k] = strip_index(k, n);
+}
+
+// =====================================================================================
+static int sm_count_k1()
+{
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+int launch_tessellate_uniform(const planet_gpu_params *p, int depth, int64_t first, int64_t nquads,
+                              Quad *d_quads, uint32_t *d_indices, cudaStream_t stream)
+{
+    if (nquads == 0) return 0;
+    const int n = p->patch_verts;
+    if (d_quads) {
+        int grid = (int)std::min<int64_t>((nquads + 127) / 128, (int64_t)sm_count_k1() * 16);
+        k_quads_uniform<<<grid, 128, 0, stream>>>(depth, first, nquads, p->radius, d_quads);
+        count_launch();
+        PLANET_CUDA(cudaGetLastError());
+    }
+    if (d_indices) {
+        const int nv = n * n + 4 * n, ni = 2 * n * n + 8 * n - 4;
+        if ((uint64_t)(nquads) * (uint64_t)nv > 0xFFFFFFFFull)
+            return set_error(PLANET_E_INVALID, "merged vertex count %lld x %d exceeds uint32 indices",
+                             (long long)nquads, nv);
+        size_t smem = (size_t)ni * sizeof(uint32_t);
+        if (smem > 48 * 1024)
+            PLANET_CUDA(cudaFuncSetAttribute(k_merged_indices, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int64_t vecs = (nquads * ni) >> 2;
+        int grid = (int)std::max<int64_t>(1, std::min<int64_t>((vecs + 255) / 256, (int64_t)sm_count_k1() * 8));
+        // indices are rebased to the caller's buffer: quad 0 of this call is vertex block 0
+        k_merged_indices<<<grid, 256, smem, stream>>>(n, nv, ni, nquads, 0u, d_indices);
+        count_launch();
+        PLANET_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+int launch_quads_from_ids(const planet_gpu_params *p, const uint64_t *d_ids, int64_t n, Quad *d_quads,
+                          cudaStream_t stream)
+{
+    if (n == 0) return 0;
+    int grid = (int)std::min<int64_t>((n + 127) / 128, (int64_t)sm_count_k1() * 16);
+    k_quads_from_ids<<<grid, 128, 0, stream>>>(d_ids, n, p->radius, d_quads);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "quads_from_ids launch");
+}
+
+int launch_patch_mesh(int n, float *d_vertices, uint32_t *d_indices, cudaStream_t stream)
+{
+    k_patch_mesh<<<8, 256, 0, stream>>>(n, d_vertices, d_indices);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "patch_mesh launch");
+}
+
+uint32_t host_strip_index(int k, int n) { return strip_index(k, n); }
+uint64_t host_uniform_leaf_id(int64_t leaf, int depth) { return uniform_leaf_id(leaf, depth); }
+
+} // namespace planet

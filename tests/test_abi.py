@@ -1,0 +1,93 @@
+"""The drop-in boundary without a GPU: the library builds, loads, exports every symbol the
+header declares, validates arguments, and refuses to compute when there is no device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import planet_b200 as pb
+from conftest import ROOT
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "planet_gpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(planet_gpu_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = pb.lib()
+    names = header_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/planet_gpu.h but not exported"
+    assert sorted(pb.EXPORTED_SYMBOLS) == names
+
+
+def test_abi_version_and_struct_layout():
+    assert pb.lib().planet_gpu_abi_version() == 1
+    assert C.sizeof(pb.Params) == 72                       # planet_gpu_params
+    assert pb.QUAD_DTYPE.itemsize == 104                   # main.cpp:68-72
+
+
+def test_default_params_are_the_reference_constants():
+    p = pb.default_params()
+    assert (p.radius, p.patch_verts, p.noise_kind, p.lacunarity) == (6371000.0, 30, pb.RIDGED, 2.0)
+    assert p.gain == np.float32(0.55) and p.fixed_octaves == 0
+    assert p.coord_scale == 0.00001 and p.height_scale == 8848.0 and p.precision == pb.EXACT
+    assert list(p.seed_offset) == [0.0, 0.0, 0.0]
+
+
+def test_host_scalars_match_reference(golden):
+    assert pb.max_lod() == int(golden["max_lod"])
+    assert np.float32(pb.max_skirt_size()) == golden["max_skirt_size"]
+    assert pb.patch_vertex_count(30) == 1020 and pb.patch_index_count(30) == 2036
+
+
+def test_strip_index_closed_form_matches_reference_buffer(golden, port):
+    L = pb.lib()
+    want = golden["patch_index_buffer"].view(np.uint32)
+    got = np.array([L.planet_gpu_strip_index(k, 30) for k in range(2036)], np.uint32)
+    assert (got == want).all()
+    for n in (2, 3, 4, 5, 7, 31, 50, 64):                  # closed form for N != 30 too
+        got = np.array([L.planet_gpu_strip_index(k, n) for k in range(pb.patch_index_count(n))], np.uint32)
+        assert (got == port.patch_indices(n)).all(), n
+
+
+def test_uniform_leaf_ids_follow_recursion_order(port):
+    L = pb.lib()
+    for depth in (0, 1, 2, 4):
+        want = np.concatenate([port.uniform_quads(f, depth)["id"] for f in range(6)])
+        got = np.array([L.planet_gpu_uniform_leaf_id(k, depth) for k in range(len(want))], np.uint64)
+        assert (got == want).all(), depth
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert pb.lib().planet_gpu_init(0) == -1                # PLANET_E_NO_DEVICE
+    assert b"no CPU path" in pb.lib().planet_gpu_last_error()
+    with pytest.raises(pb.PlanetGpuError):
+        pb.generate_height_maps_host(np.zeros(1, pb.QUAD_DTYPE), 32, 18)
+    # the reference-shaped call cannot return a status: it logs and fills NaN
+    out = pb.generate_height_map(np.zeros(1, pb.QUAD_DTYPE), 8, 18)
+    assert np.isnan(out).all()
+    assert np.isnan(pb.get_height_at([1.0, 2.0, 3.0], 0, 1))
+    with pytest.raises(pb.PlanetGpuError):
+        pb.tessellate_uniform(2)
+
+
+def test_product_never_touches_the_oracle():
+    """planet_b200/ and include/ must not import, link or load anything under oracle/."""
+    bad = []
+    for base in ("planet_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
+                    text = open(os.path.join(dirpath, f), errors="ignore").read()
+                    if re.search(r"oracle|libplanet_ref|planet_oracle", text):
+                        bad.append(os.path.join(dirpath, f))
+    assert not bad, bad

@@ -1,0 +1,395 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C-ABI, against
+ (a) the committed golden vectors produced by the reference's own code, and
+ (b) the CPU oracle on the same seeded inputs,
+plus size-independent properties at BASELINE.json's full size.
+
+Bars (north_star): index buffers, QuadIDs, quad corners and permutation hashing bit-exact;
+EXACT-mode heights bit-exact; FAST-mode heights |dh| <= 1e-5 * height_scale * sum(gain^k);
+normals <= 1e-4 rad."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import as_bits, quads_from_bytes
+from oracle.bindings import FBM, RIDGED, fnv1a32, height_params
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5          # north_star: <= 1e-5 relative on height (relative to the fractal's amplitude sum)
+
+
+def amp_sum(gain, octaves):
+    return float(sum(np.float32(gain) ** k for k in range(max(octaves, 1))))
+
+
+def dev_points(pb, pts):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(pts, np.float64)).cuda()
+
+
+def to_np(t):
+    return t.detach().cpu().numpy()
+
+
+def orc_params(p):
+    """planet_gpu_params -> oracle height_params (same constants)."""
+    return height_params(kind=p.noise_kind, lacunarity=p.lacunarity, gain=p.gain,
+                         fixed_octaves=p.fixed_octaves, coord_scale=p.coord_scale,
+                         height_scale=p.height_scale)
+
+
+# ---------------------------------------------------------------------------------------------
+# perlin.h: hashing + PerlinNoise3, main.cpp:689-734 fractals
+# ---------------------------------------------------------------------------------------------
+def test_noise3_exact_is_bit_identical_to_reference(gpu, golden):
+    got = to_np(gpu.noise(dev_points(gpu, golden["noise_points"]), octaves=0, precision=gpu.EXACT))
+    assert (as_bits(got) == golden["noise_bits"]).all()
+
+
+def test_noise3_fast_within_tolerance(gpu, golden):
+    pts = golden["noise_points"]
+    got = to_np(gpu.noise(dev_points(gpu, pts), octaves=0, precision=gpu.FAST))
+    want = golden["noise_bits"].view(np.float32)
+    err = np.abs(got.astype(np.float64) - want)
+    assert err.max() <= REL_TOL, (err.max(), pts[err.argmax()])
+
+
+@pytest.mark.parametrize("name,kind,gain,octs", [("fbm", FBM, 0.5, (1, 2, 8, 12, 16)),
+                                                 ("ridged", RIDGED, 0.55, (1, 6, 7, 12, 18))])
+def test_fractals_exact_bits_and_fast_tolerance(gpu, golden, name, kind, gain, octs):
+    pts = dev_points(gpu, golden["fractal_points"])
+    for o in octs:
+        want_bits = golden[f"{name}_{o}_bits"]
+        ex = to_np(gpu.noise(pts, kind=kind, lacunarity=2.0, gain=gain, octaves=o, precision=gpu.EXACT))
+        assert (as_bits(ex) == want_bits).all(), (name, o)
+        fa = to_np(gpu.noise(pts, kind=kind, lacunarity=2.0, gain=gain, octaves=o, precision=gpu.FAST))
+        err = np.abs(fa.astype(np.float64) - want_bits.view(np.float32)).max()
+        assert err <= REL_TOL * amp_sum(gain, o), (name, o, err)
+
+
+def test_general_lacunarity_takes_the_exact_path(gpu, golden):
+    pts = dev_points(gpu, golden["fractal_points"])
+    for prec in (gpu.EXACT, gpu.FAST):      # FAST is only defined for lacunarity 2.0; falls to EXACT on the GPU
+        got = to_np(gpu.noise(pts, kind=FBM, lacunarity=2.17, gain=0.47, octaves=6, precision=prec))
+        assert (as_bits(got) == golden["fbm_lac217_gain047_6_bits"]).all()
+
+
+def test_noise_against_oracle_on_seeded_points(gpu, port):
+    rng = np.random.default_rng(7)
+    pts = np.concatenate([rng.uniform(-70, 70, (20000, 3)), rng.uniform(-1e5, 1e5, (5000, 3)),
+                          np.floor(rng.uniform(-300, 300, (2000, 3)))])        # incl. lattice points
+    d = dev_points(gpu, pts)
+    for kind, gain, o in ((FBM, 0.5, 8), (RIDGED, 0.55, 12), (FBM, 0.5, 0)):
+        want = port.noise3(pts) if o == 0 else port.fractal(pts, kind, 2.0, gain, o)
+        ex = to_np(gpu.noise(d, kind=kind, gain=gain, octaves=o, precision=gpu.EXACT))
+        assert (as_bits(ex) == as_bits(want)).all()
+        fa = to_np(gpu.noise(d, kind=kind, gain=gain, octaves=o, precision=gpu.FAST))
+        assert np.abs(fa.astype(np.float64) - want).max() <= REL_TOL * amp_sum(gain, o)
+
+
+# ---------------------------------------------------------------------------------------------
+# K1: QuadIDs, corners, patch mesh, merged index buffer -- all bit-exact
+# ---------------------------------------------------------------------------------------------
+def test_tessellate_uniform_corners_and_ids_bit_exact(gpu, golden, port):
+    roots = gpu.quads_to_host(gpu.tessellate_uniform(0))
+    assert roots.tobytes() == golden["root_quads"].tobytes()
+    d2 = gpu.quads_to_host(gpu.tessellate_uniform(2))
+    assert d2.tobytes() == golden["depth2_quads"].tobytes()
+    d5 = gpu.quads_to_host(gpu.tessellate_uniform(5, first=0, nquads=1024))
+    assert fnv1a32(d5) == int(golden["depth5_face0_fnv"])
+    d7 = gpu.quads_to_host(gpu.tessellate_uniform(7, first=3 * 16384, nquads=16384))
+    assert fnv1a32(d7) == int(golden["depth7_face3_fnv"])
+    # a ragged sub-range that straddles two faces, against the oracle
+    sub = gpu.quads_to_host(gpu.tessellate_uniform(4, first=250, nquads=13))
+    want = np.concatenate([port.uniform_quads(0, 4), port.uniform_quads(1, 4)])[250:263]
+    assert sub.tobytes() == want.tobytes()
+
+
+def test_quads_from_ids_reproduces_processquad_leaves(gpu, golden):
+    quads = quads_from_bytes(golden["frame_quads"])               # depths 0..10, from ProcessQuad itself
+    got = gpu.quads_to_host(gpu.quads_from_ids(quads["id"].copy()))
+    assert got.tobytes() == quads.tobytes()
+
+
+def test_quads_from_ids_deepest_path_and_invalid_id(gpu, golden, port):
+    ids = golden["quad_ids"]
+    got = gpu.quads_to_host(gpu.quads_from_ids(np.concatenate([ids, np.array([0], np.uint64)])))
+    for k, i in enumerate(ids):
+        assert got[k].tobytes() == port.quad_from_id(i).tobytes(), hex(int(i))
+    assert int(got[-1]["id"]) == 0                                # invalid id (main.cpp:35) -> zero quad
+
+
+def test_patch_mesh_bit_exact(gpu, golden, port):
+    v, i = gpu.patch_mesh(30)
+    assert to_np(v).tobytes() == golden["patch_vertex_buffer"].tobytes()
+    assert to_np(i).view(np.uint32).tobytes() == golden["patch_index_buffer"].tobytes()
+    for n in (2, 5, 31, 50):
+        v, i = gpu.patch_mesh(n)
+        assert to_np(v).tobytes() == port.patch_vertices(n).tobytes(), n
+        assert (to_np(i).view(np.uint32) == port.patch_indices(n)).all(), n
+
+
+def test_merged_index_buffer(gpu, golden):
+    strip = golden["patch_index_buffer"].view(np.uint32)
+    for nq in (1, 3, 96):
+        _, idx = gpu.tessellate_uniform(2, first=0, nquads=nq, with_indices=True)
+        idx = to_np(idx).view(np.uint32).reshape(nq, 2036)
+        want = strip[None, :] + (np.arange(nq, dtype=np.uint32) * 1020)[:, None]
+        assert (idx == want).all(), nq
+    p = gpu.default_params(patch_verts=5)                         # total % 4 == 2 tail
+    _, idx = gpu.tessellate_uniform(1, first=0, nquads=3, params=p, with_indices=True)
+    ni, nv = gpu.patch_index_count(5), gpu.patch_vertex_count(5)
+    L = gpu.lib()
+    strip5 = np.array([L.planet_gpu_strip_index(k, 5) for k in range(ni)], np.uint32)
+    want = strip5[None, :] + (np.arange(3, dtype=np.uint32) * nv)[:, None]
+    assert (to_np(idx).view(np.uint32).reshape(3, ni) == want).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# K2: GenerateHeightMap / GetHeightAt
+# ---------------------------------------------------------------------------------------------
+def test_default_frame_height_maps_exact_bits(gpu, golden):
+    """117 height maps the reference's real main() produced on its first frame (ridged, 6..12 octaves)."""
+    quads = quads_from_bytes(golden["frame_quads"])
+    got = to_np(gpu.generate_height_maps(gpu.quads_to_device(quads), 32, int(golden["max_lod"]),
+                                         gpu.default_params()))
+    assert got.tobytes() == golden["frame_height_maps"].tobytes()
+
+
+def test_default_frame_height_maps_fast_tolerance(gpu, golden, port):
+    quads = quads_from_bytes(golden["frame_quads"])
+    p = gpu.default_params(precision=gpu.FAST)
+    got = to_np(gpu.generate_height_maps(gpu.quads_to_device(quads), 32, int(golden["max_lod"]), p))
+    want = golden["frame_height_maps"]
+    for k, q in enumerate(quads):
+        o = 6 + 12 * port.get_depth(int(q["id"])) // 18
+        err = np.abs(got[k].astype(np.float64) - want[k]).max()
+        assert err <= REL_TOL * 8848.0 * amp_sum(0.55, o), (k, o, err)
+
+
+@pytest.mark.parametrize("precision", ["EXACT", "FAST"])
+def test_fbm_height_maps_golden_incl_ragged_dims(gpu, golden, port, precision):
+    prec = getattr(gpu, precision)
+    ml = int(golden["max_lod"])
+
+    def check(quads, dim, octaves, want, kind=gpu.FBM, gain=0.5):
+        p = gpu.default_params(noise_kind=kind, gain=gain, fixed_octaves=octaves, precision=prec)
+        got = to_np(gpu.generate_height_maps(gpu.quads_to_device(quads), dim, ml, p))
+        if prec == gpu.EXACT:
+            assert got.tobytes() == want.tobytes(), (dim, octaves)
+        else:
+            o = octaves if octaves > 0 else 6
+            err = np.abs(got.astype(np.float64) - want).max()
+            assert err <= REL_TOL * 8848.0 * amp_sum(gain, o), (dim, octaves, err)
+
+    d5 = port.uniform_quads(0, 5)
+    check(d5[golden["fbm8_depth5_pick"]], 32, 8, golden["fbm8_depth5_maps"])
+    q7 = quads_from_bytes(golden["fbm8_depth7_quads"])
+    check(q7, 32, 8, golden["fbm8_depth7_maps"])
+    for dim in (4, 5, 7, 33, 52, 64):                              # minimum (dim > 3), odd and ragged sizes
+        check(q7[:2], dim, 12, golden[f"fbm12_dim{dim}_maps"])
+    roots = quads_from_bytes(golden["root_quads"])[[1, 5]]
+    check(roots, 128, 0, golden["ridged_roots15_dim128_maps"], kind=gpu.RIDGED, gain=0.55)
+
+
+def test_fbm8_depth5_checksum_of_checksums(gpu, golden):
+    """All 1 024 face-0 depth-5 maps, EXACT: FNV of the whole buffer == the reference's."""
+    quads = gpu.tessellate_uniform(5, first=0, nquads=1024)
+    p = gpu.default_params(noise_kind=gpu.FBM, gain=0.5, fixed_octaves=8)
+    maps = to_np(gpu.generate_height_maps(quads, 32, 18, p))
+    assert fnv1a32(maps) == int(golden["fbm8_depth5_fnv"]) == 0x62660FBE
+
+
+def test_ridged_18_octaves_and_zero_functor(gpu, port):
+    quads = port.uniform_quads(2, 3)[::7]
+    dq = gpu.quads_to_device(quads)
+    for prec in (gpu.EXACT, gpu.FAST):
+        p = gpu.default_params(fixed_octaves=18, precision=prec)
+        got = to_np(gpu.generate_height_maps(dq, 32, 18, p))
+        want = port.generate_height_maps(quads, 32, 18, orc_params(p))
+        if prec == gpu.EXACT:
+            assert got.tobytes() == want.tobytes()
+        else:
+            assert np.abs(got.astype(np.float64) - want).max() <= REL_TOL * 8848.0 * amp_sum(0.55, 18)
+        z = gpu.default_params(noise_kind=gpu.ZERO, precision=prec)           # ConstantZero, main.cpp:835-841
+        assert not to_np(gpu.generate_height_maps(dq, 32, 18, z)).any()
+
+
+def test_heights_at_golden_and_legacy_scalar_shim(gpu, golden):
+    pts, depth = golden["height_at_points"], golden["height_at_depth"]
+    want = golden["height_at_bits"]
+    for d in np.unique(depth):
+        sel = depth == d
+        ex = to_np(gpu.heights_at(dev_points(gpu, pts[sel]), int(d), 18, gpu.default_params()))
+        assert (as_bits(ex) == want[sel]).all(), d
+        fa = to_np(gpu.heights_at(dev_points(gpu, pts[sel]), int(d), 18, gpu.default_params(precision=gpu.FAST)))
+        o = 6 + 12 * int(d) // 18
+        assert np.abs(fa.astype(np.float64) - want[sel].view(np.float32)).max() <= REL_TOL * 8848.0 * amp_sum(0.55, o)
+    # ProcessQuad's call shape: GetHeightAt(p, 0, 1) through the reference-shaped pointer
+    gpu.set_params(gpu.default_params())
+    lod = np.array([gpu.get_height_at(p, 0, 1) for p in pts[:16]], np.float32)
+    assert (as_bits(lod) == golden["height_at_lod_bits"][:16]).all()
+
+
+def test_reference_shaped_generate_height_map(gpu, golden):
+    """void GenerateHeightMap(float*, int, const Quad&, int) with host buffers, as GetHeightMapForQuad calls it."""
+    quads = quads_from_bytes(golden["frame_quads"])
+    gpu.set_params(gpu.default_params())
+    for k in (0, 57, 116):
+        got = gpu.generate_height_map(quads[k], 32, int(golden["max_lod"]))
+        assert got.tobytes() == golden["frame_height_maps"][k].tobytes()
+
+
+def test_host_batch_path_equals_device_path(gpu, golden):
+    quads = quads_from_bytes(golden["frame_quads"])
+    p = gpu.default_params(precision=gpu.FAST)
+    host = gpu.generate_height_maps_host(quads, 32, 18, p)
+    dev = to_np(gpu.generate_height_maps(gpu.quads_to_device(quads), 32, 18, p))
+    assert host.tobytes() == dev.tobytes()
+
+
+def test_seed_offset_is_a_coordinate_shift(gpu, port):
+    rng = np.random.default_rng(3)
+    pts = rng.normal(size=(4096, 3)); pts = pts / np.linalg.norm(pts, axis=1, keepdims=True) * 6371000.0
+    seed = (17.25, -3.5, 101.125)
+    p = gpu.default_params(noise_kind=gpu.FBM, gain=0.5, fixed_octaves=8, seed_offset=seed)
+    got = to_np(gpu.heights_at(dev_points(gpu, pts), 0, 18, p))
+    shifted = pts * 0.00001 + np.array(seed)                       # same two roundings as the kernel
+    want = port.fractal(shifted, FBM, 2.0, 0.5, 8) * np.float32(8848.0)
+    assert (as_bits(got) == as_bits(want)).all()
+
+
+def test_wide_quads_take_the_per_sample_reduction(gpu, port):
+    """FAST: a quad spanning more than ~100 lattice cells cannot be reduced mod 256 per quad."""
+    roots = port.root_quads()
+    p = gpu.default_params(noise_kind=gpu.FBM, gain=0.5, fixed_octaves=6, coord_scale=1e-4, precision=gpu.FAST)
+    got = to_np(gpu.generate_height_maps(gpu.quads_to_device(roots), 48, 18, p))
+    want = port.generate_height_maps(roots, 48, 18, orc_params(p))
+    assert np.abs(got.astype(np.float64) - want).max() <= REL_TOL * 8848.0 * amp_sum(0.5, 6)
+
+
+def test_argument_validation_returns_errors(gpu, port):
+    import torch
+    q = gpu.quads_to_device(port.root_quads())
+    with pytest.raises(gpu.PlanetGpuError, match="dim"):
+        gpu.generate_height_maps(q, 3, 18)                          # main.cpp:128 assert(dim > 3)
+    with pytest.raises(gpu.PlanetGpuError, match="max_depth"):
+        gpu.generate_height_maps(q, 32, 0)                          # main.cpp:827 divides by max_depth
+    with pytest.raises(gpu.PlanetGpuError):
+        gpu.tessellate_uniform(28)
+    with pytest.raises(gpu.PlanetGpuError):
+        gpu.generate_height_maps(q, 32, 18, gpu.default_params(noise_kind=9))
+    empty = torch.empty((0, 13), dtype=torch.int64, device="cuda")
+    assert gpu.generate_height_maps(empty, 32, 18).shape == (0, 32, 32)     # empty input is a no-op
+
+
+# ---------------------------------------------------------------------------------------------
+# K3: displacement + normals + Lambert vs the GLSL restatement
+# ---------------------------------------------------------------------------------------------
+def angle(a, b):
+    c = np.cross(a.astype(np.float64), b.astype(np.float64))
+    return np.arctan2(np.linalg.norm(c, axis=-1), (a.astype(np.float64) * b).sum(-1))
+
+
+def check_shade(gpu, port, quads, maps, cam, n=30):
+    p = gpu.default_params(patch_verts=n)
+    import torch
+    pos, nrm = gpu.shade(gpu.quads_to_device(quads), torch.from_numpy(np.ascontiguousarray(maps)).cuda(), cam, p)
+    pos, nrm = to_np(pos), to_np(nrm)
+    wpos, wnrm = port.shade_patches(quads, cam, maps, n=n)
+    ang = angle(nrm[..., :3], wnrm[..., :3])
+    assert ang.max() <= 1e-4, ang.max()                             # north_star: <= 1e-4 angular on normals
+    assert np.abs(nrm[..., 3] - wnrm[..., 3]).max() <= 1e-4        # Lambert colour
+    assert (pos[..., 3] == wpos[..., 3]).all()                      # height - skirt: one fp32 op, exact
+    for k, q in enumerate(quads):
+        rel = np.abs(q["p"] - cam).max()
+        ext = np.linalg.norm(q["p"][3] - q["p"][0])
+        tol = 8 * 2.0 ** -23 * rel + 1e-5 * ext                     # few fp32 ulps of the camera-relative corner
+        assert np.abs(pos[k, :, :3].astype(np.float64) - wpos[k, :, :3]).max() <= tol, k
+
+
+def test_shade_default_frame(gpu, port, golden):
+    """All 117 leaf quads (depths 0..10: both the slerp and the linear branch of interpolate)."""
+    check_shade(gpu, port, quads_from_bytes(golden["frame_quads"]), golden["frame_height_maps"], golden["frame_cam"])
+
+
+def test_shade_other_patch_size_and_camera(gpu, port):
+    quads = port.uniform_quads(4, 2)
+    n = 12
+    maps = port.generate_height_maps(quads, n + 2, 18, height_params(kind=FBM, gain=0.5, fixed_octaves=5))
+    check_shade(gpu, port, quads, maps, np.array([1.0e6, -2.5e6, 7.1e6]), n=n)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json config 2 at full size: properties that need no 16M-sample oracle run
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c2(gpu):
+    """root face 0, uniform depth 7: 16 384 quads x 32^2 = 16 777 216 samples, fBm 8 octaves."""
+    quads = gpu.tessellate_uniform(7, first=0, nquads=16384)
+    p = gpu.fbm_params(octaves=8, gain=0.5, precision=gpu.FAST)
+    maps = gpu.generate_height_maps(quads, 32, 18, p)
+    return quads, p, maps
+
+
+def test_c2_fast_vs_oracle_on_a_strided_subset(gpu, port, c2):
+    quads, p, maps = c2
+    sel = np.arange(0, 16384, 61)
+    hq = gpu.quads_to_host(quads)[sel]
+    want = port.generate_height_maps(hq, 32, 18, orc_params(p), nthreads=4)
+    got = to_np(maps)[sel]
+    assert np.abs(got.astype(np.float64) - want).max() <= REL_TOL * 8848.0 * amp_sum(0.5, 8)
+
+
+def test_c2_fast_vs_exact_everywhere(gpu, c2):
+    import torch
+    quads, p, maps = c2
+    ex = gpu.generate_height_maps(quads, 32, 18, gpu.fbm_params(octaves=8, gain=0.5, precision=gpu.EXACT))
+    err = (maps.double() - ex.double()).abs().max().item()
+    assert err <= REL_TOL * 8848.0 * amp_sum(0.5, 8), err
+    assert torch.isfinite(maps).all()
+
+
+def test_c2_sharding_is_byte_invisible(gpu, c2):
+    """Any partition of the quad range gives the bytes of the unpartitioned run."""
+    import torch
+    quads, p, maps = c2
+    parts = []
+    for g in range(8):                                              # 8 shards as on 8 GPUs
+        lo, hi = g * 2048, (g + 1) * 2048
+        q = gpu.tessellate_uniform(7, first=lo, nquads=2048)
+        parts.append(gpu.generate_height_maps(q, 32, 18, p))
+    assert torch.equal(torch.cat(parts), maps)
+    ragged = torch.cat([gpu.generate_height_maps(quads[a:b], 32, 18, p) for a, b in ((0, 1), (1, 1000), (1000, 16384))])
+    assert torch.equal(ragged, maps)
+
+
+def test_c2_sibling_seams_are_continuous(gpu, c2):
+    """Child 0 and child 1 of one parent share an edge: last interior column == first interior column."""
+    quads, p, maps = c2
+    m = to_np(maps).reshape(-1, 4, 32, 32)                          # consecutive leaves = the 4 children
+    right_of_0, left_of_1 = m[:, 0, 1:31, 30], m[:, 1, 1:31, 1]
+    tol = 2 * REL_TOL * 8848.0 * amp_sum(0.5, 8)
+    assert np.abs(right_of_0.astype(np.float64) - left_of_1).max() <= tol
+    bottom_of_0, top_of_2 = m[:, 0, 30, 1:31], m[:, 2, 1, 1:31]
+    assert np.abs(bottom_of_0.astype(np.float64) - top_of_2).max() <= tol
+
+
+def test_c2_shade_normals_are_unit_and_positions_displace_radially(gpu, c2):
+    import torch
+    quads, p, maps = c2
+    cam = (0.0, 0.0, -6371000.0 - 10.0)
+    pos, nrm = gpu.shade(quads[:4096], maps[:4096], cam)
+    n3 = nrm[..., :3]
+    assert (n3.norm(dim=-1) - 1).abs().max().item() <= 1e-5
+    assert (nrm[..., 3] >= 0.0316).all() and (nrm[..., 3] <= 1.0005).all()      # sqrt(0.001) .. sqrt(1.001)
+    # |pos + cam| - R == height (to fp32 resolution at 6.4e6 m) for non-skirt vertices
+    interior = torch.ones(1020, dtype=torch.bool, device="cuda")
+    interior[:30] = False; interior[-30:] = False
+    interior[30::32][:30] = False; interior[61::32][:30] = False
+    w = pos[:, interior, :3].double() + torch.tensor(cam, dtype=torch.float64, device="cuda")
+    r = w.norm(dim=-1) - 6371000.0
+    # the shader lifts the flat quad to the arc (linear branch below depth 6 keeps the chord):
+    # at depth 7 the sagitta of a 78 km quad is ~120 m, so compare with a loose bound and the exact w channel
+    assert (r - pos[:, interior, 3].double()).abs().max().item() < 250.0
