@@ -276,8 +276,10 @@ def test_argument_validation_returns_errors(gpu, port):
         gpu.generate_height_maps(q, 3, 18)                          # main.cpp:128 assert(dim > 3)
     with pytest.raises(gpu.PlanetGpuError, match="max_depth"):
         gpu.generate_height_maps(q, 32, 0)                          # main.cpp:827 divides by max_depth
-    with pytest.raises(gpu.PlanetGpuError):
-        gpu.tessellate_uniform(28)
+    with pytest.raises(gpu.PlanetGpuError, match="depth"):
+        gpu.tessellate_uniform(28, first=0, nquads=1)               # depth + 1 < 32 and 55 path bits
+    with pytest.raises(gpu.PlanetGpuError, match="leaf range"):
+        gpu.tessellate_uniform(2, first=90, nquads=10)              # only 96 leaves at depth 2
     with pytest.raises(gpu.PlanetGpuError):
         gpu.generate_height_maps(q, 32, 18, gpu.default_params(noise_kind=9))
     empty = torch.empty((0, 13), dtype=torch.int64, device="cuda")
