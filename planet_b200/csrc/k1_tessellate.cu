@@ -96,8 +96,7 @@ __host__ __device__ inline uint64_t uniform_leaf_id(int64_t leaf, int depth)
     return (1ull << 63) | (face << 60) | ((uint64_t)depth << 55) | path;
 }
 
-// one Quad is 13 8-byte words; 13 consecutive threads each write one word of a quad so
-// the 104-byte records leave the SM as coalesced 8-byte stores.
+// 104-byte record store (the quads are ~1 % of K1's traffic; the index buffer is the rest)
 __device__ __forceinline__ void store_quad(Quad *dst, const Quad &q)
 {
     *dst = q;
@@ -157,34 +156,32 @@ __host__ __device__ inline uint32_t strip_index(int k, int n)
 }
 
 // merged index buffer: out[q*ni + k] = q*nv + strip[k].  The strip is staged once per CTA
-// in shared memory; each thread then streams 4 consecutive indices as one 16-byte store.
+// in shared memory; a CTA then walks whole quads, each thread streaming VEC consecutive
+// indices per store (16 bytes when ni % 4 == 0, i.e. even patch_verts; else 8 bytes -- ni is
+// always even), so the kernel is a pure coalesced HBM write with ~3 instructions per index.
+template <int VEC>
 __global__ void __launch_bounds__(256)
-k_merged_indices(int n, int nv, int ni, int64_t nquads, uint32_t base_quad, uint32_t *__restrict__ out)
+k_merged_indices(int n, int nv, int ni, int64_t nquads, uint32_t *__restrict__ out)
 {
-    extern __shared__ uint32_t s_strip[];
+    extern __shared__ __align__(16) uint32_t s_strip[];
     for (int k = threadIdx.x; k < ni; k += blockDim.x) s_strip[k] = strip_index(k, n);
     __syncthreads();
-    const int64_t total = nquads * ni;                 // ni is even; total % 4 may be 0 or 2
-    const int64_t vecs = total >> 2;
-    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < vecs;
-         v += (int64_t)gridDim.x * blockDim.x) {
-        int64_t e = v << 2;
-        int64_t q = e / ni;
-        int k = (int)(e - q * ni);
-        uint32_t r[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            int kk = k + j;
-            int64_t qq = q;
-            if (kk >= ni) { kk -= ni; qq++; }
-            r[j] = (uint32_t)(base_quad + qq) * (uint32_t)nv + s_strip[kk];
+    const int nvec = ni / VEC;
+    for (int64_t q = blockIdx.x; q < nquads; q += gridDim.x) {
+        const uint32_t base = (uint32_t)q * (uint32_t)nv;
+        if (VEC == 4) {
+            uint4 *dst = reinterpret_cast<uint4 *>(out + q * ni);
+            for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+                uint4 s = reinterpret_cast<const uint4 *>(s_strip)[v];
+                __stcs(dst + v, make_uint4(s.x + base, s.y + base, s.z + base, s.w + base));
+            }
+        } else {
+            uint2 *dst = reinterpret_cast<uint2 *>(out + q * ni);
+            for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+                uint2 s = reinterpret_cast<const uint2 *>(s_strip)[v];
+                __stcs(dst + v, make_uint2(s.x + base, s.y + base));
+            }
         }
-        reinterpret_cast<uint4 *>(out)[v] = make_uint4(r[0], r[1], r[2], r[3]);
-    }
-    if (blockIdx.x == 0 && threadIdx.x < (int)(total & 3)) {
-        int64_t e = (vecs << 2) + threadIdx.x;
-        int64_t q = e / ni;
-        out[e] = (uint32_t)(base_quad + q) * (uint32_t)nv + s_strip[(int)(e - q * ni)];
     }
 }
 
@@ -244,12 +241,17 @@ int launch_tessellate_uniform(const planet_gpu_params *p, int depth, int64_t fir
             return set_error(PLANET_E_INVALID, "merged vertex count %lld x %d exceeds uint32 indices",
                              (long long)nquads, nv);
         size_t smem = (size_t)ni * sizeof(uint32_t);
-        if (smem > 48 * 1024)
-            PLANET_CUDA(cudaFuncSetAttribute(k_merged_indices, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int64_t vecs = (nquads * ni) >> 2;
-        int grid = (int)std::max<int64_t>(1, std::min<int64_t>((vecs + 255) / 256, (int64_t)sm_count_k1() * 8));
+        const bool vec4 = (ni % 4 == 0) && (reinterpret_cast<uintptr_t>(d_indices) & 15) == 0;
+        if ((reinterpret_cast<uintptr_t>(d_indices) & 7) != 0)
+            return set_error(PLANET_E_INVALID, "index buffer must be 8-byte aligned");
+        if (smem > 48 * 1024) {
+            PLANET_CUDA(cudaFuncSetAttribute(k_merged_indices<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PLANET_CUDA(cudaFuncSetAttribute(k_merged_indices<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        int grid = (int)std::min<int64_t>(nquads, (int64_t)sm_count_k1() * 8);
         // indices are rebased to the caller's buffer: quad 0 of this call is vertex block 0
-        k_merged_indices<<<grid, 256, smem, stream>>>(n, nv, ni, nquads, 0u, d_indices);
+        if (vec4) k_merged_indices<4><<<grid, 256, smem, stream>>>(n, nv, ni, nquads, d_indices);
+        else      k_merged_indices<2><<<grid, 256, smem, stream>>>(n, nv, ni, nquads, d_indices);
         count_launch();
         PLANET_CUDA(cudaGetLastError());
     }

@@ -22,12 +22,16 @@
 //    dependent lookups per octave-sample never bank-conflict no matter how random the
 //    cells are.  Entries are stored pre-scaled as byte offsets of the next row, so a
 //    chained lookup is one IADD + one LDS.  T12 (levels 1,2: 512 rows x 128 B) packs
-//    both scalings as two u16; T3 (level 3: 512 rows x 256 B) holds the decoded
-//    gradient of perlin.h:30-36 as {half2(gx, gy), float gz}, read with one LDS.64 and
-//    unpacked on the FMA pipe (HADD2.F32), keeping the half-rate ALU pipe for hashing.
+//    both scalings as two u16; T3 (level 3: 512 rows x 256 B) holds, per row, the gradient
+//    codes of BOTH z-neighbours (rows i and i+1) so one LDS.64 serves two cube corners:
+//    14 shared-memory wavefronts per octave-sample in total (shared memory moves 128 B/clk
+//    per SM, which would otherwise be the wall).  A code is three bytes, each the top byte
+//    of the float 2*v (v in {0,+-1}), so a component decodes with a single AND/PRMT/shift.
 //  * 512-thread CTAs, one per SM (192 KB of tables), persistent over tiles of 1024
-//    consecutive samples; each thread owns 2 consecutive texels (float2 store) for ILP.
-//  * Per-tile prologue: three threads per touched quad turn the 104-byte Quad into the
+//    consecutive samples; each thread owns 2 consecutive texels and carries them as one
+//    packed f32x2 pair: every FADD/FMUL/FFMA of fade, gradient dots, lerps and the octave
+//    accumulation is an FADD2/FMUL2/FFMA2 -- half the issue slots (the kernel is issue-bound).
+//  * Per-tile prologue: one thread per touched quad turns the 104-byte Quad into the
 //    bilinear form P = A + B x + y (C + D x) per axis in doubles pre-scaled by 2^55
 //    (same sample points as main.cpp:132-146 up to 1 ulp of double), so a sample's
 //    position costs 3 DFMA + one F2I per axis.
@@ -108,11 +112,11 @@ k_noise_exact(const double *__restrict__ xyz, int64_t n, int kind, double lacuna
 namespace fast {
 
 constexpr int THREADS = 512;
-constexpr int S = 2;                          // consecutive samples per thread
+constexpr int S = 2;                          // consecutive samples per thread (one f32x2 pair)
 constexpr int TILE = THREADS * S;             // samples per CTA iteration
 constexpr int ROWS = 512;                     // table index range: perm (<=255) + cell (<=255) + 1
 constexpr int T12_ROW = 128;                  // 32 lanes x u32
-constexpr int T3_ROW = 256;                   // 32 lanes x {u32, f32}
+constexpr int T3_ROW = 256;                   // 32 lanes x {u32 G(i), u32 G(i+1)}
 constexpr int T12_BYTES = ROWS * T12_ROW;     // 64 KB
 constexpr int T3_BYTES = ROWS * T3_ROW;       // 128 KB
 constexpr int MAX_TILE_QUADS = TILE / 16 + 2; // dim >= 4 -> at most this many quads per tile
@@ -125,6 +129,16 @@ struct TileQuad { AxisCoef ax[3]; int octaves; int wide; };
 
 constexpr int SMEM_BYTES = T12_BYTES + T3_BYTES + MAX_TILE_QUADS * (int)sizeof(TileQuad);
 
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, one issue slot for two lanes) ----
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pack(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack(f2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 splat(float v) { return pack(v, v); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 // shared-memory table reads; `base` is a pointer into the dynamic shared array, so the
 // compiler emits LDS.U16 / LDS.64 with 32-bit addressing and immediate offsets
 __device__ __forceinline__ uint32_t lds_u16(const unsigned char *base, uint32_t off)
@@ -136,8 +150,20 @@ __device__ __forceinline__ uint2 lds_v2(const unsigned char *base, uint32_t off)
     return *reinterpret_cast<const uint2 *>(base + off);
 }
 
-// Build the lane-replicated tables.  T12[i][lane] = (perm*128) | (perm*256) << 16,
-// T3[i][lane] = { half2(gx, gy), gz } of perlin_vectors[perm & 15]; perm = table[i & 255].
+// A gradient vector of perlin.h:30-36 as three byte codes, one per component, each the TOP
+// byte of the float 2*v: 0x00 -> 0.0, 0x40 -> +2.0, 0xC0 -> -2.0.  Component x sits in byte 3
+// (decoded by one AND), y in byte 1 (one PRMT), z in byte 0 (one shift); the factor 2 is
+// exact and is taken back out of the octave amplitude.
+__device__ __forceinline__ uint32_t grad_code(int h)
+{
+    const float *g = g_grad[h & 15];
+    auto byte = [](float v) -> uint32_t { return v > 0.f ? 0x40u : (v < 0.f ? 0xC0u : 0x00u); };
+    return (byte(g[0]) << 24) | (byte(g[1]) << 8) | byte(g[2]);
+}
+
+// Build the lane-replicated tables (perm = table[i & 255]):
+//   T12[i][lane] = (perm*128) | (perm*256) << 16      next-row byte offsets for levels 1 and 2
+//   T3 [i][lane] = { G(table[i]), G(table[i+1]) }     both z-neighbours' gradients in one LDS.64
 __device__ void build_tables(unsigned char *smem)
 {
     uint32_t *t12 = reinterpret_cast<uint32_t *>(smem);
@@ -146,97 +172,120 @@ __device__ void build_tables(unsigned char *smem)
         int i = w >> 5;
         uint32_t p = g_perm[i & 255];
         t12[w] = (p << 7) | (p << 24);
-        const float *g = g_grad[p & 15];
-        __half2 h = __floats2half2_rn(g[0], g[1]);
-        uint2 e;
-        e.x = *reinterpret_cast<uint32_t *>(&h);
-        e.y = __float_as_uint(g[2]);
-        t3[w] = e;
+        t3[w] = make_uint2(grad_code(p), grad_code(g_perm[(i + 1) & 255]));
     }
 }
 
-// one gradient corner: perlin.h:43-48 with the vector pre-decoded in T3.  Exactly one
-// of (gx, gy, gz) is zero and the others are +-1, so the sum has a single rounding and
-// equals the reference's (x*v0 + y*v1) + z*v2 bit for bit.
-__device__ __forceinline__ float corner(const unsigned char *t3, uint32_t off, float X, float Y, float Z)
+// dot of the decoded gradients of one corner with the corner-relative position, for the
+// thread's two samples at once (perlin.h:43-48).  Exactly one component is zero and the
+// others are +-2, so the sum has a single rounding: 2 * the reference's (x*v0 + y*v1) + z*v2.
+__device__ __forceinline__ f2 corner(uint32_t ga, uint32_t gb, f2 X, f2 Y, f2 Z)
 {
-    uint2 e = lds_v2(t3, off);
-    __half2 h = *reinterpret_cast<__half2 *>(&e.x);
-    float gx = __low2float(h), gy = __high2float(h), gz = __uint_as_float(e.y);
-    return fmaf(gz, Z, fmaf(gy, Y, gx * X));
+    f2 cx = pack(__uint_as_float(ga & 0xFF000000u), __uint_as_float(gb & 0xFF000000u));
+    f2 cy = pack(__uint_as_float(__byte_perm(ga, 0, 0x1444)), __uint_as_float(__byte_perm(gb, 0, 0x1444)));
+    f2 cz = pack(__uint_as_float(ga << 24), __uint_as_float(gb << 24));
+    return fma2(cz, Z, fma2(cy, Y, mul2(cx, X)));
 }
 
-__device__ __forceinline__ float fade(float t)        // perlin.h:62 in fp32 + FMA
+__device__ __forceinline__ f2 fade2(f2 t)             // perlin.h:62 in fp32 + FMA
 {
-    return t * t * t * fmaf(t, fmaf(t, 6.0f, -15.0f), 10.0f);
+    f2 t2 = mul2(t, t);
+    f2 a = fma2(fma2(t, splat(6.0f), splat(-15.0f)), t, splat(10.0f));
+    return mul2(mul2(t2, t), a);
 }
-__device__ __forceinline__ float lerp(float a, float b, float t) { return fmaf(b - a, t, a); }
+__device__ __forceinline__ f2 lerp2(f2 a, f2 b, f2 t) { return fma2(sub2(b, a), t, a); }
 
-// PerlinNoise3 for octave k of a fixed-point coordinate.  t12/t3 point at this lane's
-// slot of row 0 of each table (lane*4 / lane*8 bytes in).
-__device__ __forceinline__ float noise_octave(const unsigned char *t12_lane, const unsigned char *t3_lane,
-                                              uint32_t xlo, uint32_t xhi, uint32_t ylo, uint32_t yhi,
-                                              uint32_t zlo, uint32_t zhi, int k)
+struct Fixed3 { uint32_t xlo, xhi, ylo, yhi, zlo, zhi; };
+
+// hash chain R(R(R(ix)+iy)+iz) of one sample for octave k (perlin.h:45): returns the four
+// {z, z+1} gradient-code pairs of the (x, y) columns 00, 10, 01, 11 and the three fractions
+struct Hashed { uint2 e00, e10, e01, e11; float mx, my, mz; };
+
+__device__ __forceinline__ Hashed hash_octave(const unsigned char *t12_lane, const unsigned char *t3_lane,
+                                              const Fixed3 &p, int k)
 {
-    // 32-bit windows: bits 30..23 = cell & 255, bits 22..0 = top of the fraction
-    uint32_t wx = __funnelshift_l(xlo, xhi, k);
-    uint32_t wy = __funnelshift_l(ylo, yhi, k);
-    uint32_t wz = __funnelshift_l(zlo, zhi, k);
-    float fx = __uint_as_float((wx & 0x007FFFFFu) | 0x3F800000u) - 1.0f;   // [0,1), 23 bits
-    float fy = __uint_as_float((wy & 0x007FFFFFu) | 0x3F800000u) - 1.0f;
-    float fz = __uint_as_float((wz & 0x007FFFFFu) | 0x3F800000u) - 1.0f;
-    float gx1 = fx - 1.0f, gy1 = fy - 1.0f, gz1 = fz - 1.0f;
-
-    // hash chain R(R(R(ix)+iy)+iz) for the 8 corners (perlin.h:45), 2 + 4 + 8 lookups
-    uint32_t cx = (wx >> 16) & 0x7F80u;                 // (cell & 255) * 128
+    // 32-bit windows of the fixed-point coordinate: bits 30..23 = cell & 255, 22..0 = fraction
+    uint32_t wx = __funnelshift_l(p.xlo, p.xhi, k);
+    uint32_t wy = __funnelshift_l(p.ylo, p.yhi, k);
+    uint32_t wz = __funnelshift_l(p.zlo, p.zhi, k);
+    Hashed h;
+    h.mx = __uint_as_float((wx & 0x007FFFFFu) | 0x3F800000u);       // 1 + fraction, 23 bits
+    h.my = __uint_as_float((wy & 0x007FFFFFu) | 0x3F800000u);
+    h.mz = __uint_as_float((wz & 0x007FFFFFu) | 0x3F800000u);
+    uint32_t cx = (wx >> 16) & 0x7F80u;                             // (cell & 255) * 128
     uint32_t cy = (wy >> 16) & 0x7F80u;
-    uint32_t cz = (wz >> 15) & 0xFF00u;                 // (cell & 255) * 256
+    uint32_t cz = (wz >> 15) & 0xFF00u;                             // (cell & 255) * 256
     uint32_t a0 = lds_u16(t12_lane, cx), a1 = lds_u16(t12_lane, cx + T12_ROW);   // R(ix), R(ix+1) (*128)
     uint32_t b00 = lds_u16(t12_lane, a0 + cy + 2), b01 = lds_u16(t12_lane, a0 + cy + 2 + T12_ROW);
     uint32_t b10 = lds_u16(t12_lane, a1 + cy + 2), b11 = lds_u16(t12_lane, a1 + cy + 2 + T12_ROW);
-    float g0 = corner(t3_lane, b00 + cz,          fx,  fy,  fz);     // R(R(R(ix)+iy)+iz) -> vector
-    float g1 = corner(t3_lane, b10 + cz,          gx1, fy,  fz);
-    float g2 = corner(t3_lane, b01 + cz,          fx,  gy1, fz);
-    float g3 = corner(t3_lane, b11 + cz,          gx1, gy1, fz);
-    float g4 = corner(t3_lane, b00 + cz + T3_ROW, fx,  fy,  gz1);
-    float g5 = corner(t3_lane, b10 + cz + T3_ROW, gx1, fy,  gz1);
-    float g6 = corner(t3_lane, b01 + cz + T3_ROW, fx,  gy1, gz1);
-    float g7 = corner(t3_lane, b11 + cz + T3_ROW, gx1, gy1, gz1);
-
-    float u = fade(fx), v = fade(fy), w = fade(fz);
-    float l0 = lerp(g0, g1, u), l1 = lerp(g2, g3, u), l2 = lerp(g4, g5, u), l3 = lerp(g6, g7, u);
-    return lerp(lerp(l0, l1, v), lerp(l2, l3, v), w);
+    h.e00 = lds_v2(t3_lane, b00 + cz);                              // R(R(R(ix)+iy)+iz), ..+iz+1
+    h.e10 = lds_v2(t3_lane, b10 + cz);
+    h.e01 = lds_v2(t3_lane, b01 + cz);
+    h.e11 = lds_v2(t3_lane, b11 + cz);
+    return h;
 }
 
-// fractal sum over octaves for S samples at once (main.cpp:689-734 with FMA)
-struct Fixed3 { uint32_t xlo, xhi, ylo, yhi, zlo, zhi; };
+// 2 * PerlinNoise3 of octave k for the thread's two samples (perlin.h:50-88)
+__device__ __forceinline__ f2 noise_octave2(const unsigned char *t12_lane, const unsigned char *t3_lane,
+                                            const Fixed3 &pa, const Fixed3 &pb, int k)
+{
+    Hashed A = hash_octave(t12_lane, t3_lane, pa, k);
+    Hashed B = hash_octave(t12_lane, t3_lane, pb, k);
+    f2 mx = pack(A.mx, B.mx), my = pack(A.my, B.my), mz = pack(A.mz, B.mz);
+    f2 x0 = add2(mx, splat(-1.0f)), x1 = add2(mx, splat(-2.0f));    // fraction, fraction - 1 (exact)
+    f2 y0 = add2(my, splat(-1.0f)), y1 = add2(my, splat(-2.0f));
+    f2 z0 = add2(mz, splat(-1.0f)), z1 = add2(mz, splat(-2.0f));
+    f2 g0 = corner(A.e00.x, B.e00.x, x0, y0, z0);                   // perlin.h:68-75
+    f2 g1 = corner(A.e10.x, B.e10.x, x1, y0, z0);
+    f2 g2 = corner(A.e01.x, B.e01.x, x0, y1, z0);
+    f2 g3 = corner(A.e11.x, B.e11.x, x1, y1, z0);
+    f2 g4 = corner(A.e00.y, B.e00.y, x0, y0, z1);
+    f2 g5 = corner(A.e10.y, B.e10.y, x1, y0, z1);
+    f2 g6 = corner(A.e01.y, B.e01.y, x0, y1, z1);
+    f2 g7 = corner(A.e11.y, B.e11.y, x1, y1, z1);
+    f2 u = fade2(x0), v = fade2(y0), w = fade2(z0);
+    f2 l0 = lerp2(g0, g1, u), l1 = lerp2(g2, g3, u), l2 = lerp2(g4, g5, u), l3 = lerp2(g6, g7, u);
+    return lerp2(lerp2(l0, l1, v), lerp2(l2, l3, v), w);            // perlin.h:77-86
+}
 
+// fractal sum over octaves for the two samples (main.cpp:689-734 with FMA).  `half_amp`
+// carries amplitude/2 because noise_octave2 returns 2*noise.
 template <bool GUARD>
 __device__ __forceinline__ void fractal_loop(const unsigned char *t12_lane, const unsigned char *t3_lane,
                                              const Fixed3 (&p)[S], const int (&octaves)[S], int omax,
                                              int kind, float gain, float (&value)[S])
 {
-    float amp = 1.0f;
-    float weight[S];
+    float half_amp = 0.5f;
+    if (kind == PLANET_NOISE_RIDGED) {                               // main.cpp:716-731
+        float weight[S] = { 1.0f, 1.0f };
+        value[0] = value[1] = 0.0f;
+        for (int k = 0; k < omax; k++) {
+            float n[S];
+            unpack(noise_octave2(t12_lane, t3_lane, p[0], p[1], k), n[0], n[1]);
 #pragma unroll
-    for (int s = 0; s < S; s++) { value[s] = 0.0f; weight[s] = 1.0f; }
-    for (int k = 0; k < omax; k++) {
-#pragma unroll
-        for (int s = 0; s < S; s++) {
-            float n = noise_octave(t12_lane, t3_lane, p[s].xlo, p[s].xhi, p[s].ylo, p[s].yhi,
-                                   p[s].zlo, p[s].zhi, k);
-            bool live = !GUARD || k < octaves[s];
-            if (kind == PLANET_NOISE_RIDGED) {        // main.cpp:722-728
-                float v = 1.0f - fabsf(n);
+            for (int s = 0; s < S; s++) {
+                float v = fmaf(-0.5f, fabsf(n[s]), 1.0f);           // offset - |noise|
                 v = v * v;
-                float nv = fmaf(v * amp, weight[s], value[s]);
-                if (live) { value[s] = nv; weight[s] = v; }
-            } else {                                  // main.cpp:701
-                float nv = fmaf(n, amp, value[s]);
-                if (live) value[s] = nv;
+                float nv = fmaf(v * (2.0f * half_amp), weight[s], value[s]);
+                if (!GUARD || k < octaves[s]) { value[s] = nv; weight[s] = v; }
             }
+            half_amp *= gain;
         }
-        amp *= gain;                                  // main.cpp:703 / 730
+    } else {                                                         // main.cpp:699-704
+        f2 acc = splat(0.0f);
+        for (int k = 0; k < omax; k++) {
+            f2 n = noise_octave2(t12_lane, t3_lane, p[0], p[1], k);
+            if (GUARD) {
+                float lo, hi, alo, ahi;
+                unpack(fma2(n, splat(half_amp), acc), lo, hi);
+                unpack(acc, alo, ahi);
+                acc = pack(k < octaves[0] ? lo : alo, k < octaves[1] ? hi : ahi);
+            } else {
+                acc = fma2(n, splat(half_amp), acc);
+            }
+            half_amp *= gain;                                        // main.cpp:703
+        }
+        unpack(acc, value[0], value[1]);
     }
 }
 
@@ -244,12 +293,9 @@ __device__ __forceinline__ void fractal(const unsigned char *t12_lane, const uns
                                         const Fixed3 (&p)[S], const int (&octaves)[S], int kind,
                                         float gain, float (&value)[S])
 {
-    int omax = octaves[0];
-    bool same = true;
-#pragma unroll
-    for (int s = 1; s < S; s++) { omax = max(omax, octaves[s]); same = same && octaves[s] == octaves[0]; }
-    if (same) fractal_loop<false>(t12_lane, t3_lane, p, octaves, omax, kind, gain, value);
-    else      fractal_loop<true>(t12_lane, t3_lane, p, octaves, omax, kind, gain, value);
+    int omax = max(octaves[0], octaves[1]);
+    if (octaves[0] == octaves[1]) fractal_loop<false>(t12_lane, t3_lane, p, octaves, omax, kind, gain, value);
+    else                          fractal_loop<true>(t12_lane, t3_lane, p, octaves, omax, kind, gain, value);
 }
 
 // reduce a scaled coordinate (units of 2^-55) to one period and convert to fixed point
@@ -264,10 +310,14 @@ __device__ __forceinline__ double wrap_period(double v)     // v - 2^63 * rint(v
     return fma(-FIX_WRAP, rint(v * (1.0 / FIX_WRAP)), v);
 }
 
+// exact r / d for r*d < 2^40 with m = ceil(2^40 / d) (host-computed)
+__device__ __forceinline__ uint32_t div_magic(uint32_t r, uint64_t m) { return (uint32_t)(((uint64_t)r * m) >> 40); }
+
 // ---- height maps --------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS, 1)
 k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, HeightCfg cfg,
-                   float *__restrict__ out, int64_t ntiles, int out_aligned8)
+                   float *__restrict__ out, int64_t ntiles, int out_aligned8,
+                   uint64_t magic_dim, uint64_t magic_dim2)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     TileQuad *tq = reinterpret_cast<TileQuad *>(smem + T12_BYTES + T3_BYTES);
@@ -284,6 +334,7 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
         const int64_t last = min(base + TILE, total) - 1;
         const int64_t q_first = base / dim2;
         const int nq = (int)(last / dim2 - q_first) + 1;
+        const uint32_t r_base = (uint32_t)(base - q_first * dim2);  // offset of the tile inside its first quad
         __syncthreads();                  // tables built / previous tile done with tq[]
 
         // prologue: quad -> per-axis bilinear coefficients (main.cpp:130-146 regrouped)
@@ -312,16 +363,18 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
         __syncthreads();
 
         const int64_t lin0 = base + (int64_t)threadIdx.x * S;
+        const uint32_t r_last = r_base + (uint32_t)(last - base);
         Fixed3 p[S];
         int oct[S];
 #pragma unroll
         for (int s = 0; s < S; s++) {
-            int64_t lin = min(lin0 + s, last);
-            int64_t q = lin / dim2;
-            int r = (int)(lin - q * dim2);
-            int y = r / dim, x = r - y * dim;
-            const TileQuad &c = tq[(int)(q - q_first)];
-            double xd = (double)(x - 1), yd = (double)(y - 1);
+            uint32_t r = min(r_base + (uint32_t)threadIdx.x * S + s, r_last);   // sample index from the first quad
+            uint32_t q = div_magic(r, magic_dim2);
+            r -= q * (uint32_t)dim2;
+            uint32_t y = div_magic(r, magic_dim);
+            uint32_t x = r - y * (uint32_t)dim;
+            const TileQuad &c = tq[q];
+            double xd = (double)((int)x - 1), yd = (double)((int)y - 1);
             double P[3];
 #pragma unroll
             for (int a = 0; a < 3; a++) {
@@ -344,7 +397,7 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
 
         if (out_aligned8 && lin0 + S - 1 <= last) {          // lin0 is even by construction
             float2 h = make_float2(value[0] * cfg.height_scale, value[1] * cfg.height_scale);
-            *reinterpret_cast<float2 *>(out + lin0) = h;
+            __stcs(reinterpret_cast<float2 *>(out + lin0), h);
         } else {
 #pragma unroll
             for (int s = 0; s < S; s++)
@@ -451,8 +504,10 @@ int launch_height_maps(const planet_gpu_params *p, const Quad *d_quads, int64_t 
         if (rc) return rc;
         int64_t ntiles = (total + fast::TILE - 1) / fast::TILE;
         int grid = (int)std::min<int64_t>(ntiles, sm_count());
+        const uint64_t one40 = 1ull << 40;
         fast::k_height_maps_fast<<<grid, fast::THREADS, fast::SMEM_BYTES, stream>>>(
-            d_quads, total, dim, cfg, d_out, ntiles, (reinterpret_cast<uintptr_t>(d_out) & 7) == 0);
+            d_quads, total, dim, cfg, d_out, ntiles, (reinterpret_cast<uintptr_t>(d_out) & 7) == 0,
+            (one40 + dim - 1) / dim, (one40 + (uint64_t)dim * dim - 1) / ((uint64_t)dim * dim));
     } else {
         int64_t blocks = (total + 255) / 256;
         int grid = (int)std::min<int64_t>(blocks, (int64_t)sm_count() * 8);

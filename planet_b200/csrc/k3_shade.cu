@@ -5,17 +5,23 @@
 // height texture (render.cpp:415-435).  Here the same arithmetic runs once per vertex
 // for whole batches of quads and the results stay in HBM as two float4 streams.
 //
-// Per quad (one CTA iteration):
-//   A. threads 0..3 form the uniforms P[j] = float(q.p[j] - cam), N[j] = float(Normalize(q.p[j]))
-//      in fp64 exactly as main.cpp:666-672; all threads stage the (n+2)^2 height map into
-//      shared memory with coalesced 16-byte loads (each height is read from HBM once; the
-//      5-point stencil of compute_normal, main.cpp:338-346, is then served on chip);
-//   B. 2n threads evaluate the two edge interpolants p = interpolate(a,b,UV.x),
-//      q = interpolate(c,d,UV.x) (main.cpp:354-355) once per COLUMN -- they do not depend on
-//      UV.y, so the shader's per-vertex acos/sin/tan work drops from 3 interpolate calls
-//      to 1 -- together with q.p - p.p and xyscale (main.cpp:361);
-//   C. every thread shades vertices: v = interpolate(p, q, UV.y), height, tangent frame,
-//      Normal, position (main.cpp:356-366), Lambert (main.cpp:373-380); float4 stores.
+// HBM-bound by design: 4 B read + 32 B written per vertex, so everything else is kept
+// off the critical path:
+//   A. per quad, threads 0..3 form the uniforms P[j] = float(q.p[j] - cam),
+//      N[j] = float(Normalize(q.p[j])) in fp64 exactly as main.cpp:666-672, while all
+//      threads stage the (n+2)^2 height map into shared memory with 16-byte loads: each
+//      height leaves HBM once, the 5-point stencil of compute_normal (main.cpp:338-346)
+//      is served on chip;
+//   B. the edge interpolants p = interpolate(a,b,UV.x), q = interpolate(c,d,UV.x)
+//      (main.cpp:354-355) do not depend on UV.y: they are evaluated once per COLUMN (2n
+//      per quad instead of 2 per vertex), together with q.p - p.p, xyscale (main.cpp:361)
+//      and the column-constant terms of the third interpolate (acos, tan, 1/sin), and kept
+//      in shared memory as struct-of-arrays so a warp reading 32 columns hits 32 banks;
+//   C. one warp shades one patch ROW (n+2 vertices incl. the two skirt vertices; 32 lanes
+//      for the reference's n = 30): lane = column, so height taps and column data are
+//      conflict-free and each float4 store instruction writes 512 contiguous bytes.
+// Normalisations use rsqrt (MUFU) + multiplies instead of the shader's sqrt + divide; the
+// difference (<= 2 ulp) is far inside the 1e-4 rad parity bound.
 //
 // With the quad's own height map the sampler coordinate of main.cpp:358 is the centre of
 // texel (vx+1, vy+1), so GL_LINEAR filtering (render.cpp:429-430) is a direct read.
@@ -28,6 +34,8 @@ namespace planet {
 namespace shade {
 
 constexpr int THREADS = 256;
+constexpr int WARPS = THREADS / 32;
+constexpr int COL_ARRAYS = 20;       // floats kept per column (SoA)
 
 struct V { float3 p, n; };                                          // main.cpp:298
 
@@ -35,23 +43,26 @@ __device__ __forceinline__ float3 f3(float x, float y, float z) { return make_fl
 __device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
 __device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
 __device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
-__device__ __forceinline__ float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ float length(float3 a) { return sqrtf(dot(a, a)); }
-__device__ __forceinline__ float3 normalize(float3 a) { float l = length(a); return f3(a.x / l, a.y / l, a.z / l); }
+__device__ __forceinline__ float dot(float3 a, float3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+__device__ __forceinline__ float3 normalize(float3 a) { return a * rsqrtf(dot(a, a)); }
 __device__ __forceinline__ float3 cross(float3 a, float3 b)
 {
     return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
-__device__ __forceinline__ float3 mix(float3 a, float3 b, float t) { return a * (1.0f - t) + b * t; }
+// GLSL mix(x, y, a) = x*(1-a) + y*a
+__device__ __forceinline__ float3 mix(float3 a, float3 b, float t, float omt)
+{
+    return f3(fmaf(b.x, t, a.x * omt), fmaf(b.y, t, a.y * omt), fmaf(b.z, t, a.z * omt));
+}
 
-// main.cpp:300-332
-__device__ __forceinline__ V interpolate(const V &v0, const V &v1, float t)
+// main.cpp:300-332, used for the two edge interpolants (phase B, 2n calls per quad)
+__device__ V interpolate(const V &v0, const V &v1, float t)
 {
     V r;
     float d = dot(v0.n, v1.n);
     if (1.0f - d < 0.001f) {                                        // interpolate_linear
-        r.n = normalize(mix(v0.n, v1.n, t));
-        r.p = mix(v0.p, v1.p, t);
+        r.n = normalize(mix(v0.n, v1.n, t, 1.0f - t));
+        r.p = mix(v0.p, v1.p, t, 1.0f - t);
         return r;
     }
     float theta2 = acosf(d);
@@ -63,13 +74,14 @@ __device__ __forceinline__ V interpolate(const V &v0, const V &v1, float t)
     float x = 1.0f - tanf(gamma) / tan_theta;
     float y = 1.0f / sinf(theta) - 1.0f / (cosf(gamma) * tan_theta);
     float3 v = (v1.p - v0.p) * 0.5f;
-    r.p = v0.p + v * x + n * (y * length(v));
+    r.p = v0.p + v * x + n * (y * sqrtf(dot(v, v)));
     r.n = n;
     return r;
 }
 
-// per-column data produced in phase B: 16 floats
-struct Column { V p, q; float3 pq; float xyscale; };
+// SoA column record: index of each array inside s_col (each array holds n floats, padded)
+enum { C_PPX, C_PPY, C_PPZ, C_PNX, C_PNY, C_PNZ, C_QPX, C_QPY, C_QPZ, C_QNX, C_QNY, C_QNZ,
+       C_PQX, C_PQY, C_PQZ, C_XYS, C_TH2, C_ITAN, C_ISIN, C_HLEN };
 
 __global__ void __launch_bounds__(THREADS)
 k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, double cam_y, double cam_z,
@@ -78,13 +90,15 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int dim = n + 2, dim2 = dim * dim, w = n + 2, nv = n * n + 4 * n;
-    V *s_corner = reinterpret_cast<V *>(smem);                       // 4 x 24 B
-    Column *s_col = reinterpret_cast<Column *>(smem + 128);          // n x 64 B
-    float *s_uv = reinterpret_cast<float *>(smem + 128 + (size_t)n * sizeof(Column));   // n floats
-    float *s_h = s_uv + ((n + 3) & ~3);                              // dim2 floats (if staged)
+    const int np = (n + 31) & ~31;                                   // padded column count
+    V *s_corner = reinterpret_cast<V *>(smem);                       // 4 x 24 B (in 128 B)
+    float *s_col = reinterpret_cast<float *>(smem + 128);            // COL_ARRAYS x np floats
+    float *s_uv = s_col + COL_ARRAYS * np;                           // np floats: UV.x / UV.y values
+    float *s_h = s_uv + np;                                          // dim2 floats (if staged)
     const double div = __ddiv_rn(1.0, (double)(n - 1));              // main.cpp:404
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    for (int i = threadIdx.x; i < n; i += blockDim.x)                // UV.x / UV.y values (main.cpp:406-420)
+    for (int i = threadIdx.x; i < n; i += blockDim.x)                // main.cpp:406-420
         s_uv[i] = __double2float_rn(__dmul_rn((double)i, div));
 
     for (int64_t qi = blockIdx.x; qi < nquads; qi += gridDim.x) {
@@ -110,58 +124,85 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
             }
         }
         __syncthreads();
-        // ---- B: per-column edge interpolants -------------------------------------------------
-        for (int t = threadIdx.x; t < 2 * n; t += blockDim.x) {
-            int x = t >> 1, which = t & 1;
-            V r = which ? interpolate(s_corner[2], s_corner[3], s_uv[x])     // main.cpp:355
-                        : interpolate(s_corner[0], s_corner[1], s_uv[x]);    // main.cpp:354
-            if (which) s_col[x].q = r; else s_col[x].p = r;
-        }
-        __syncthreads();
+        // ---- B: per-column edge interpolants and column constants -------------------------------
         for (int x = threadIdx.x; x < n; x += blockDim.x) {
-            float3 pq = s_col[x].q.p - s_col[x].p.p;
-            s_col[x].pq = pq;
-            s_col[x].xyscale = length(pq) / (float)(n - 1);          // main.cpp:361 (29.0 == n-1)
+            const float ux = s_uv[x];
+            V p = interpolate(s_corner[0], s_corner[1], ux);         // main.cpp:354
+            V q = interpolate(s_corner[2], s_corner[3], ux);         // main.cpp:355
+            float3 pq = q.p - p.p;
+            float len = sqrtf(dot(pq, pq));
+            s_col[C_PPX * np + x] = p.p.x; s_col[C_PPY * np + x] = p.p.y; s_col[C_PPZ * np + x] = p.p.z;
+            s_col[C_PNX * np + x] = p.n.x; s_col[C_PNY * np + x] = p.n.y; s_col[C_PNZ * np + x] = p.n.z;
+            s_col[C_QPX * np + x] = q.p.x; s_col[C_QPY * np + x] = q.p.y; s_col[C_QPZ * np + x] = q.p.z;
+            s_col[C_QNX * np + x] = q.n.x; s_col[C_QNY * np + x] = q.n.y; s_col[C_QNZ * np + x] = q.n.z;
+            s_col[C_PQX * np + x] = pq.x; s_col[C_PQY * np + x] = pq.y; s_col[C_PQZ * np + x] = pq.z;
+            s_col[C_XYS * np + x] = 2.0f * (len / (float)(n - 1));   // 2*xyscale, main.cpp:345,361 (29.0 == n-1)
+            // column-constant part of v = interpolate(p, q, UV.y), main.cpp:310-326
+            float d = dot(p.n, q.n);
+            float th2 = -1.0f, itan = 0.f, isin = 0.f;
+            if (!(1.0f - d < 0.001f)) {
+                th2 = acosf(d);
+                float theta = th2 * 0.5f;
+                itan = 1.0f / tanf(theta);
+                isin = 1.0f / sinf(theta);
+            }
+            s_col[C_TH2 * np + x] = th2; s_col[C_ITAN * np + x] = itan; s_col[C_ISIN * np + x] = isin;
+            s_col[C_HLEN * np + x] = 0.5f * len;                     // length((q.p - p.p) * 0.5)
         }
         __syncthreads();
-        // ---- C: vertices -----------------------------------------------------------------------
-        // main.cpp:674-677
-        float skirt_size = max_skirt;
+        // ---- C: one warp per patch row ---------------------------------------------------------
+        float skirt_size = max_skirt;                                // main.cpp:674-677
         {
             int d = (int)quad_depth(quads[qi].id) - 1;
             if (d > 0) skirt_size /= (float)(2 << d);
         }
         const float *Hs = stage_heights ? s_h : H;
-        for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-            int vx, vy; float skirt;
-            if (i < n) { vx = i; vy = 0; skirt = 1.0f; }
-            else if (i < n + n * w) {
-                int r = i - n; vy = r / w; int c = r - vy * w;
-                if (c == 0) { vx = 0; skirt = 1.0f; }
-                else if (c == w - 1) { vx = n - 1; skirt = 1.0f; }
-                else { vx = c - 1; skirt = 0.0f; }
-            } else { vx = i - n - n * w; vy = n - 1; skirt = 1.0f; }
-
-            const Column col = s_col[vx];
-            V v = interpolate(col.p, col.q, s_uv[vy]);               // main.cpp:356
-            const int tx = vx + 1, ty = vy + 1;
-            const float hc = Hs[ty * dim + tx];
-            const float height = hc - skirt_size * skirt;            // main.cpp:360
-            const float x0 = Hs[ty * dim + tx - 1], x1 = Hs[ty * dim + tx + 1];
-            const float y0 = Hs[(ty - 1) * dim + tx], y1 = Hs[(ty + 1) * dim + tx];
-            float3 nt = normalize(f3(x0 - x1, 2.0f * col.xyscale, y0 - y1));     // main.cpp:345
-            float3 nn = v.n;
-            float3 t = normalize(cross(nn, col.pq));                 // main.cpp:363
-            float3 bi = normalize(cross(t, nn));                     // main.cpp:364
-            float3 N = normalize(t * nt.x + nn * nt.y + bi * nt.z);  // main.cpp:365
-            float3 pos = v.p + v.n * height;                         // main.cpp:366
-            // fragment stage at the vertex: l = normalize(0,1,-1)   // main.cpp:374-378
-            const float inv_sqrt2 = 0.70710678118654752f;
-            float lambert = N.y * inv_sqrt2 - N.z * inv_sqrt2;
-            float light = 0.001f + fmaxf(lambert, 0.0f);
-            int64_t o = qi * nv + i;
-            if (pos4) pos4[o] = make_float4(pos.x, pos.y, pos.z, height);
-            if (nrm4) nrm4[o] = make_float4(N.x, N.y, N.z, sqrtf(light));
+        // row task r: 0 = top skirt row, 1..n = vertex rows 0..n-1, n+1 = bottom skirt row
+        for (int r = warp; r < n + 2; r += WARPS) {
+            const bool edge_row = (r == 0) || (r == n + 1);
+            const int vy = min(max(r - 1, 0), n - 1);
+            const int row_slot = (r == 0) ? 0 : (r == n + 1) ? n + n * w : n + (r - 1) * w;
+            const int row_len = edge_row ? n : w;
+            const float t = s_uv[vy], omt = 1.0f - t;
+            const float *h_mid = Hs + (vy + 1) * dim, *h_up = h_mid - dim, *h_dn = h_mid + dim;
+            for (int c = lane; c < row_len; c += 32) {
+                const int vx = edge_row ? c : min(max(c - 1, 0), n - 1);
+                const float skirt = (edge_row || c == 0 || c == w - 1) ? 1.0f : 0.0f;
+                const float3 pp = f3(s_col[C_PPX * np + vx], s_col[C_PPY * np + vx], s_col[C_PPZ * np + vx]);
+                const float3 pn = f3(s_col[C_PNX * np + vx], s_col[C_PNY * np + vx], s_col[C_PNZ * np + vx]);
+                const float3 qp = f3(s_col[C_QPX * np + vx], s_col[C_QPY * np + vx], s_col[C_QPZ * np + vx]);
+                const float3 qn = f3(s_col[C_QNX * np + vx], s_col[C_QNY * np + vx], s_col[C_QNZ * np + vx]);
+                const float3 pq = f3(s_col[C_PQX * np + vx], s_col[C_PQY * np + vx], s_col[C_PQZ * np + vx]);
+                const float th2 = s_col[C_TH2 * np + vx];
+                // v = interpolate(p, q, UV.y)                      // main.cpp:356
+                float3 vp, vn;
+                if (th2 < 0.0f) {                                    // interpolate_linear, main.cpp:300-308
+                    vn = normalize(mix(pn, qn, t, omt));
+                    vp = mix(pp, qp, t, omt);
+                } else {                                             // main.cpp:314-331
+                    vn = normalize(pn * sinf(omt * th2) + qn * sinf(t * th2));
+                    float gamma = th2 * 0.5f - th2 * t;
+                    float itan = s_col[C_ITAN * np + vx];
+                    float x = 1.0f - tanf(gamma) * itan;
+                    float y = s_col[C_ISIN * np + vx] - itan / cosf(gamma);
+                    vp = pp + pq * (0.5f * x) + vn * (y * s_col[C_HLEN * np + vx]);
+                }
+                const int tx = vx + 1;
+                const float hc = h_mid[tx];
+                const float height = hc - skirt_size * skirt;        // main.cpp:360
+                float3 nt = normalize(f3(h_mid[tx - 1] - h_mid[tx + 1], s_col[C_XYS * np + vx],
+                                         h_up[tx] - h_dn[tx]));      // main.cpp:339-345
+                float3 tg = normalize(cross(vn, pq));                // main.cpp:363
+                float3 bi = normalize(cross(tg, vn));                // main.cpp:364
+                float3 N = normalize(tg * nt.x + vn * nt.y + bi * nt.z);   // main.cpp:365
+                float3 pos = f3(fmaf(vn.x, height, vp.x), fmaf(vn.y, height, vp.y), fmaf(vn.z, height, vp.z));   // :366
+                // fragment stage at the vertex: l = normalize(0,1,-1), main.cpp:374-378
+                const float inv_sqrt2 = 0.70710678118654752f;
+                float light = 0.001f + fmaxf((N.y - N.z) * inv_sqrt2, 0.0f);
+                const int64_t o = qi * nv + row_slot + c;
+                if (pos4) __stcs(pos4 + o, make_float4(pos.x, pos.y, pos.z, height));
+                if (nrm4) __stcs(nrm4 + o, make_float4(N.x, N.y, N.z, sqrtf(light)));
+            }
         }
     }
 }
@@ -175,8 +216,8 @@ int launch_shade(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads
     const int n = p->patch_verts;
     if (n < 2 || n > 254)
         return set_error(PLANET_E_UNSUPPORTED, "planet_gpu_shade: patch_verts %d outside [2, 254]", n);
-    const int dim = n + 2;
-    size_t base = 128 + (size_t)n * sizeof(shade::Column) + (size_t)((n + 3) & ~3) * sizeof(float);
+    const int dim = n + 2, np = (n + 31) & ~31;
+    size_t base = 128 + (size_t)(shade::COL_ARRAYS + 1) * np * sizeof(float);
     size_t hbytes = (size_t)dim * dim * sizeof(float);
     int stage = (base + hbytes) <= 200 * 1024;
     size_t smem = base + (stage ? hbytes : 0);
