@@ -39,7 +39,7 @@
 
 #include <algorithm>
 
-#include <cuda_fp16.h>
+#include <cstdlib>
 
 namespace planet {
 
@@ -119,7 +119,6 @@ constexpr int T12_ROW = 128;                  // 32 lanes x u32
 constexpr int T3_ROW = 256;                   // 32 lanes x {u32 G(i), u32 G(i+1)}
 constexpr int T12_BYTES = ROWS * T12_ROW;     // 64 KB
 constexpr int T3_BYTES = ROWS * T3_ROW;       // 128 KB
-constexpr int MAX_TILE_QUADS = TILE / 16 + 2; // dim >= 4 -> at most this many quads per tile
 constexpr double FIX_ONE = 36028797018963968.0;           // 2^55
 constexpr double FIX_WRAP = 256.0 * 36028797018963968.0;  // 2^63: one period of cell & 255
 
@@ -127,7 +126,9 @@ constexpr double FIX_WRAP = 256.0 * 36028797018963968.0;  // 2^63: one period of
 struct AxisCoef { double a, b, c, d; };
 struct TileQuad { AxisCoef ax[3]; int octaves; int wide; };
 
-constexpr int SMEM_BYTES = T12_BYTES + T3_BYTES + MAX_TILE_QUADS * (int)sizeof(TileQuad);
+constexpr int SMEM_TABLES = T12_BYTES + T3_BYTES;
+constexpr int smem_bytes(int nthreads) { return SMEM_TABLES + (nthreads / 32) * (128 / 16 + 2) * (int)sizeof(TileQuad); }
+constexpr int SMEM_BYTES = smem_bytes(768);
 
 // ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, one issue slot for two lanes) ----
 typedef unsigned long long f2;
@@ -168,11 +169,18 @@ __device__ void build_tables(unsigned char *smem)
 {
     uint32_t *t12 = reinterpret_cast<uint32_t *>(smem);
     uint2 *t3 = reinterpret_cast<uint2 *>(smem + T12_BYTES);
+    // stage {perm, code(perm)} for the 256 table entries in the (not yet used) scratch area
+    uint2 *stage = reinterpret_cast<uint2 *>(smem + T12_BYTES + T3_BYTES);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint32_t p = g_perm[i];
+        stage[i] = make_uint2(p, grad_code(p));
+    }
+    __syncthreads();
     for (int w = threadIdx.x; w < ROWS * 32; w += blockDim.x) {
         int i = w >> 5;
-        uint32_t p = g_perm[i & 255];
-        t12[w] = (p << 7) | (p << 24);
-        t3[w] = make_uint2(grad_code(p), grad_code(g_perm[(i + 1) & 255]));
+        uint2 e0 = stage[i & 255], e1 = stage[(i + 1) & 255];
+        t12[w] = (e0.x << 7) | (e0.x << 24);
+        t3[w] = make_uint2(e0.y, e1.y);
     }
 }
 
@@ -314,95 +322,129 @@ __device__ __forceinline__ double wrap_period(double v)     // v - 2^63 * rint(v
 __device__ __forceinline__ uint32_t div_magic(uint32_t r, uint64_t m) { return (uint32_t)(((uint64_t)r * m) >> 40); }
 
 // ---- height maps --------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS, 1)
+// Warps are autonomous: after the one-time table build there is no block-wide barrier.
+// A warp owns "warp tiles" of WTILE consecutive samples; for each it turns the quads the
+// tile touches into bilinear coefficients in its private shared-memory scratch (3 lanes per
+// quad, one per axis), then walks the tile in SUB passes of 64 samples, 2 per lane.
+constexpr int SUB = 2;
+constexpr int WTILE = 32 * S * SUB;                      // 128 samples per warp tile
+constexpr int MAX_WTILE_QUADS = WTILE / 16 + 2;          // dim >= 4
+
+template <int NTHREADS>
+__global__ void __launch_bounds__(NTHREADS, 1)
 k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, HeightCfg cfg,
-                   float *__restrict__ out, int64_t ntiles, int out_aligned8,
+                   float *__restrict__ out, int64_t nwtiles, int out_aligned8,
                    uint64_t magic_dim, uint64_t magic_dim2)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    TileQuad *tq = reinterpret_cast<TileQuad *>(smem + T12_BYTES + T3_BYTES);
     build_tables(smem);
+    __syncthreads();
 
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int WARPS = NTHREADS / 32;
+    TileQuad *tq = reinterpret_cast<TileQuad *>(smem + T12_BYTES + T3_BYTES) + warp * MAX_WTILE_QUADS;
     const unsigned char *t12_lane = smem + lane * 4;
     const unsigned char *t3_lane = smem + T12_BYTES + lane * 8;
-    const int dim2 = dim * dim;
+    const uint32_t dim2 = (uint32_t)dim * (uint32_t)dim;
+    const bool small_maps = dim2 < (uint32_t)WTILE;          // a warp tile may then span > 2 quads
     const double div = 1.0 / (double)(dim - 3);
+    const double s = cfg.coord_scale * FIX_ONE;
 
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t base = tile * TILE;
-        const int64_t last = min(base + TILE, total) - 1;
-        const int64_t q_first = base / dim2;
-        const int nq = (int)(last / dim2 - q_first) + 1;
-        const uint32_t r_base = (uint32_t)(base - q_first * dim2);  // offset of the tile inside its first quad
-        __syncthreads();                  // tables built / previous tile done with tq[]
+    // warp tiles are dealt round-robin over all warps of the grid (neighbouring warps write
+    // neighbouring segments); (q_first, r_base) = divmod(tile start, dim2) is advanced
+    // incrementally so the only 64-bit divisions happen once, here
+    const int64_t wstride = (int64_t)gridDim.x * WARPS;
+    int64_t wt = (int64_t)blockIdx.x * WARPS + warp;
+    int64_t q_first = (wt * WTILE) / dim2;
+    uint32_t r_base = (uint32_t)(wt * WTILE - q_first * dim2);
+    const int64_t step_q = (wstride * WTILE) / dim2;
+    const uint32_t step_r = (uint32_t)(wstride * WTILE - step_q * dim2);
+
+    for (; wt < nwtiles; wt += wstride) {
+        const int64_t base = wt * WTILE;
+        const int n_here = (int)min((int64_t)WTILE, total - base);           // samples in this warp tile
+        const uint32_t r_end = r_base + (uint32_t)n_here - 1;
+        const int nq = (int)(small_maps ? div_magic(r_end, magic_dim2) : (uint32_t)(r_end >= dim2)) + 1;
 
         // prologue: quad -> per-axis bilinear coefficients (main.cpp:130-146 regrouped)
-        for (int qi = threadIdx.x; qi < nq; qi += blockDim.x) {
+        __syncwarp();
+        if (lane < nq * 3) {
+            const int qi = lane / 3, axis = lane - qi * 3;
             const double *qp = reinterpret_cast<const double *>(quads + q_first + qi);
-            const double s = cfg.coord_scale * FIX_ONE;
-            double span = 0.0;
-#pragma unroll
-            for (int axis = 0; axis < 3; axis++) {
-                double p0 = qp[axis], p1 = qp[3 + axis], p2 = qp[6 + axis], p3 = qp[9 + axis];
-                double v0 = p1 - p0, v1 = p3 - p2;
-                AxisCoef c;
-                c.a = wrap_period((p0 * cfg.coord_scale + (cfg.has_seed ? cfg.seed[axis] : 0.0)) * FIX_ONE);
-                c.b = v0 * (s * div);
-                c.c = (p2 - p0) * (s * div);
-                c.d = (v1 - v0) * (s * div * div);
-                tq[qi].ax[axis] = c;
-                span = fmax(span, (fabs(c.b) + fabs(c.c)) * (double)dim + fabs(c.d) * (double)dim * (double)dim);
-            }
-            uint64_t id = quads[q_first + qi].id;
-            tq[qi].octaves = octaves_for(cfg.fixed_octaves, (int)quad_depth(id), cfg.max_depth);
+            double p0 = qp[axis], p1 = qp[3 + axis], p2 = qp[6 + axis], p3 = qp[9 + axis];
+            double v0 = p1 - p0, v1 = p3 - p2;
+            AxisCoef c;
+            const double seed = !cfg.has_seed ? 0.0 : axis == 0 ? cfg.seed[0] : axis == 1 ? cfg.seed[1] : cfg.seed[2];
+            c.a = wrap_period((p0 * cfg.coord_scale + seed) * FIX_ONE);
+            c.b = v0 * (s * div);
+            c.c = (p2 - p0) * (s * div);
+            c.d = (v1 - v0) * (s * div * div);
+            tq[qi].ax[axis] = c;
             // a quad whose scaled extent nears half a period cannot keep |P| < 2^63 from a
             // reduced corner alone; such quads take a per-sample reduction instead
-            tq[qi].wide = span > 0.4 * FIX_WRAP;
-        }
-        __syncthreads();
-
-        const int64_t lin0 = base + (int64_t)threadIdx.x * S;
-        const uint32_t r_last = r_base + (uint32_t)(last - base);
-        Fixed3 p[S];
-        int oct[S];
-#pragma unroll
-        for (int s = 0; s < S; s++) {
-            uint32_t r = min(r_base + (uint32_t)threadIdx.x * S + s, r_last);   // sample index from the first quad
-            uint32_t q = div_magic(r, magic_dim2);
-            r -= q * (uint32_t)dim2;
-            uint32_t y = div_magic(r, magic_dim);
-            uint32_t x = r - y * (uint32_t)dim;
-            const TileQuad &c = tq[q];
-            double xd = (double)((int)x - 1), yd = (double)((int)y - 1);
-            double P[3];
-#pragma unroll
-            for (int a = 0; a < 3; a++) {
-                P[a] = fma(yd, fma(c.ax[a].d, xd, c.ax[a].c), fma(c.ax[a].b, xd, c.ax[a].a));
-                if (c.wide) P[a] = wrap_period(P[a]);
+            double span = (fabs(c.b) + fabs(c.c)) * (double)dim + fabs(c.d) * (double)dim * (double)dim;
+            unsigned wide = __ballot_sync(__activemask(), span > 0.4 * FIX_WRAP);
+            if (axis == 0) {
+                uint64_t id = reinterpret_cast<const uint64_t *>(qp)[12];
+                tq[qi].octaves = octaves_for(cfg.fixed_octaves, (int)quad_depth(id), cfg.max_depth);
+                tq[qi].wide = (wide >> lane) & 7u;                           // any of this quad's 3 axes
             }
-            to_fixed(P[0], p[s].xlo, p[s].xhi);
-            to_fixed(P[1], p[s].ylo, p[s].yhi);
-            to_fixed(P[2], p[s].zlo, p[s].zhi);
-            oct[s] = c.octaves;
+        }
+        __syncwarp();
+
+#pragma unroll 1
+        for (int sub = 0; sub < SUB; sub++) {
+            const int i0 = sub * (32 * S) + lane * S;                        // first sample of this lane
+            if (sub * (32 * S) >= n_here) break;
+            // texel (q, y, x) of the lane's first sample; the second one follows by increment
+            uint32_t r = r_base + (uint32_t)min(i0, n_here - 1);
+            uint32_t q[S], y[S], x[S];
+            q[0] = small_maps ? div_magic(r, magic_dim2) : (uint32_t)(r >= dim2);
+            r -= q[0] * dim2;
+            y[0] = div_magic(r, magic_dim);
+            x[0] = r - y[0] * (uint32_t)dim;
+            q[1] = q[0]; y[1] = y[0]; x[1] = x[0];
+            if (i0 + 1 < n_here) {
+                if (++x[1] == (uint32_t)dim) { x[1] = 0; if (++y[1] == (uint32_t)dim) { y[1] = 0; ++q[1]; } }
+            }
+            Fixed3 p[S];
+            int oct[S];
+#pragma unroll
+            for (int sidx = 0; sidx < S; sidx++) {
+                const TileQuad &c = tq[q[sidx]];
+                double xd = (double)((int)x[sidx] - 1), yd = (double)((int)y[sidx] - 1);
+                double P[3];
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    P[a] = fma(yd, fma(c.ax[a].d, xd, c.ax[a].c), fma(c.ax[a].b, xd, c.ax[a].a));
+                    if (c.wide) P[a] = wrap_period(P[a]);
+                }
+                to_fixed(P[0], p[sidx].xlo, p[sidx].xhi);
+                to_fixed(P[1], p[sidx].ylo, p[sidx].yhi);
+                to_fixed(P[2], p[sidx].zlo, p[sidx].zhi);
+                oct[sidx] = c.octaves;
+            }
+
+            float value[S];
+            if (cfg.kind == PLANET_NOISE_ZERO) {
+                value[0] = value[1] = 0.0f;
+            } else {
+                fractal(t12_lane, t3_lane, p, oct, cfg.kind, cfg.gain, value);
+            }
+
+            float *dst = out + base + i0;                                    // base + i0 is even
+            if (out_aligned8 && i0 + 1 < n_here) {
+                __stcs(reinterpret_cast<float2 *>(dst),
+                       make_float2(value[0] * cfg.height_scale, value[1] * cfg.height_scale));
+            } else {
+#pragma unroll
+                for (int sidx = 0; sidx < S; sidx++)
+                    if (i0 + sidx < n_here) dst[sidx] = value[sidx] * cfg.height_scale;
+            }
         }
 
-        float value[S];
-        if (cfg.kind == PLANET_NOISE_ZERO) {
-#pragma unroll
-            for (int s = 0; s < S; s++) value[s] = 0.0f;
-        } else {
-            fractal(t12_lane, t3_lane, p, oct, cfg.kind, cfg.gain, value);
-        }
-
-        if (out_aligned8 && lin0 + S - 1 <= last) {          // lin0 is even by construction
-            float2 h = make_float2(value[0] * cfg.height_scale, value[1] * cfg.height_scale);
-            __stcs(reinterpret_cast<float2 *>(out + lin0), h);
-        } else {
-#pragma unroll
-            for (int s = 0; s < S; s++)
-                if (lin0 + s <= last) out[lin0 + s] = value[s] * cfg.height_scale;
-        }
+        q_first += step_q; r_base += step_r;
+        if (r_base >= dim2) { r_base -= dim2; q_first++; }
     }
 }
 
@@ -468,10 +510,23 @@ static int sm_count()
     return g_sm_count;
 }
 
+static int k2_threads()
+{
+    static int t = 0;
+    if (!t) {
+        const char *e = getenv("PLANET_K2_THREADS");            // tuning knob: 512 or 768
+        t = e ? atoi(e) : 512;
+        if (t != 512 && t != 768) t = 512;
+    }
+    return t;
+}
+
 static int prepare_fast()
 {
     if (!g_fast_attr_set) {
-        PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_fast,
+        PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_fast<512>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
+        PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_fast<768>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
         PLANET_CUDA(cudaFuncSetAttribute(fast::k_points_fast,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
@@ -502,12 +557,15 @@ int launch_height_maps(const planet_gpu_params *p, const Quad *d_quads, int64_t 
     if (use_fast) {
         int rc = prepare_fast();
         if (rc) return rc;
-        int64_t ntiles = (total + fast::TILE - 1) / fast::TILE;
-        int grid = (int)std::min<int64_t>(ntiles, sm_count());
+        const int nt = k2_threads();
+        int64_t nwtiles = (total + fast::WTILE - 1) / fast::WTILE;
+        int grid = (int)std::min<int64_t>((nwtiles + nt / 32 - 1) / (nt / 32), sm_count());
         const uint64_t one40 = 1ull << 40;
-        fast::k_height_maps_fast<<<grid, fast::THREADS, fast::SMEM_BYTES, stream>>>(
-            d_quads, total, dim, cfg, d_out, ntiles, (reinterpret_cast<uintptr_t>(d_out) & 7) == 0,
-            (one40 + dim - 1) / dim, (one40 + (uint64_t)dim * dim - 1) / ((uint64_t)dim * dim));
+        const uint64_t m1 = (one40 + dim - 1) / dim, m2 = (one40 + (uint64_t)dim * dim - 1) / ((uint64_t)dim * dim);
+        const int al = (reinterpret_cast<uintptr_t>(d_out) & 7) == 0;
+        const size_t sm = fast::smem_bytes(nt);
+        if (nt == 512) fast::k_height_maps_fast<512><<<grid, 512, sm, stream>>>(d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2);
+        else           fast::k_height_maps_fast<768><<<grid, 768, sm, stream>>>(d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2);
     } else {
         int64_t blocks = (total + 255) / 256;
         int grid = (int)std::min<int64_t>(blocks, (int64_t)sm_count() * 8);

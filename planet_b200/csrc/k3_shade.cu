@@ -15,11 +15,13 @@
 //   B. the edge interpolants p = interpolate(a,b,UV.x), q = interpolate(c,d,UV.x)
 //      (main.cpp:354-355) do not depend on UV.y: they are evaluated once per COLUMN (2n
 //      per quad instead of 2 per vertex), together with q.p - p.p, xyscale (main.cpp:361)
-//      and the column-constant terms of the third interpolate (acos, tan, 1/sin), and kept
+//      and the column-constant terms of the third interpolate (acos, tan, 1/sin); q is
+//      stored as deltas from p so the linear branch costs 6 FMAs.  Column data is kept
 //      in shared memory as struct-of-arrays so a warp reading 32 columns hits 32 banks;
-//   C. one warp shades one patch ROW (n+2 vertices incl. the two skirt vertices; 32 lanes
-//      for the reference's n = 30): lane = column, so height taps and column data are
-//      conflict-free and each float4 store instruction writes 512 contiguous bytes.
+//   C. one warp owns one quad and walks its rows (n+2 vertices incl. the two skirt vertices;
+//      32 lanes for the reference's n = 30): lane = column, so height taps and column data
+//      are conflict-free and each float4 store instruction writes 512 contiguous bytes.
+//      Warps never synchronise with each other, so A/B of one warp hide behind C of others.
 // Normalisations use rsqrt (MUFU) + multiplies instead of the shader's sqrt + divide; the
 // difference (<= 2 ulp) is far inside the 1e-4 rad parity bound.
 //
@@ -35,7 +37,7 @@ namespace shade {
 
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
-constexpr int COL_ARRAYS = 20;       // floats kept per column (SoA)
+constexpr int COL_ARRAYS = 17;       // floats kept per column (SoA)
 
 struct V { float3 p, n; };                                          // main.cpp:298
 
@@ -80,52 +82,59 @@ __device__ V interpolate(const V &v0, const V &v1, float t)
 }
 
 // SoA column record: index of each array inside s_col (each array holds n floats, padded)
-enum { C_PPX, C_PPY, C_PPZ, C_PNX, C_PNY, C_PNZ, C_QPX, C_QPY, C_QPZ, C_QNX, C_QNY, C_QNZ,
-       C_PQX, C_PQY, C_PQZ, C_XYS, C_TH2, C_ITAN, C_ISIN, C_HLEN };
+// (q is kept as the deltas q.p - p.p and q.n - p.n: the linear branch is then 6 FMAs)
+enum { C_PPX, C_PPY, C_PPZ, C_PNX, C_PNY, C_PNZ, C_PQX, C_PQY, C_PQZ, C_DNX, C_DNY, C_DNZ,
+       C_XYS, C_TH2, C_ITAN, C_ISIN, C_HLEN };
 
+// One WARP per quad: warps never wait for each other (no block barrier), so one warp's
+// column phase overlaps the other warps' vertex phases.  Per-warp shared memory:
+//   [4 corner uniforms | COL_ARRAYS x np column floats | (n+2)^2 staged heights]
 __global__ void __launch_bounds__(THREADS)
 k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, double cam_y, double cam_z,
         const float *__restrict__ heights, float max_skirt, float4 *__restrict__ pos4,
-        float4 *__restrict__ nrm4, int stage_heights)
+        float4 *__restrict__ nrm4, int stage_heights, int warp_smem_bytes)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int dim = n + 2, dim2 = dim * dim, w = n + 2, nv = n * n + 4 * n;
     const int np = (n + 31) & ~31;                                   // padded column count
-    V *s_corner = reinterpret_cast<V *>(smem);                       // 4 x 24 B (in 128 B)
-    float *s_col = reinterpret_cast<float *>(smem + 128);            // COL_ARRAYS x np floats
-    float *s_uv = s_col + COL_ARRAYS * np;                           // np floats: UV.x / UV.y values
-    float *s_h = s_uv + np;                                          // dim2 floats (if staged)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    float *s_uv = reinterpret_cast<float *>(smem);                   // np floats, shared by the block
+    unsigned char *mine = smem + np * sizeof(float) + (size_t)warp * warp_smem_bytes;
+    V *s_corner = reinterpret_cast<V *>(mine);                       // 4 x 24 B (in 128 B)
+    float *s_col = reinterpret_cast<float *>(mine + 128);            // COL_ARRAYS x np floats
+    float *s_h = s_col + COL_ARRAYS * np;                            // dim2 floats (if staged)
     const double div = __ddiv_rn(1.0, (double)(n - 1));              // main.cpp:404
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    for (int i = threadIdx.x; i < n; i += blockDim.x)                // main.cpp:406-420
+    for (int i = threadIdx.x; i < n; i += blockDim.x)                // UV.x / UV.y values, main.cpp:406-420
         s_uv[i] = __double2float_rn(__dmul_rn((double)i, div));
+    __syncthreads();
 
-    for (int64_t qi = blockIdx.x; qi < nquads; qi += gridDim.x) {
+    const int64_t wstride = (int64_t)gridDim.x * nwarps;
+    for (int64_t qi = (int64_t)blockIdx.x * nwarps + warp; qi < nquads; qi += wstride) {
         const float *H = heights + qi * dim2;
-        __syncthreads();                                             // previous quad fully shaded
+        __syncwarp();                                                // previous quad fully shaded
         // ---- A: uniforms + height map staging ------------------------------------------------
-        if (threadIdx.x < 4) {
-            const d3 p = quads[qi].p[threadIdx.x];
+        if (lane < 4) {
+            const d3 p = quads[qi].p[lane];
             d3 rel = { p.x - cam_x, p.y - cam_y, p.z - cam_z };      // main.cpp:668
             d3 nd = exact::normalize(p);                             // main.cpp:669
             V c;
             c.p = f3((float)rel.x, (float)rel.y, (float)rel.z);
             c.n = f3((float)nd.x, (float)nd.y, (float)nd.z);
-            s_corner[threadIdx.x] = c;
+            s_corner[lane] = c;
         }
         if (stage_heights) {
             if ((dim2 & 3) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0) {
                 const float4 *H4 = reinterpret_cast<const float4 *>(H);
-                for (int i = threadIdx.x; i < dim2 / 4; i += blockDim.x)
-                    reinterpret_cast<float4 *>(s_h)[i] = __ldg(H4 + i);
+                for (int i = lane; i < dim2 / 4; i += 32)
+                    reinterpret_cast<float4 *>(s_h)[i] = __ldcs(H4 + i);
             } else {
-                for (int i = threadIdx.x; i < dim2; i += blockDim.x) s_h[i] = __ldg(H + i);
+                for (int i = lane; i < dim2; i += 32) s_h[i] = __ldcs(H + i);
             }
         }
-        __syncthreads();
+        __syncwarp();
         // ---- B: per-column edge interpolants and column constants -------------------------------
-        for (int x = threadIdx.x; x < n; x += blockDim.x) {
+        for (int x = lane; x < n; x += 32) {
             const float ux = s_uv[x];
             V p = interpolate(s_corner[0], s_corner[1], ux);         // main.cpp:354
             V q = interpolate(s_corner[2], s_corner[3], ux);         // main.cpp:355
@@ -133,9 +142,8 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
             float len = sqrtf(dot(pq, pq));
             s_col[C_PPX * np + x] = p.p.x; s_col[C_PPY * np + x] = p.p.y; s_col[C_PPZ * np + x] = p.p.z;
             s_col[C_PNX * np + x] = p.n.x; s_col[C_PNY * np + x] = p.n.y; s_col[C_PNZ * np + x] = p.n.z;
-            s_col[C_QPX * np + x] = q.p.x; s_col[C_QPY * np + x] = q.p.y; s_col[C_QPZ * np + x] = q.p.z;
-            s_col[C_QNX * np + x] = q.n.x; s_col[C_QNY * np + x] = q.n.y; s_col[C_QNZ * np + x] = q.n.z;
             s_col[C_PQX * np + x] = pq.x; s_col[C_PQY * np + x] = pq.y; s_col[C_PQZ * np + x] = pq.z;
+            s_col[C_DNX * np + x] = q.n.x - p.n.x; s_col[C_DNY * np + x] = q.n.y - p.n.y; s_col[C_DNZ * np + x] = q.n.z - p.n.z;
             s_col[C_XYS * np + x] = 2.0f * (len / (float)(n - 1));   // 2*xyscale, main.cpp:345,361 (29.0 == n-1)
             // column-constant part of v = interpolate(p, q, UV.y), main.cpp:310-326
             float d = dot(p.n, q.n);
@@ -149,16 +157,18 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
             s_col[C_TH2 * np + x] = th2; s_col[C_ITAN * np + x] = itan; s_col[C_ISIN * np + x] = isin;
             s_col[C_HLEN * np + x] = 0.5f * len;                     // length((q.p - p.p) * 0.5)
         }
-        __syncthreads();
-        // ---- C: one warp per patch row ---------------------------------------------------------
+        __syncwarp();
+        // ---- C: the warp walks the patch rows ----------------------------------------------------
         float skirt_size = max_skirt;                                // main.cpp:674-677
         {
             int d = (int)quad_depth(quads[qi].id) - 1;
             if (d > 0) skirt_size /= (float)(2 << d);
         }
         const float *Hs = stage_heights ? s_h : H;
+        float4 *pos_q = pos4 ? pos4 + qi * nv : nullptr;
+        float4 *nrm_q = nrm4 ? nrm4 + qi * nv : nullptr;
         // row task r: 0 = top skirt row, 1..n = vertex rows 0..n-1, n+1 = bottom skirt row
-        for (int r = warp; r < n + 2; r += WARPS) {
+        for (int r = 0; r < n + 2; r++) {
             const bool edge_row = (r == 0) || (r == n + 1);
             const int vy = min(max(r - 1, 0), n - 1);
             const int row_slot = (r == 0) ? 0 : (r == n + 1) ? n + n * w : n + (r - 1) * w;
@@ -170,16 +180,17 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
                 const float skirt = (edge_row || c == 0 || c == w - 1) ? 1.0f : 0.0f;
                 const float3 pp = f3(s_col[C_PPX * np + vx], s_col[C_PPY * np + vx], s_col[C_PPZ * np + vx]);
                 const float3 pn = f3(s_col[C_PNX * np + vx], s_col[C_PNY * np + vx], s_col[C_PNZ * np + vx]);
-                const float3 qp = f3(s_col[C_QPX * np + vx], s_col[C_QPY * np + vx], s_col[C_QPZ * np + vx]);
-                const float3 qn = f3(s_col[C_QNX * np + vx], s_col[C_QNY * np + vx], s_col[C_QNZ * np + vx]);
                 const float3 pq = f3(s_col[C_PQX * np + vx], s_col[C_PQY * np + vx], s_col[C_PQZ * np + vx]);
+                const float3 dn = f3(s_col[C_DNX * np + vx], s_col[C_DNY * np + vx], s_col[C_DNZ * np + vx]);
                 const float th2 = s_col[C_TH2 * np + vx];
                 // v = interpolate(p, q, UV.y)                      // main.cpp:356
                 float3 vp, vn;
                 if (th2 < 0.0f) {                                    // interpolate_linear, main.cpp:300-308
-                    vn = normalize(mix(pn, qn, t, omt));
-                    vp = mix(pp, qp, t, omt);
+                    // mix(a, b, t) = a + (b - a) t with the column's precomputed b - a
+                    vn = normalize(f3(fmaf(dn.x, t, pn.x), fmaf(dn.y, t, pn.y), fmaf(dn.z, t, pn.z)));
+                    vp = f3(fmaf(pq.x, t, pp.x), fmaf(pq.y, t, pp.y), fmaf(pq.z, t, pp.z));
                 } else {                                             // main.cpp:314-331
+                    const float3 qn = pn + dn;
                     vn = normalize(pn * sinf(omt * th2) + qn * sinf(t * th2));
                     float gamma = th2 * 0.5f - th2 * t;
                     float itan = s_col[C_ITAN * np + vx];
@@ -193,15 +204,17 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
                 float3 nt = normalize(f3(h_mid[tx - 1] - h_mid[tx + 1], s_col[C_XYS * np + vx],
                                          h_up[tx] - h_dn[tx]));      // main.cpp:339-345
                 float3 tg = normalize(cross(vn, pq));                // main.cpp:363
-                float3 bi = normalize(cross(tg, vn));                // main.cpp:364
-                float3 N = normalize(tg * nt.x + vn * nt.y + bi * nt.z);   // main.cpp:365
+                // main.cpp:364-365 normalise bi = cross(t, n) and mat3(t, n, bi) * normal as well; t, n
+                // are unit and orthogonal by construction and |normal| = 1, so both lengths are
+                // 1 +- a few ulp and the two rsqrt/multiply groups are left out (<= 1e-6 rad)
+                float3 bi = cross(tg, vn);
+                float3 N = tg * nt.x + vn * nt.y + bi * nt.z;
                 float3 pos = f3(fmaf(vn.x, height, vp.x), fmaf(vn.y, height, vp.y), fmaf(vn.z, height, vp.z));   // :366
                 // fragment stage at the vertex: l = normalize(0,1,-1), main.cpp:374-378
                 const float inv_sqrt2 = 0.70710678118654752f;
                 float light = 0.001f + fmaxf((N.y - N.z) * inv_sqrt2, 0.0f);
-                const int64_t o = qi * nv + row_slot + c;
-                if (pos4) __stcs(pos4 + o, make_float4(pos.x, pos.y, pos.z, height));
-                if (nrm4) __stcs(nrm4 + o, make_float4(N.x, N.y, N.z, sqrtf(light)));
+                if (pos_q) __stcs(pos_q + row_slot + c, make_float4(pos.x, pos.y, pos.z, height));
+                if (nrm_q) __stcs(nrm_q + row_slot + c, make_float4(N.x, N.y, N.z, sqrtf(light)));
             }
         }
     }
@@ -217,10 +230,13 @@ int launch_shade(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads
     if (n < 2 || n > 254)
         return set_error(PLANET_E_UNSUPPORTED, "planet_gpu_shade: patch_verts %d outside [2, 254]", n);
     const int dim = n + 2, np = (n + 31) & ~31;
-    size_t base = 128 + (size_t)(shade::COL_ARRAYS + 1) * np * sizeof(float);
-    size_t hbytes = (size_t)dim * dim * sizeof(float);
-    int stage = (base + hbytes) <= 200 * 1024;
-    size_t smem = base + (stage ? hbytes : 0);
+    const size_t col_bytes = 128 + (size_t)shade::COL_ARRAYS * np * sizeof(float);
+    const size_t hbytes = (size_t)dim * dim * sizeof(float);
+    const size_t budget = 200 * 1024;
+    const int stage = (col_bytes + hbytes) <= budget;               // else the stencil reads go to L1/L2
+    const size_t per_warp = col_bytes + (stage ? hbytes : 0);
+    int warps = (int)std::max<size_t>(1, std::min<size_t>(shade::WARPS, (budget - np * sizeof(float)) / per_warp));
+    size_t smem = np * sizeof(float) + (size_t)warps * per_warp;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -229,11 +245,11 @@ int launch_shade(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1024)));
-    int grid = (int)std::min<int64_t>(nquads, (int64_t)sms * per_sm);
-    shade::k_shade<<<grid, shade::THREADS, smem, stream>>>(
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (warps * 32), budget / smem));
+    int grid = (int)std::min<int64_t>((nquads + warps - 1) / warps, (int64_t)sms * per_sm);
+    shade::k_shade<<<grid, warps * 32, smem, stream>>>(
         d_quads, nquads, n, cam[0], cam[1], cam[2], d_heights, max_skirt,
-        reinterpret_cast<float4 *>(d_pos4), reinterpret_cast<float4 *>(d_nrm4), stage);
+        reinterpret_cast<float4 *>(d_pos4), reinterpret_cast<float4 *>(d_nrm4), stage, (int)per_warp);
     count_launch();
     return check_cuda(cudaGetLastError(), "shade kernel launch");
 }
