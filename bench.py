@@ -270,7 +270,7 @@ def run_ours(args, rank, local_rank, world):
                          "peak_source": "FFMA probe measured in this run", "nominal_peak": nominal_tf,
                          "frac_of_nominal": k2_tf / nominal_tf, "flop_per_vertex": FLOP_PER_VERTEX,
                          "vertices_per_s": VERTS_PER_GPU / (ms_k2 * 1e-3)},
-            "roofline_k1": {"kernel": "k_merged_indices+k_quads_uniform", "bound": "hbm",
+            "roofline_k1": {"kernel": "k_tessellate_fused", "bound": "hbm",
                             "achieved": k1_bytes / (ms_k1 * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": k1_bytes / (ms_k1 * 1e-3) / 1e9 / hbm_peak, "bytes": k1_bytes,
                             "peak_source": peak_src},

@@ -103,7 +103,7 @@ __device__ __forceinline__ void store_quad(Quad *dst, const Quad &q)
 }
 
 __global__ void __launch_bounds__(128)
-k_quads_uniform(int depth, int64_t first, int64_t n, double radius, Quad *__restrict__ out)
+k_quads_uniform(int depth, int64_t first, int64_t n, double radius, Quad *__restrict__ out)   // quads only
 {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x)
@@ -158,25 +158,36 @@ __host__ __device__ inline uint32_t strip_index(int k, int n)
 // merged index buffer: out[q*ni + k] = q*nv + strip[k].  The strip is staged once per CTA
 // in shared memory; a CTA then walks whole quads, each thread streaming VEC consecutive
 // indices per store (16 bytes when ni % 4 == 0, i.e. even patch_verts; else 8 bytes -- ni is
-// always even), so the kernel is a pure coalesced HBM write with ~3 instructions per index.
+// always even), so the index part is a pure coalesced HBM write with ~3 instructions per index.
+// K1 as ONE launch: the first `quad_blocks` CTAs walk QuadIDs to corners (latency-bound fp64
+// chains, few warps), all other CTAs stream the merged index buffer (bandwidth-bound).  The two
+// outputs are independent, so running them side by side hides the corner chains completely.
 template <int VEC>
 __global__ void __launch_bounds__(256)
-k_merged_indices(int n, int nv, int ni, int64_t nquads, uint32_t *__restrict__ out)
+k_tessellate_fused(int depth, int64_t first, int64_t nquads, double radius, Quad *__restrict__ quads,
+                   int quad_blocks, int n, int nv, int ni, uint32_t *__restrict__ indices)
 {
     extern __shared__ __align__(16) uint32_t s_strip[];
+    if ((int)blockIdx.x < quad_blocks) {
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nquads;
+             i += (int64_t)quad_blocks * blockDim.x)
+            store_quad(quads + i, quad_from_id(uniform_leaf_id(first + i, depth), radius));
+        return;
+    }
     for (int k = threadIdx.x; k < ni; k += blockDim.x) s_strip[k] = strip_index(k, n);
     __syncthreads();
     const int nvec = ni / VEC;
-    for (int64_t q = blockIdx.x; q < nquads; q += gridDim.x) {
+    const int64_t qstride = (int64_t)gridDim.x - quad_blocks;
+    for (int64_t q = (int64_t)blockIdx.x - quad_blocks; q < nquads; q += qstride) {
         const uint32_t base = (uint32_t)q * (uint32_t)nv;
         if (VEC == 4) {
-            uint4 *dst = reinterpret_cast<uint4 *>(out + q * ni);
+            uint4 *dst = reinterpret_cast<uint4 *>(indices + q * ni);
             for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
                 uint4 s = reinterpret_cast<const uint4 *>(s_strip)[v];
                 __stcs(dst + v, make_uint4(s.x + base, s.y + base, s.z + base, s.w + base));
             }
         } else {
-            uint2 *dst = reinterpret_cast<uint2 *>(out + q * ni);
+            uint2 *dst = reinterpret_cast<uint2 *>(indices + q * ni);
             for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
                 uint2 s = reinterpret_cast<const uint2 *>(s_strip)[v];
                 __stcs(dst + v, make_uint2(s.x + base, s.y + base));
@@ -229,33 +240,34 @@ int launch_tessellate_uniform(const planet_gpu_params *p, int depth, int64_t fir
 {
     if (nquads == 0) return 0;
     const int n = p->patch_verts;
-    if (d_quads) {
-        int grid = (int)std::min<int64_t>((nquads + 127) / 128, (int64_t)sm_count_k1() * 16);
-        k_quads_uniform<<<grid, 128, 0, stream>>>(depth, first, nquads, p->radius, d_quads);
-        count_launch();
-        PLANET_CUDA(cudaGetLastError());
-    }
+    const int nv = n * n + 4 * n, ni = 2 * n * n + 8 * n - 4;
     if (d_indices) {
-        const int nv = n * n + 4 * n, ni = 2 * n * n + 8 * n - 4;
         if ((uint64_t)(nquads) * (uint64_t)nv > 0xFFFFFFFFull)
             return set_error(PLANET_E_INVALID, "merged vertex count %lld x %d exceeds uint32 indices",
                              (long long)nquads, nv);
-        size_t smem = (size_t)ni * sizeof(uint32_t);
-        const bool vec4 = (ni % 4 == 0) && (reinterpret_cast<uintptr_t>(d_indices) & 15) == 0;
         if ((reinterpret_cast<uintptr_t>(d_indices) & 7) != 0)
             return set_error(PLANET_E_INVALID, "index buffer must be 8-byte aligned");
-        if (smem > 48 * 1024) {
-            PLANET_CUDA(cudaFuncSetAttribute(k_merged_indices<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            PLANET_CUDA(cudaFuncSetAttribute(k_merged_indices<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
-        int grid = (int)std::min<int64_t>(nquads, (int64_t)sm_count_k1() * 8);
-        // indices are rebased to the caller's buffer: quad 0 of this call is vertex block 0
-        if (vec4) k_merged_indices<4><<<grid, 256, smem, stream>>>(n, nv, ni, nquads, d_indices);
-        else      k_merged_indices<2><<<grid, 256, smem, stream>>>(n, nv, ni, nquads, d_indices);
-        count_launch();
-        PLANET_CUDA(cudaGetLastError());
     }
-    return 0;
+    if (d_quads && !d_indices) {
+        int grid = (int)std::min<int64_t>((nquads + 31) / 32, (int64_t)sm_count_k1() * 16);
+        k_quads_uniform<<<grid, 32, 0, stream>>>(depth, first, nquads, p->radius, d_quads);
+    } else {
+        size_t smem = (size_t)ni * sizeof(uint32_t);
+        const bool vec4 = (ni % 4 == 0) && (reinterpret_cast<uintptr_t>(d_indices) & 15) == 0;
+        if (smem > 48 * 1024) {
+            PLANET_CUDA(cudaFuncSetAttribute(k_tessellate_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PLANET_CUDA(cudaFuncSetAttribute(k_tessellate_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        // indices are rebased to the caller's buffer: quad 0 of this call is vertex block 0
+        int quad_blocks = d_quads ? (int)std::min<int64_t>((nquads + 255) / 256, sm_count_k1()) : 0;
+        int idx_blocks = (int)std::min<int64_t>(nquads, (int64_t)sm_count_k1() * 6);
+        if (vec4) k_tessellate_fused<4><<<quad_blocks + idx_blocks, 256, smem, stream>>>(
+                      depth, first, nquads, p->radius, d_quads, quad_blocks, n, nv, ni, d_indices);
+        else      k_tessellate_fused<2><<<quad_blocks + idx_blocks, 256, smem, stream>>>(
+                      depth, first, nquads, p->radius, d_quads, quad_blocks, n, nv, ni, d_indices);
+    }
+    count_launch();
+    return check_cuda(cudaGetLastError(), "tessellate launch");
 }
 
 int launch_quads_from_ids(const planet_gpu_params *p, const uint64_t *d_ids, int64_t n, Quad *d_quads,
