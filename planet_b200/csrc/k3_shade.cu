@@ -89,10 +89,11 @@ enum { C_PPX, C_PPY, C_PPZ, C_PNX, C_PNY, C_PNZ, C_PQX, C_PQY, C_PQZ, C_DNX, C_D
 // One WARP per quad: warps never wait for each other (no block barrier), so one warp's
 // column phase overlaps the other warps' vertex phases.  Per-warp shared memory:
 //   [4 corner uniforms | COL_ARRAYS x np column floats | (n+2)^2 staged heights]
+template <bool STAGE>      // STAGE: height map staged in shared memory (else taps read global via L1)
 __global__ void __launch_bounds__(THREADS)
 k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, double cam_y, double cam_z,
         const float *__restrict__ heights, float max_skirt, float4 *__restrict__ pos4,
-        float4 *__restrict__ nrm4, int stage_heights, int warp_smem_bytes)
+        float4 *__restrict__ nrm4, int warp_smem_bytes)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int dim = n + 2, dim2 = dim * dim, w = n + 2, nv = n * n + 4 * n;
@@ -123,7 +124,7 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
             c.n = f3((float)nd.x, (float)nd.y, (float)nd.z);
             s_corner[lane] = c;
         }
-        if (stage_heights) {
+        if (STAGE) {
             if ((dim2 & 3) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0) {
                 const float4 *H4 = reinterpret_cast<const float4 *>(H);
                 for (int i = lane; i < dim2 / 4; i += 32)
@@ -164,7 +165,6 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
             int d = (int)quad_depth(quads[qi].id) - 1;
             if (d > 0) skirt_size /= (float)(2 << d);
         }
-        const float *Hs = stage_heights ? s_h : H;
         float4 *pos_q = pos4 ? pos4 + qi * nv : nullptr;
         float4 *nrm_q = nrm4 ? nrm4 + qi * nv : nullptr;
         // row task r: 0 = top skirt row, 1..n = vertex rows 0..n-1, n+1 = bottom skirt row
@@ -174,7 +174,7 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
             const int row_slot = (r == 0) ? 0 : (r == n + 1) ? n + n * w : n + (r - 1) * w;
             const int row_len = edge_row ? n : w;
             const float t = s_uv[vy], omt = 1.0f - t;
-            const float *h_mid = Hs + (vy + 1) * dim, *h_up = h_mid - dim, *h_dn = h_mid + dim;
+            const int row_off = (vy + 1) * dim;
             for (int c = lane; c < row_len; c += 32) {
                 const int vx = edge_row ? c : min(max(c - 1, 0), n - 1);
                 const float skirt = (edge_row || c == 0 || c == w - 1) ? 1.0f : 0.0f;
@@ -198,11 +198,12 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
                     float y = s_col[C_ISIN * np + vx] - itan / cosf(gamma);
                     vp = pp + pq * (0.5f * x) + vn * (y * s_col[C_HLEN * np + vx]);
                 }
-                const int tx = vx + 1;
-                const float hc = h_mid[tx];
+                const int ti = row_off + vx + 1;                     // texel (vx+1, vy+1)
+                float hc, hl, hr, hu, hd;
+                if (STAGE) { hc = s_h[ti]; hl = s_h[ti - 1]; hr = s_h[ti + 1]; hu = s_h[ti - dim]; hd = s_h[ti + dim]; }
+                else { hc = __ldg(H + ti); hl = __ldg(H + ti - 1); hr = __ldg(H + ti + 1); hu = __ldg(H + ti - dim); hd = __ldg(H + ti + dim); }
                 const float height = hc - skirt_size * skirt;        // main.cpp:360
-                float3 nt = normalize(f3(h_mid[tx - 1] - h_mid[tx + 1], s_col[C_XYS * np + vx],
-                                         h_up[tx] - h_dn[tx]));      // main.cpp:339-345
+                float3 nt = normalize(f3(hl - hr, s_col[C_XYS * np + vx], hu - hd));   // main.cpp:339-345
                 float3 tg = normalize(cross(vn, pq));                // main.cpp:363
                 // main.cpp:364-365 normalise bi = cross(t, n) and mat3(t, n, bi) * normal as well; t, n
                 // are unit and orthogonal by construction and |normal| = 1, so both lengths are
@@ -239,7 +240,8 @@ int launch_shade(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads
     size_t smem = np * sizeof(float) + (size_t)warps * per_warp;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     int dev = 0, sms = 148;
@@ -247,9 +249,14 @@ int launch_shade(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (warps * 32), budget / smem));
     int grid = (int)std::min<int64_t>((nquads + warps - 1) / warps, (int64_t)sms * per_sm);
-    shade::k_shade<<<grid, warps * 32, smem, stream>>>(
-        d_quads, nquads, n, cam[0], cam[1], cam[2], d_heights, max_skirt,
-        reinterpret_cast<float4 *>(d_pos4), reinterpret_cast<float4 *>(d_nrm4), stage, (int)per_warp);
+    if (stage)
+        shade::k_shade<true><<<grid, warps * 32, smem, stream>>>(
+            d_quads, nquads, n, cam[0], cam[1], cam[2], d_heights, max_skirt,
+            reinterpret_cast<float4 *>(d_pos4), reinterpret_cast<float4 *>(d_nrm4), (int)per_warp);
+    else
+        shade::k_shade<false><<<grid, warps * 32, smem, stream>>>(
+            d_quads, nquads, n, cam[0], cam[1], cam[2], d_heights, max_skirt,
+            reinterpret_cast<float4 *>(d_pos4), reinterpret_cast<float4 *>(d_nrm4), (int)per_warp);
     count_launch();
     return check_cuda(cudaGetLastError(), "shade kernel launch");
 }

@@ -40,6 +40,8 @@ static struct Staging {
     void *d_in = nullptr;     size_t d_in_cap = 0;
     void *d_out = nullptr;    size_t d_out_cap = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;           // D2H of finished chunks overlaps the next chunk's kernel
+    cudaEvent_t chunk_done[16] = {};
 } g_stage;
 
 int set_error(int code, const char *fmt, ...)
@@ -141,6 +143,10 @@ static int grow(void **ptr, size_t *cap, size_t need, bool pinned)
 static int stage_stream()
 {
     if (!g_stage.stream) PLANET_CUDA(cudaStreamCreateWithFlags(&g_stage.stream, cudaStreamNonBlocking));
+    if (!g_stage.copy_stream) {
+        PLANET_CUDA(cudaStreamCreateWithFlags(&g_stage.copy_stream, cudaStreamNonBlocking));
+        for (auto &e : g_stage.chunk_done) PLANET_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     return 0;
 }
 
@@ -196,6 +202,10 @@ void planet_gpu_shutdown(void)
     if (g_stage.d_in) cudaFree(g_stage.d_in);
     if (g_stage.d_out) cudaFree(g_stage.d_out);
     if (g_stage.stream) cudaStreamDestroy(g_stage.stream);
+    if (g_stage.copy_stream) {
+        cudaStreamDestroy(g_stage.copy_stream);
+        for (auto &e : g_stage.chunk_done) if (e) cudaEventDestroy(e);
+    }
     g_stage = Staging();
     g_ready = false;
 }
@@ -279,10 +289,26 @@ int planet_gpu_generate_height_maps_host(const planet_gpu_params *p, const plane
     // Caller memory may be pageable; cudaMemcpyAsync then stages through the driver's own
     // pinned buffers.  Callers that want full PCIe rate pass cudaHostRegister'ed memory.
     PLANET_CUDA(cudaMemcpyAsync(g_stage.d_in, h_quads, in_bytes, cudaMemcpyHostToDevice, g_stage.stream));
-    rc = launch_height_maps(p, (const Quad *)g_stage.d_in, nquads, dim, max_depth, d_out, g_stage.stream);
-    if (rc) return rc;
-    PLANET_CUDA(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, g_stage.stream));
+    // The output (dim*dim*4 bytes per quad) dominates the PCIe traffic, so large batches run as
+    // a pipeline: kernel on chunk c while chunk c-1 drains to the host on the copy stream.
+    const int chunks = nquads >= 4096 ? 16 : nquads >= 256 ? 4 : 1;
+    const size_t per_quad = (size_t)dim * dim;
+    for (int c = 0; c < chunks; c++) {
+        const int64_t lo = nquads * c / chunks, hi = nquads * (c + 1) / chunks;
+        if (hi == lo) continue;
+        rc = launch_height_maps(p, (const Quad *)g_stage.d_in + lo, hi - lo, dim, max_depth,
+                                d_out + lo * per_quad, g_stage.stream);
+        if (rc) return rc;
+        cudaStream_t cs = chunks > 1 ? g_stage.copy_stream : g_stage.stream;
+        if (chunks > 1) {
+            PLANET_CUDA(cudaEventRecord(g_stage.chunk_done[c], g_stage.stream));
+            PLANET_CUDA(cudaStreamWaitEvent(cs, g_stage.chunk_done[c], 0));
+        }
+        PLANET_CUDA(cudaMemcpyAsync(h_out + lo * per_quad, d_out + lo * per_quad,
+                                    (size_t)(hi - lo) * per_quad * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    }
     PLANET_CUDA(cudaStreamSynchronize(g_stage.stream));
+    if (chunks > 1) PLANET_CUDA(cudaStreamSynchronize(g_stage.copy_stream));
     return 0;
 }
 
