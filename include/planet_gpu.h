@@ -139,6 +139,15 @@ uint64_t planet_gpu_uniform_leaf_id(int64_t leaf, int depth);
 int   planet_gpu_max_lod(double radius, int patch_verts);          /* main.cpp:497 */
 float planet_gpu_max_skirt_size(double radius, int patch_verts);   /* main.cpp:500 */
 
+/* K0 (the caller of the path): camera-driven LOD selection, i.e. the leaf
+ * quads RenderPlanet/ProcessQuad (main.cpp:537-624) would put in planet.quads for a camera at
+ * cam_pos (HOST pointer, 3 doubles), in the same order, with bit-identical corners and ids.
+ * Split decisions evaluate GetHeightAt(p, 0, 1) in EXACT arithmetic whatever p->precision says.
+ * d_quads (DEVICE) must hold `capacity` quads; *count (HOST) receives the number of leaves.
+ * Synchronises `stream` once per quadtree level. */
+int planet_gpu_select_lod(const planet_gpu_params *p, const double *cam_pos, int max_lod,
+                          planet_gpu_quad *d_quads, int64_t capacity, int64_t *count, void *stream);
+
 /* K3: the GLSL stage (main.cpp:286-380) for every vertex of every quad, in the patch
  * vertex order of main.cpp:406-422.  d_heights holds the quads' own height maps
  * (dim = patch_verts + 2).  Outputs, nv float4 per quad:

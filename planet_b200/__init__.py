@@ -66,6 +66,7 @@ def lib():
             "planet_gpu_uniform_leaf_id": (C.c_uint64, [i64, i]),
             "planet_gpu_max_lod": (i, [d, i]),
             "planet_gpu_max_skirt_size": (f, [d, i]),
+            "planet_gpu_select_lod": (i, [pp, vp, i, vp, i64, C.POINTER(i64), vp]),
             "planet_gpu_shade": (i, [pp, vp, i64, vp, vp, f, vp, vp, vp]),
             "planet_gpu_generate_height_maps_host": (i, [pp, vp, i64, i, i, vp, vp]),
             "planet_gpu_measure_fp32_peak": (i, [d, C.POINTER(d), C.POINTER(d)]),
@@ -86,7 +87,7 @@ EXPORTED_SYMBOLS = [
     "planet_gpu_quads_from_ids", "planet_gpu_patch_mesh", "planet_gpu_patch_vertex_count",
     "planet_gpu_patch_index_count", "planet_gpu_strip_index", "planet_gpu_uniform_leaf_id",
     "planet_gpu_max_lod", "planet_gpu_max_skirt_size",
-    "planet_gpu_shade", "planet_gpu_generate_height_maps_host", "planet_gpu_measure_fp32_peak",
+    "planet_gpu_select_lod", "planet_gpu_shade", "planet_gpu_generate_height_maps_host", "planet_gpu_measure_fp32_peak",
     "planet_gpu_launch_count",
 ]
 
@@ -193,6 +194,20 @@ def patch_mesh(n=30, stream=None):
     i = torch.empty(patch_index_count(n), dtype=torch.int32, device="cuda")
     _check(lib().planet_gpu_patch_mesh(n, v.data_ptr(), i.data_ptr(), _stream(stream)))
     return v, i
+
+
+def select_lod(cam_pos, max_lod=None, params=None, capacity=65536, stream=None):
+    """K0: the leaf quads ProcessQuad/RenderPlanet (main.cpp:537-624) select for a camera, in the
+    reference's order.  Returns an int64[n,13] device tensor."""
+    torch = _torch()
+    params = params or default_params()
+    if max_lod is None:
+        max_lod = lib().planet_gpu_max_lod(params.radius, params.patch_verts)
+    buf = torch.empty((capacity, QUAD_WORDS), dtype=torch.int64, device="cuda")
+    cam = (C.c_double * 3)(*[float(c) for c in cam_pos])
+    n = C.c_int64(0)
+    _check(lib().planet_gpu_select_lod(C.byref(params), cam, max_lod, buf.data_ptr(), capacity, C.byref(n), _stream(stream)))
+    return buf[:n.value]
 
 
 def generate_height_maps(quads, dim, max_depth, params=None, out=None, stream=None):

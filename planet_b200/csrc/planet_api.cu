@@ -22,6 +22,7 @@ int launch_quads_from_ids(const planet_gpu_params *, const uint64_t *, int64_t, 
 int launch_patch_mesh(int, float *, uint32_t *, cudaStream_t);
 int launch_shade(const planet_gpu_params *, const Quad *, int64_t, const double *, const float *, float,
                  float *, float *, cudaStream_t);
+int launch_select_lod(const planet_gpu_params *, const double *, int, Quad *, int64_t, int64_t *, cudaStream_t);
 uint32_t host_strip_index(int, int);
 uint64_t host_uniform_leaf_id(int64_t, int);
 
@@ -419,6 +420,17 @@ int planet_gpu_shade(const planet_gpu_params *p, const planet_gpu_quad *d_quads,
     if (max_skirt < 0.0f) max_skirt = planet_gpu_max_skirt_size(p->radius, p->patch_verts);
     return launch_shade(p, (const Quad *)d_quads, nquads, cam_pos, d_heights, max_skirt, d_pos4, d_nrm4,
                         (cudaStream_t)stream);
+}
+
+int planet_gpu_select_lod(const planet_gpu_params *p, const double *cam_pos, int max_lod,
+                          planet_gpu_quad *d_quads, int64_t capacity, int64_t *count, void *stream)
+{
+    if (!ensure_init()) return PLANET_E_NO_DEVICE;
+    int rc = validate_params(p);
+    if (rc) return rc;
+    if (!cam_pos || !d_quads || !count) return set_error(PLANET_E_INVALID, "NULL argument");
+    if (max_lod < 0 || max_lod > 27) return set_error(PLANET_E_INVALID, "max_lod %d outside [0, 27]", max_lod);
+    return launch_select_lod(p, cam_pos, max_lod, (Quad *)d_quads, capacity, count, (cudaStream_t)stream);
 }
 
 int planet_gpu_measure_fp32_peak(double ms, double *tflops, double *elapsed_ms)

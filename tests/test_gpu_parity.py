@@ -147,6 +147,29 @@ def test_merged_index_buffer(gpu, golden):
 
 
 # ---------------------------------------------------------------------------------------------
+# K0: camera-driven LOD selection (ProcessQuad / RenderPlanet, main.cpp:537-624)
+# ---------------------------------------------------------------------------------------------
+def test_select_lod_reproduces_the_reference_default_frame(gpu, golden):
+    """planet.quads of the reference's first frame: 117 leaves, depths 0..10, same order, same bytes."""
+    got = gpu.quads_to_host(gpu.select_lod(golden["frame_cam"], int(golden["max_lod"])))
+    assert len(got) == 117
+    assert got.tobytes() == golden["frame_quads"].tobytes()
+
+
+def test_select_lod_other_cameras_against_the_reference(gpu, ref):
+    for cam in ([3.0e6, 5.0e6, -4.5e6], [0.0, 6371000.0 + 2000.0, 0.0], [-9.0e6, 1.0e5, 2.0e5], [0.0, 0.0, 0.0]):
+        want, _, _ = ref.render_frame(np.array(cam, np.float64))
+        got = gpu.quads_to_host(gpu.select_lod(cam))
+        assert len(got) == len(want), (cam, len(got), len(want))
+        assert got.tobytes() == want.tobytes(), cam
+
+
+def test_select_lod_capacity_error(gpu, golden):
+    with pytest.raises(gpu.PlanetGpuError, match="capacity"):
+        gpu.select_lod(golden["frame_cam"], capacity=40)
+
+
+# ---------------------------------------------------------------------------------------------
 # K2: GenerateHeightMap / GetHeightAt
 # ---------------------------------------------------------------------------------------------
 def test_default_frame_height_maps_exact_bits(gpu, golden):
