@@ -115,10 +115,18 @@ constexpr int THREADS = 512;
 constexpr int S = 2;                          // consecutive samples per thread (one f32x2 pair)
 constexpr int TILE = THREADS * S;             // samples per CTA iteration
 constexpr int ROWS = 512;                     // table index range: perm (<=255) + cell (<=255) + 1
-constexpr int T12_ROW = 128;                  // 32 lanes x u32
-constexpr int T3_ROW = 256;                   // 32 lanes x {u32 G(i), u32 G(i+1)}
-constexpr int T12_BYTES = ROWS * T12_ROW;     // 64 KB
-constexpr int T3_BYTES = ROWS * T3_ROW;       // 128 KB
+// Table layout for a replication factor REPL (copies of every entry per row): REPL = 32 gives
+// every lane its own bank (conflict-free, 192 KB, for throughput); REPL = 1 is the compact 6 KB
+// layout whose build costs nothing, used for small batches where latency is what matters.
+template <int REPL> struct Layout {
+    static constexpr int T12_ROW = REPL * 4;              // REPL x u32
+    static constexpr int T3_ROW = REPL * 8;               // REPL x {u32 G(i), u32 G(i+1)}
+    static constexpr int T12_BYTES = ROWS * T12_ROW;      // 64 KB at REPL 32
+    static constexpr int T3_BYTES = ROWS * T3_ROW;        // 128 KB at REPL 32
+    static constexpr int TABLES = T12_BYTES + T3_BYTES;
+    static constexpr int LOG12 = REPL == 32 ? 7 : REPL == 16 ? 6 : REPL == 8 ? 5 : REPL == 4 ? 4 : REPL == 2 ? 3 : 2;
+    static constexpr int LOG3 = LOG12 + 1;
+};
 constexpr double FIX_ONE = 36028797018963968.0;           // 2^55
 constexpr double FIX_WRAP = 256.0 * 36028797018963968.0;  // 2^63: one period of cell & 255
 
@@ -126,9 +134,13 @@ constexpr double FIX_WRAP = 256.0 * 36028797018963968.0;  // 2^63: one period of
 struct AxisCoef { double a, b, c, d; };
 struct TileQuad { AxisCoef ax[3]; int octaves; int wide; };
 
-constexpr int SMEM_TABLES = T12_BYTES + T3_BYTES;
-constexpr int smem_bytes(int nthreads) { return SMEM_TABLES + (nthreads / 32) * (128 / 16 + 2) * (int)sizeof(TileQuad); }
-constexpr int SMEM_BYTES = smem_bytes(768);
+template <int REPL> constexpr int smem_bytes(int nthreads)
+{
+    // tables + per-warp quad scratch (never less than the 2 KB the table build stages through)
+    return Layout<REPL>::TABLES + ((nthreads / 32) * (128 / 16 + 2) * (int)sizeof(TileQuad) > 2048
+                                       ? (nthreads / 32) * (128 / 16 + 2) * (int)sizeof(TileQuad) : 2048);
+}
+constexpr int SMEM_BYTES = smem_bytes<32>(768);
 
 // ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, one issue slot for two lanes) ----
 typedef unsigned long long f2;
@@ -162,24 +174,26 @@ __device__ __forceinline__ uint32_t grad_code(int h)
     return (byte(g[0]) << 24) | (byte(g[1]) << 8) | byte(g[2]);
 }
 
-// Build the lane-replicated tables (perm = table[i & 255]):
-//   T12[i][lane] = (perm*128) | (perm*256) << 16      next-row byte offsets for levels 1 and 2
-//   T3 [i][lane] = { G(table[i]), G(table[i+1]) }     both z-neighbours' gradients in one LDS.64
+// Build the (lane-replicated) tables, perm = table[i & 255]:
+//   T12[i][copy] = (perm*T12_ROW) | (perm*T3_ROW) << 16   next-row byte offsets for levels 1 and 2
+//   T3 [i][copy] = { G(table[i]), G(table[i+1]) }         both z-neighbours' gradients in one LDS.64
+template <int REPL>
 __device__ void build_tables(unsigned char *smem)
 {
+    using L = Layout<REPL>;
     uint32_t *t12 = reinterpret_cast<uint32_t *>(smem);
-    uint2 *t3 = reinterpret_cast<uint2 *>(smem + T12_BYTES);
+    uint2 *t3 = reinterpret_cast<uint2 *>(smem + L::T12_BYTES);
     // stage {perm, code(perm)} for the 256 table entries in the (not yet used) scratch area
-    uint2 *stage = reinterpret_cast<uint2 *>(smem + T12_BYTES + T3_BYTES);
+    uint2 *stage = reinterpret_cast<uint2 *>(smem + L::TABLES);
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         uint32_t p = g_perm[i];
         stage[i] = make_uint2(p, grad_code(p));
     }
     __syncthreads();
-    for (int w = threadIdx.x; w < ROWS * 32; w += blockDim.x) {
-        int i = w >> 5;
+    for (int w = threadIdx.x; w < ROWS * REPL; w += blockDim.x) {
+        int i = w / REPL;
         uint2 e0 = stage[i & 255], e1 = stage[(i + 1) & 255];
-        t12[w] = (e0.x << 7) | (e0.x << 24);
+        t12[w] = (e0.x << L::LOG12) | (e0.x << (16 + L::LOG3));       // next-row byte offsets, levels 1 and 2
         t3[w] = make_uint2(e0.y, e1.y);
     }
 }
@@ -209,9 +223,12 @@ struct Fixed3 { uint32_t xlo, xhi, ylo, yhi, zlo, zhi; };
 // {z, z+1} gradient-code pairs of the (x, y) columns 00, 10, 01, 11 and the three fractions
 struct Hashed { uint2 e00, e10, e01, e11; float mx, my, mz; };
 
+template <int REPL>
 __device__ __forceinline__ Hashed hash_octave(const unsigned char *t12_lane, const unsigned char *t3_lane,
                                               const Fixed3 &p, int k)
 {
+    using L = Layout<REPL>;
+    constexpr int T12_ROW = L::T12_ROW, T3_ROW = L::T3_ROW;
     // 32-bit windows of the fixed-point coordinate: bits 30..23 = cell & 255, 22..0 = fraction
     uint32_t wx = __funnelshift_l(p.xlo, p.xhi, k);
     uint32_t wy = __funnelshift_l(p.ylo, p.yhi, k);
@@ -220,9 +237,9 @@ __device__ __forceinline__ Hashed hash_octave(const unsigned char *t12_lane, con
     h.mx = __uint_as_float((wx & 0x007FFFFFu) | 0x3F800000u);       // 1 + fraction, 23 bits
     h.my = __uint_as_float((wy & 0x007FFFFFu) | 0x3F800000u);
     h.mz = __uint_as_float((wz & 0x007FFFFFu) | 0x3F800000u);
-    uint32_t cx = (wx >> 16) & 0x7F80u;                             // (cell & 255) * 128
-    uint32_t cy = (wy >> 16) & 0x7F80u;
-    uint32_t cz = (wz >> 15) & 0xFF00u;                             // (cell & 255) * 256
+    uint32_t cx = (wx >> (23 - L::LOG12)) & (255u << L::LOG12);     // (cell & 255) * T12_ROW
+    uint32_t cy = (wy >> (23 - L::LOG12)) & (255u << L::LOG12);
+    uint32_t cz = (wz >> (23 - L::LOG3)) & (255u << L::LOG3);       // (cell & 255) * T3_ROW
     uint32_t a0 = lds_u16(t12_lane, cx), a1 = lds_u16(t12_lane, cx + T12_ROW);   // R(ix), R(ix+1) (*128)
     uint32_t b00 = lds_u16(t12_lane, a0 + cy + 2), b01 = lds_u16(t12_lane, a0 + cy + 2 + T12_ROW);
     uint32_t b10 = lds_u16(t12_lane, a1 + cy + 2), b11 = lds_u16(t12_lane, a1 + cy + 2 + T12_ROW);
@@ -230,15 +247,17 @@ __device__ __forceinline__ Hashed hash_octave(const unsigned char *t12_lane, con
     h.e10 = lds_v2(t3_lane, b10 + cz);
     h.e01 = lds_v2(t3_lane, b01 + cz);
     h.e11 = lds_v2(t3_lane, b11 + cz);
+    (void)T3_ROW;
     return h;
 }
 
 // 2 * PerlinNoise3 of octave k for the thread's two samples (perlin.h:50-88)
+template <int REPL>
 __device__ __forceinline__ f2 noise_octave2(const unsigned char *t12_lane, const unsigned char *t3_lane,
                                             const Fixed3 &pa, const Fixed3 &pb, int k)
 {
-    Hashed A = hash_octave(t12_lane, t3_lane, pa, k);
-    Hashed B = hash_octave(t12_lane, t3_lane, pb, k);
+    Hashed A = hash_octave<REPL>(t12_lane, t3_lane, pa, k);
+    Hashed B = hash_octave<REPL>(t12_lane, t3_lane, pb, k);
     f2 mx = pack(A.mx, B.mx), my = pack(A.my, B.my), mz = pack(A.mz, B.mz);
     f2 x0 = add2(mx, splat(-1.0f)), x1 = add2(mx, splat(-2.0f));    // fraction, fraction - 1 (exact)
     f2 y0 = add2(my, splat(-1.0f)), y1 = add2(my, splat(-2.0f));
@@ -258,7 +277,7 @@ __device__ __forceinline__ f2 noise_octave2(const unsigned char *t12_lane, const
 
 // fractal sum over octaves for the two samples (main.cpp:689-734 with FMA).  `half_amp`
 // carries amplitude/2 because noise_octave2 returns 2*noise.
-template <bool GUARD>
+template <int REPL, bool GUARD>
 __device__ __forceinline__ void fractal_loop(const unsigned char *t12_lane, const unsigned char *t3_lane,
                                              const Fixed3 (&p)[S], const int (&octaves)[S], int omax,
                                              int kind, float gain, float (&value)[S])
@@ -269,7 +288,7 @@ __device__ __forceinline__ void fractal_loop(const unsigned char *t12_lane, cons
         value[0] = value[1] = 0.0f;
         for (int k = 0; k < omax; k++) {
             float n[S];
-            unpack(noise_octave2(t12_lane, t3_lane, p[0], p[1], k), n[0], n[1]);
+            unpack(noise_octave2<REPL>(t12_lane, t3_lane, p[0], p[1], k), n[0], n[1]);
 #pragma unroll
             for (int s = 0; s < S; s++) {
                 float v = fmaf(-0.5f, fabsf(n[s]), 1.0f);           // offset - |noise|
@@ -282,7 +301,7 @@ __device__ __forceinline__ void fractal_loop(const unsigned char *t12_lane, cons
     } else {                                                         // main.cpp:699-704
         f2 acc = splat(0.0f);
         for (int k = 0; k < omax; k++) {
-            f2 n = noise_octave2(t12_lane, t3_lane, p[0], p[1], k);
+            f2 n = noise_octave2<REPL>(t12_lane, t3_lane, p[0], p[1], k);
             if (GUARD) {
                 float lo, hi, alo, ahi;
                 unpack(fma2(n, splat(half_amp), acc), lo, hi);
@@ -297,13 +316,14 @@ __device__ __forceinline__ void fractal_loop(const unsigned char *t12_lane, cons
     }
 }
 
+template <int REPL>
 __device__ __forceinline__ void fractal(const unsigned char *t12_lane, const unsigned char *t3_lane,
                                         const Fixed3 (&p)[S], const int (&octaves)[S], int kind,
                                         float gain, float (&value)[S])
 {
     int omax = max(octaves[0], octaves[1]);
-    if (octaves[0] == octaves[1]) fractal_loop<false>(t12_lane, t3_lane, p, octaves, omax, kind, gain, value);
-    else                          fractal_loop<true>(t12_lane, t3_lane, p, octaves, omax, kind, gain, value);
+    if (octaves[0] == octaves[1]) fractal_loop<REPL, false>(t12_lane, t3_lane, p, octaves, omax, kind, gain, value);
+    else                          fractal_loop<REPL, true>(t12_lane, t3_lane, p, octaves, omax, kind, gain, value);
 }
 
 // reduce a scaled coordinate (units of 2^-55) to one period and convert to fixed point
@@ -330,21 +350,22 @@ constexpr int SUB = 2;
 constexpr int WTILE = 32 * S * SUB;                      // 128 samples per warp tile
 constexpr int MAX_WTILE_QUADS = WTILE / 16 + 2;          // dim >= 4
 
-template <int NTHREADS>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int NTHREADS, int REPL>
+__global__ void __launch_bounds__(NTHREADS, REPL == 32 ? 1 : 2)
 k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, HeightCfg cfg,
                    float *__restrict__ out, int64_t nwtiles, int out_aligned8,
                    uint64_t magic_dim, uint64_t magic_dim2)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    build_tables(smem);
+    using L = Layout<REPL>;
+    build_tables<REPL>(smem);
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int WARPS = NTHREADS / 32;
-    TileQuad *tq = reinterpret_cast<TileQuad *>(smem + T12_BYTES + T3_BYTES) + warp * MAX_WTILE_QUADS;
-    const unsigned char *t12_lane = smem + lane * 4;
-    const unsigned char *t3_lane = smem + T12_BYTES + lane * 8;
+    TileQuad *tq = reinterpret_cast<TileQuad *>(smem + L::TABLES) + warp * MAX_WTILE_QUADS;
+    const unsigned char *t12_lane = smem + (lane % REPL) * 4;
+    const unsigned char *t3_lane = smem + L::T12_BYTES + (lane % REPL) * 8;
     const uint32_t dim2 = (uint32_t)dim * (uint32_t)dim;
     const bool small_maps = dim2 < (uint32_t)WTILE;          // a warp tile may then span > 2 quads
     const double div = 1.0 / (double)(dim - 3);
@@ -429,7 +450,7 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
             if (cfg.kind == PLANET_NOISE_ZERO) {
                 value[0] = value[1] = 0.0f;
             } else {
-                fractal(t12_lane, t3_lane, p, oct, cfg.kind, cfg.gain, value);
+                fractal<REPL>(t12_lane, t3_lane, p, oct, cfg.kind, cfg.gain, value);
             }
 
             float *dst = out + base + i0;                                    // base + i0 is even
@@ -450,17 +471,18 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
 
 // ---- points: batched GetHeightAt and raw noise ----------------------------------------
 // scale / seed / height_scale == 1 / 0 / 1 and octaves0 == 1 give PerlinNoise3 itself.
-__global__ void __launch_bounds__(THREADS, 1)
+template <int REPL>
+__global__ void __launch_bounds__(THREADS, REPL == 32 ? 1 : 2)
 k_points_fast(const double *__restrict__ xyz, int64_t n, int kind, float gain, int octaves,
               double coord_scale, double sx, double sy, double sz, float height_scale,
               float *__restrict__ out, int64_t ntiles)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    build_tables(smem);
+    build_tables<REPL>(smem);
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const unsigned char *t12_lane = smem + lane * 4;
-    const unsigned char *t3_lane = smem + T12_BYTES + lane * 8;
+    const unsigned char *t12_lane = smem + (lane % REPL) * 4;
+    const unsigned char *t3_lane = smem + Layout<REPL>::T12_BYTES + (lane % REPL) * 8;
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         // samples of one thread are strided by THREADS so the 24-byte point loads and the
@@ -484,7 +506,7 @@ k_points_fast(const double *__restrict__ xyz, int64_t n, int kind, float gain, i
             oct[s] = octaves;
         }
         float value[S];
-        fractal(t12_lane, t3_lane, p, oct, kind, gain, value);
+        fractal<REPL>(t12_lane, t3_lane, p, oct, kind, gain, value);
 #pragma unroll
         for (int s = 0; s < S; s++)
             if (idx[s] < n) out[idx[s]] = value[s] * height_scale;
@@ -521,18 +543,38 @@ static int k2_threads()
     return t;
 }
 
+// batches of at most this many samples use the compact-table kernels (no 192 KB table build)
+static int64_t k2_small_max()
+{
+    static int64_t v = -1;
+    if (v < 0) {
+        const char *e = getenv("PLANET_K2_SMALL_MAX");
+        v = e ? atoll(e) : (1 << 20);
+    }
+    return v;
+}
+
 static int prepare_fast()
 {
     if (!g_fast_attr_set) {
-        PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_fast<512>,
+        PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_fast<512, 32>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
-        PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_fast<768>,
+        PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_fast<768, 32>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
-        PLANET_CUDA(cudaFuncSetAttribute(fast::k_points_fast,
+        PLANET_CUDA(cudaFuncSetAttribute(fast::k_points_fast<32>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
         g_fast_attr_set = true;
     }
     return 0;
+}
+
+template <int REPL>
+static void launch_points(int grid, cudaStream_t stream, const double *d_xyz, int64_t n, int kind, float gain,
+                          int octaves, double scale, double sx, double sy, double sz, float hs, float *d_out,
+                          int64_t ntiles)
+{
+    fast::k_points_fast<REPL><<<grid, fast::THREADS, fast::smem_bytes<REPL>(fast::THREADS), stream>>>(
+        d_xyz, n, kind, gain, octaves, scale, sx, sy, sz, hs, d_out, ntiles);
 }
 
 // FAST handles the lattice split as shifts, which needs lacunarity == 2 and every octave's
@@ -557,15 +599,22 @@ int launch_height_maps(const planet_gpu_params *p, const Quad *d_quads, int64_t 
     if (use_fast) {
         int rc = prepare_fast();
         if (rc) return rc;
-        const int nt = k2_threads();
         int64_t nwtiles = (total + fast::WTILE - 1) / fast::WTILE;
-        int grid = (int)std::min<int64_t>((nwtiles + nt / 32 - 1) / (nt / 32), sm_count());
         const uint64_t one40 = 1ull << 40;
         const uint64_t m1 = (one40 + dim - 1) / dim, m2 = (one40 + (uint64_t)dim * dim - 1) / ((uint64_t)dim * dim);
         const int al = (reinterpret_cast<uintptr_t>(d_out) & 7) == 0;
-        const size_t sm = fast::smem_bytes(nt);
-        if (nt == 512) fast::k_height_maps_fast<512><<<grid, 512, sm, stream>>>(d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2);
-        else           fast::k_height_maps_fast<768><<<grid, 768, sm, stream>>>(d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2);
+        if (total <= k2_small_max()) {
+            // latency path: compact tables (6 KB), 256-thread CTAs spread over the whole chip
+            int grid = (int)std::min<int64_t>((nwtiles + 7) / 8, (int64_t)sm_count() * 8);
+            fast::k_height_maps_fast<256, 1><<<grid, 256, fast::smem_bytes<1>(256), stream>>>(
+                d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2);
+        } else {
+            const int nt = k2_threads();
+            int grid = (int)std::min<int64_t>((nwtiles + nt / 32 - 1) / (nt / 32), sm_count());
+            const size_t sm = fast::smem_bytes<32>(nt);
+            if (nt == 512) fast::k_height_maps_fast<512, 32><<<grid, 512, sm, stream>>>(d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2);
+            else           fast::k_height_maps_fast<768, 32><<<grid, 768, sm, stream>>>(d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2);
+        }
     } else {
         int64_t blocks = (total + 255) / 256;
         int grid = (int)std::min<int64_t>(blocks, (int64_t)sm_count() * 8);
@@ -587,11 +636,14 @@ int launch_heights_at(const planet_gpu_params *p, const double *d_xyz, int64_t n
         int rc = prepare_fast();
         if (rc) return rc;
         int64_t ntiles = (n + fast::TILE - 1) / fast::TILE;
-        int grid = (int)std::min<int64_t>(ntiles, sm_count());
-        fast::k_points_fast<<<grid, fast::THREADS, fast::SMEM_BYTES, stream>>>(
-            d_xyz, n, cfg.kind, cfg.gain, octaves, cfg.coord_scale,
-            cfg.has_seed ? cfg.seed[0] : 0.0, cfg.has_seed ? cfg.seed[1] : 0.0,
-            cfg.has_seed ? cfg.seed[2] : 0.0, cfg.height_scale, d_out, ntiles);
+        const double s0 = cfg.has_seed ? cfg.seed[0] : 0.0, s1 = cfg.has_seed ? cfg.seed[1] : 0.0,
+                     s2 = cfg.has_seed ? cfg.seed[2] : 0.0;
+        if (n <= k2_small_max())
+            launch_points<1>((int)std::min<int64_t>(ntiles, (int64_t)sm_count() * 2), stream, d_xyz, n, cfg.kind, cfg.gain,
+                             octaves, cfg.coord_scale, s0, s1, s2, cfg.height_scale, d_out, ntiles);
+        else
+            launch_points<32>((int)std::min<int64_t>(ntiles, sm_count()), stream, d_xyz, n, cfg.kind, cfg.gain,
+                              octaves, cfg.coord_scale, s0, s1, s2, cfg.height_scale, d_out, ntiles);
     } else {
         int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8);
         k_heights_at_exact<<<grid, 256, 0, stream>>>(d_xyz, n, depth, cfg, d_out);
@@ -608,11 +660,14 @@ int launch_noise(const double *d_xyz, int64_t n, int kind, double lacunarity, fl
         int rc = prepare_fast();
         if (rc) return rc;
         int64_t ntiles = (n + fast::TILE - 1) / fast::TILE;
-        int grid = (int)std::min<int64_t>(ntiles, sm_count());
         // a single PerlinNoise3 is a 1-octave fBm with amplitude 1
-        fast::k_points_fast<<<grid, fast::THREADS, fast::SMEM_BYTES, stream>>>(
-            d_xyz, n, octaves == 0 ? PLANET_NOISE_FBM : kind, gain, octaves == 0 ? 1 : octaves,
-            1.0, 0.0, 0.0, 0.0, 1.0f, d_out, ntiles);
+        const int k = octaves == 0 ? PLANET_NOISE_FBM : kind, o = octaves == 0 ? 1 : octaves;
+        if (n <= k2_small_max())
+            launch_points<1>((int)std::min<int64_t>(ntiles, (int64_t)sm_count() * 2), stream, d_xyz, n, k, gain, o,
+                             1.0, 0.0, 0.0, 0.0, 1.0f, d_out, ntiles);
+        else
+            launch_points<32>((int)std::min<int64_t>(ntiles, sm_count()), stream, d_xyz, n, k, gain, o,
+                              1.0, 0.0, 0.0, 0.0, 1.0f, d_out, ntiles);
     } else {
         int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8);
         k_noise_exact<<<grid, 256, 0, stream>>>(d_xyz, n, kind, lacunarity, gain, octaves, d_out);

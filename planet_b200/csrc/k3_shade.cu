@@ -105,6 +105,7 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
     float *s_col = reinterpret_cast<float *>(mine + 128);            // COL_ARRAYS x np floats
     float *s_h = s_col + COL_ARRAYS * np;                            // dim2 floats (if staged)
     const double div = __ddiv_rn(1.0, (double)(n - 1));              // main.cpp:404
+    const unsigned magic_w = (unsigned)(((1ull << 32) + (unsigned)w - 1) / (unsigned)w);   // ceil(2^32 / w)
 
     for (int i = threadIdx.x; i < n; i += blockDim.x)                // UV.x / UV.y values, main.cpp:406-420
         s_uv[i] = __double2float_rn(__dmul_rn((double)i, div));
@@ -167,17 +168,25 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
         }
         float4 *pos_q = pos4 ? pos4 + qi * nv : nullptr;
         float4 *nrm_q = nrm4 ? nrm4 + qi * nv : nullptr;
-        // row task r: 0 = top skirt row, 1..n = vertex rows 0..n-1, n+1 = bottom skirt row
-        for (int r = 0; r < n + 2; r++) {
-            const bool edge_row = (r == 0) || (r == n + 1);
-            const int vy = min(max(r - 1, 0), n - 1);
-            const int row_slot = (r == 0) ? 0 : (r == n + 1) ? n + n * w : n + (r - 1) * w;
-            const int row_len = edge_row ? n : w;
-            const float t = s_uv[vy], omt = 1.0f - t;
-            const int row_off = (vy + 1) * dim;
-            for (int c = lane; c < row_len; c += 32) {
-                const int vx = edge_row ? c : min(max(c - 1, 0), n - 1);
-                const float skirt = (edge_row || c == 0 || c == w - 1) ? 1.0f : 0.0f;
+        // The warp walks the quad's nv vertex slots 32 at a time (main.cpp:406-422 order: n top-skirt
+        // slots, n rows of n+2, n bottom-skirt slots); a lane's slot gives its row and column.  For
+        // the reference's n = 30 a 32-slot step is exactly one row; for other sizes lanes of one
+        // step may sit on two rows, which costs nothing since everything below is per lane.
+        for (int i0 = 0; i0 < nv; i0 += 32) {
+            const int i = i0 + lane;
+            if (i < nv) {
+                int vx, vy; float skirt;
+                if (i < n) { vx = i; vy = 0; skirt = 1.0f; }
+                else if (i < n + n * w) {
+                    const int r = i - n;
+                    vy = (int)__umulhi((unsigned)r, magic_w);             // r / w, exact for r < 2^16, w <= 256
+                    const int c = r - vy * w;
+                    vx = min(max(c - 1, 0), n - 1);
+                    skirt = (c == 0 || c == w - 1) ? 1.0f : 0.0f;
+                } else { vx = i - n - n * w; vy = n - 1; skirt = 1.0f; }
+                const float t = s_uv[vy], omt = 1.0f - t;
+                const int row_off = (vy + 1) * dim;
+                const int c = 0, row_slot = i;                            // output slot = i
                 const float3 pp = f3(s_col[C_PPX * np + vx], s_col[C_PPY * np + vx], s_col[C_PPZ * np + vx]);
                 const float3 pn = f3(s_col[C_PNX * np + vx], s_col[C_PNY * np + vx], s_col[C_PNZ * np + vx]);
                 const float3 pq = f3(s_col[C_PQX * np + vx], s_col[C_PQY * np + vx], s_col[C_PQZ * np + vx]);
