@@ -18,6 +18,7 @@
 #include "planet_common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace planet {
 

@@ -30,6 +30,7 @@
 #include "planet_common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace planet {
 
@@ -245,7 +246,9 @@ int launch_shade(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads
     const size_t budget = 200 * 1024;
     const int stage = (col_bytes + hbytes) <= budget;               // else the stencil reads go to L1/L2
     const size_t per_warp = col_bytes + (stage ? hbytes : 0);
-    int warps = (int)std::max<size_t>(1, std::min<size_t>(shade::WARPS, (budget - np * sizeof(float)) / per_warp));
+    int want_warps = shade::WARPS;
+    if (const char *e = getenv("PLANET_K3_WARPS")) want_warps = std::max(1, std::min(8, atoi(e)));   // tuning knob
+    int warps = (int)std::max<size_t>(1, std::min<size_t>(want_warps, (budget - np * sizeof(float)) / per_warp));
     size_t smem = np * sizeof(float) + (size_t)warps * per_warp;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
