@@ -226,14 +226,15 @@ __global__ void k_patch_mesh(int n, float *__restrict__ verts, uint32_t *__restr
 // =====================================================================================
 static int sm_count_k1()
 {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+    static int n[64] = {};                                           // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!n[dev]) {
+        cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (n[dev] <= 0) n[dev] = 148;
     }
-    return n;
+    return n[dev];
 }
 
 int launch_tessellate_uniform(const planet_gpu_params *p, int depth, int64_t first, int64_t nquads,

@@ -538,18 +538,25 @@ k_points_fast(const double *__restrict__ xyz, int64_t n, int kind, float gain, i
 // =====================================================================================
 // host-side launchers
 // =====================================================================================
-static int g_sm_count = 0;
-static bool g_fast_attr_set = false;
+// per-device caches (a process may drive several GPUs)
+static int g_sm_count[64] = {};
+static bool g_fast_attr_set[64] = {};
+
+static int current_device()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev & 63;
+}
 
 static int sm_count()
 {
-    if (!g_sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sm_count <= 0) g_sm_count = 148;
+    const int dev = current_device();
+    if (!g_sm_count[dev]) {
+        cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count[dev] <= 0) g_sm_count[dev] = 148;
     }
-    return g_sm_count;
+    return g_sm_count[dev];
 }
 
 static int k2_threads()
@@ -576,14 +583,15 @@ static int64_t k2_small_max()
 
 static int prepare_fast()
 {
-    if (!g_fast_attr_set) {
+    const int dev = current_device();
+    if (!g_fast_attr_set[dev]) {
         PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_fast<512, 32>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
         PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_fast<768, 32>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
         PLANET_CUDA(cudaFuncSetAttribute(fast::k_points_fast<32>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
-        g_fast_attr_set = true;
+        g_fast_attr_set[dev] = true;
     }
     return 0;
 }

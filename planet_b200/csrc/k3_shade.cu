@@ -250,15 +250,15 @@ int launch_shade(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads
     if (const char *e = getenv("PLANET_K3_WARPS")) want_warps = std::max(1, std::min(8, atoi(e)));   // tuning knob
     int warps = (int)std::max<size_t>(1, std::min<size_t>(want_warps, (budget - np * sizeof(float)) / per_warp));
     size_t smem = np * sizeof(float) + (size_t)warps * per_warp;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static size_t configured[64] = {};                               // per device
+    if (smem > 48 * 1024 && smem > configured[dev & 63]) {
+        PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev & 63] = smem;
+    }
     int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (warps * 32), budget / smem));
     int grid = (int)std::min<int64_t>((nquads + warps - 1) / warps, (int64_t)sms * per_sm);
     if (stage)
