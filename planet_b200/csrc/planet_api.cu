@@ -42,7 +42,7 @@ static struct Staging {
     void *d_out = nullptr;    size_t d_out_cap = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;           // D2H of finished chunks overlaps the next chunk's kernel
-    cudaEvent_t chunk_done[16] = {};
+    cudaEvent_t chunk_done[8] = {};
 } g_stage;
 
 int set_error(int code, const char *fmt, ...)
@@ -292,7 +292,7 @@ int planet_gpu_generate_height_maps_host(const planet_gpu_params *p, const plane
     PLANET_CUDA(cudaMemcpyAsync(g_stage.d_in, h_quads, in_bytes, cudaMemcpyHostToDevice, g_stage.stream));
     // The output (dim*dim*4 bytes per quad) dominates the PCIe traffic, so large batches run as
     // a pipeline: kernel on chunk c while chunk c-1 drains to the host on the copy stream.
-    const int chunks = nquads >= 4096 ? 16 : nquads >= 256 ? 4 : 1;
+    const int chunks = nquads >= 4096 ? 8 : nquads >= 256 ? 4 : 1;
     const size_t per_quad = (size_t)dim * dim;
     for (int c = 0; c < chunks; c++) {
         const int64_t lo = nquads * c / chunks, hi = nquads * (c + 1) / chunks;
