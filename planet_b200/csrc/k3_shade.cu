@@ -36,7 +36,7 @@ namespace planet {
 
 namespace shade {
 
-constexpr int THREADS = 256;
+constexpr int THREADS = 128;        // 4 warps per CTA, up to 6 CTAs per SM: best of the sweep in tools/k3_sweep.py
 constexpr int WARPS = THREADS / 32;
 constexpr int COL_ARRAYS = 17;       // floats kept per column (SoA)
 
@@ -259,7 +259,8 @@ int launch_shade(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads
         PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev & 63] = smem;
     }
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (warps * 32), budget / smem));
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(6, 2048 / (warps * 32)), budget / smem));
+    if (const char *e = getenv("PLANET_K3_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));   // tuning knob
     int grid = (int)std::min<int64_t>((nquads + warps - 1) / warps, (int64_t)sms * per_sm);
     if (stage)
         shade::k_shade<true><<<grid, warps * 32, smem, stream>>>(
