@@ -247,7 +247,7 @@ int launch_shade(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads
     const int stage = (col_bytes + hbytes) <= budget;               // else the stencil reads go to L1/L2
     const size_t per_warp = col_bytes + (stage ? hbytes : 0);
     int want_warps = shade::WARPS;
-    if (const char *e = getenv("PLANET_K3_WARPS")) want_warps = std::max(1, std::min(8, atoi(e)));   // tuning knob
+    if (const char *e = getenv("PLANET_K3_WARPS")) want_warps = std::max(1, std::min(shade::WARPS, atoi(e)));   // tuning knob
     int warps = (int)std::max<size_t>(1, std::min<size_t>(want_warps, (budget - np * sizeof(float)) / per_warp));
     size_t smem = np * sizeof(float) + (size_t)warps * per_warp;
     int dev = 0, sms = 148;
