@@ -36,6 +36,7 @@
 //    (same sample points as main.cpp:132-146 up to 1 ulp of double), so a sample's
 //    position costs 3 DFMA + one F2I per axis.
 #include "planet_common.cuh"
+#include "planet_call_surface.cuh"
 
 #include <algorithm>
 
@@ -87,21 +88,19 @@ k_heights_at_exact(const double *__restrict__ xyz, int64_t n, int depth, HeightC
     }
 }
 
-// raw PerlinNoise3 (octaves == 0) / PerlinfBm / PerlinRidged on points
+// raw PerlinNoise3 (octaves == 0) / PerlinfBm / PerlinRidged on points, through the
+// reference-named device functions of planet_call_surface.cuh
 __global__ void __launch_bounds__(256)
 k_noise_exact(const double *__restrict__ xyz, int64_t n, int kind, double lacunarity, float gain,
               int octaves, float *__restrict__ out)
 {
-    __shared__ unsigned char s_perm[256];
-    __shared__ float s_grad[48];
-    stage_small_tables(s_perm, s_grad);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
         float v;
-        if (octaves == 0) v = exact::noise3(s_perm, s_grad, x, y, z);
-        else if (kind == PLANET_NOISE_RIDGED) v = exact::ridged(s_perm, s_grad, x, y, z, lacunarity, gain, octaves);
-        else v = exact::fbm(s_perm, s_grad, x, y, z, lacunarity, gain, octaves);
+        if (octaves == 0) v = PerlinNoise3(x, y, z);
+        else if (kind == PLANET_NOISE_RIDGED) v = PerlinRidged(x, y, z, lacunarity, gain, octaves);
+        else v = PerlinfBm(x, y, z, lacunarity, gain, octaves);
         out[i] = v;
     }
 }

@@ -91,3 +91,13 @@ def test_product_never_touches_the_oracle():
                     if re.search(r"oracle|libplanet_ref|planet_oracle", text):
                         bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_vector_call_surface_on_the_host(tmp_path):
+    """vec3.h / math.h names as __host__ __device__ functions (planet_call_surface.cuh), host half."""
+    import subprocess
+    exe = str(tmp_path / "call_surface_host_test")
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-std=c++17", "-O1", "-o", exe,
+                           os.path.join(ROOT, "tests", "call_surface_host_test.cu")])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    assert "call surface ok" in out
