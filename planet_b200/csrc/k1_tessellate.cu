@@ -175,11 +175,41 @@ k_tessellate_fused(int depth, int64_t first, int64_t nquads, double radius, Quad
             store_quad(quads + i, quad_from_id(uniform_leaf_id(first + i, depth), radius));
         return;
     }
-    for (int k = threadIdx.x; k < ni; k += blockDim.x) s_strip[k] = strip_index(k, n);
-    __syncthreads();
+    // Each thread owns up to KV vectors of the strip (slots t, t + 256, ...) in REGISTERS and
+    // walks the quads: the loop body is pure address arithmetic + streaming stores, no loads.
+    constexpr int KV = 4;                                  // 4 x 256 threads x VEC indices >= ni for n <= ~44
     const int nvec = ni / VEC;
     const int64_t qstride = (int64_t)gridDim.x - quad_blocks;
-    for (int64_t q = (int64_t)blockIdx.x - quad_blocks; q < nquads; q += qstride) {
+    const int64_t q0 = (int64_t)blockIdx.x - quad_blocks;
+    if (nvec <= KV * (int)blockDim.x) {
+        uint32_t reg[KV][VEC];
+#pragma unroll
+        for (int j = 0; j < KV; j++) {
+            const int v = threadIdx.x + j * blockDim.x;
+#pragma unroll
+            for (int e = 0; e < VEC; e++) reg[j][e] = v < nvec ? strip_index(v * VEC + e, n) : 0u;
+        }
+        for (int64_t q = q0; q < nquads; q += qstride) {
+            const uint32_t base = (uint32_t)q * (uint32_t)nv;
+            uint32_t *dst = indices + q * ni;
+#pragma unroll
+            for (int j = 0; j < KV; j++) {
+                const int v = threadIdx.x + j * blockDim.x;
+                if (v < nvec) {
+                    if (VEC == 4)
+                        __stcs(reinterpret_cast<uint4 *>(dst) + v,
+                               make_uint4(reg[j][0] + base, reg[j][1] + base, reg[j][2] + base, reg[j][3 % VEC] + base));
+                    else
+                        __stcs(reinterpret_cast<uint2 *>(dst) + v, make_uint2(reg[j][0] + base, reg[j][1] + base));
+                }
+            }
+        }
+        return;
+    }
+    // large patches: stage the strip in shared memory instead
+    for (int k = threadIdx.x; k < ni; k += blockDim.x) s_strip[k] = strip_index(k, n);
+    __syncthreads();
+    for (int64_t q = q0; q < nquads; q += qstride) {
         const uint32_t base = (uint32_t)q * (uint32_t)nv;
         if (VEC == 4) {
             uint4 *dst = reinterpret_cast<uint4 *>(indices + q * ni);
