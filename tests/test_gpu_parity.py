@@ -418,3 +418,89 @@ def test_c2_shade_normals_are_unit_and_positions_displace_radially(gpu, c2):
     # the shader lifts the flat quad to the arc (linear branch below depth 6 keeps the chord):
     # at depth 7 the sagitta of a 78 km quad is ~120 m, so compare with a loose bound and the exact w channel
     assert (r - pos[:, interior, 3].double()).abs().max().item() < 250.0
+
+
+# ---------------------------------------------------------------------------------------------
+# out-of-bounds canaries (compute-sanitizer is not available on this pool): every output is a
+# window inside a sentinel-filled buffer, at ragged sizes, and the sentinel must survive
+# ---------------------------------------------------------------------------------------------
+def _window(torch, numel, dtype, pad=4099, offset_elems=0):
+    big = torch.full((numel + 2 * pad + offset_elems,), -12345.0 if dtype.is_floating_point else -12345,
+                     dtype=dtype, device="cuda")
+    return big, big[pad + offset_elems: pad + offset_elems + numel]
+
+
+def _intact(big, win_start, numel):
+    sentinel = big[0].item()
+    return bool((big[:win_start] == sentinel).all()) and bool((big[win_start + numel:] == sentinel).all())
+
+
+@pytest.mark.parametrize("dim,nq,octaves,offset", [(4, 37, 3, 0), (5, 129, 2, 1), (33, 7, 8, 0), (32, 1025, 1, 3), (52, 300, 12, 0), (64, 257, 4, 1)])
+@pytest.mark.parametrize("small_path", [True, False])
+def test_k2_writes_exactly_its_output(gpu, port, dim, nq, octaves, offset, small_path, monkeypatch):
+    import torch
+    quads = gpu.tessellate_uniform(5, first=11, nquads=nq)
+    numel = nq * dim * dim
+    big, win = _window(torch, numel, torch.float32, offset_elems=offset)       # offset 1/3: not 8-byte aligned
+    p = gpu.fbm_params(octaves, 0.5, gpu.FAST)
+    # small_path False exercises the replicated-table kernel even for small batches
+    if not small_path:
+        import subprocess, sys, json, os
+        code = ("import sys; sys.path.insert(0, %r); import torch, planet_b200 as pb; pb.init(0);"
+                "q = pb.tessellate_uniform(5, first=11, nquads=%d);"
+                "big = torch.full((%d,), -12345.0, device='cuda'); win = big[%d:%d];"
+                "pb.generate_height_maps(q, %d, 18, pb.fbm_params(%d, 0.5, pb.FAST), out=win.view(%d, %d, %d));"
+                "torch.cuda.synchronize();"
+                "ok = bool((big[:%d] == -12345.0).all()) and bool((big[%d:] == -12345.0).all()) and bool((win != -12345.0).all());"
+                "print('OK' if ok else 'BAD')") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), nq,
+                                                   numel + 8198 + offset, 4099 + offset, 4099 + offset + numel,
+                                                   dim, octaves, nq, dim, dim, 4099 + offset, 4099 + offset + numel)
+        env = dict(os.environ, PLANET_K2_SMALL_MAX="0")
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+        assert out.stdout.strip().endswith("OK"), out.stdout + out.stderr
+        return
+    gpu.generate_height_maps(quads, dim, 18, p, out=win.view(nq, dim, dim))
+    torch.cuda.synchronize()
+    assert _intact(big, 4099 + offset, numel)
+    assert bool((win != -12345.0).all())                                        # and every texel was written
+    sel = [0, nq // 2, nq - 1]
+    want = port.generate_height_maps(gpu.quads_to_host(quads)[sel], dim, 18, orc_params(p))
+    got = to_np(win.view(nq, dim, dim))[sel]
+    assert np.abs(got.astype(np.float64) - want).max() <= REL_TOL * 8848.0 * amp_sum(0.5, octaves)
+
+
+@pytest.mark.parametrize("n,nq", [(30, 5), (5, 3), (31, 17), (50, 9), (12, 1)])
+def test_k1_k3_write_exactly_their_outputs(gpu, n, nq):
+    import torch
+    p = gpu.default_params(patch_verts=n)
+    nv, ni, dim = gpu.patch_vertex_count(n), gpu.patch_index_count(n), n + 2
+    bq, wq = _window(torch, nq * 13, torch.int64)
+    bi, wi = _window(torch, nq * ni, torch.int32, pad=4100)                     # keeps the window 8-byte aligned
+    L, C = gpu.lib(), gpu.C
+    gpu._check(L.planet_gpu_tessellate_uniform(C.byref(p), 3, 20, nq, wq.data_ptr(), wi.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert _intact(bq, 4099, nq * 13) and _intact(bi, 4100, nq * ni)
+    strip = np.array([L.planet_gpu_strip_index(k, n) for k in range(ni)], np.uint32)
+    want = strip[None, :] + (np.arange(nq, dtype=np.uint32) * nv)[:, None]
+    assert (to_np(wi).view(np.uint32).reshape(nq, ni) == want).all()
+    quads = wq.view(nq, 13)
+    heights = gpu.generate_height_maps(quads, dim, 18, gpu.fbm_params(4, 0.5, gpu.FAST, patch_verts=n))
+    bp, wp = _window(torch, nq * nv * 4, torch.float32, pad=4100)
+    bn, wn = _window(torch, nq * nv * 4, torch.float32, pad=4100)
+    gpu.shade(quads, heights, (1.0e6, 2.0e6, -7.0e6), p, pos=wp.view(nq, nv, 4), nrm=wn.view(nq, nv, 4))
+    torch.cuda.synchronize()
+    assert _intact(bp, 4100, nq * nv * 4) and _intact(bn, 4100, nq * nv * 4)
+    assert bool((wp != -12345.0).all()) and bool((wn != -12345.0).all())
+
+
+def test_c4_shape_against_the_oracle(gpu, port):
+    """BASELINE config 4's shape: patch 50 (dim 52), depth 8, fBm 12 octaves -- a strided subset."""
+    p = gpu.fbm_params(12, 0.5, gpu.FAST, patch_verts=50)
+    quads = gpu.tessellate_uniform(8, first=5 * 65536 + 1000, nquads=4096, params=p)
+    maps = gpu.generate_height_maps(quads, 52, 18, p)
+    sel = np.arange(0, 4096, 409)
+    hq = gpu.quads_to_host(quads)[sel]
+    assert hq.tobytes() == port.uniform_quads(5, 8)[1000:1000 + 4096][sel].tobytes()
+    want = port.generate_height_maps(hq, 52, 18, orc_params(p), nthreads=4)
+    assert np.abs(to_np(maps)[sel].astype(np.float64) - want).max() <= REL_TOL * 8848.0 * amp_sum(0.5, 12)
+    check_shade(gpu, port, hq[:3], to_np(maps)[sel][:3], np.array([0.0, 0.0, -6371010.0]), n=50)
