@@ -159,6 +159,44 @@ int planet_gpu_shade(const planet_gpu_params *p, const planet_gpu_quad *d_quads,
                      const double *cam_pos /* host, 3 doubles */, const float *d_heights,
                      float max_skirt, float *d_pos4, float *d_nrm4, void *stream);
 
+/* ---- height-map residency (main.cpp:75-102, 191-278) ------------------ */
+/* What GetHeightMapForQuad returns per quad (TextureRect, main.cpp:184-189), with the GL texture
+ * name replaced by a slot of the cache's device pool. */
+enum { PLANET_TEXRECT_HIT = 0, PLANET_TEXRECT_GENERATED = 1, PLANET_TEXRECT_PARENT = 2 };
+typedef struct planet_gpu_texrect {
+    int32_t slot;            /* pool slot holding the map to sample                         */
+    int32_t flags;           /* PLANET_TEXRECT_*                                            */
+    float corners[4];        /* corners[0].xy, corners[1].xy  (main.cpp:197-198, 232-233)   */
+    float pixel_size[2];     /* main.cpp:199, 234                                           */
+} planet_gpu_texrect;
+
+/* cache of `cache_max` maps of dim x dim floats in a hash table of `map_max` slots (the reference:
+ * 32, 1024, 1499 -- main.cpp:75-76, 194); `extra_slots` bounds the generations of one frame beyond
+ * the cache size (evicted slots are recycled one frame later).  Returns NULL on error. */
+void *planet_gpu_cache_create(int dim, int cache_max, int map_max, int extra_slots);
+void  planet_gpu_cache_destroy(void *cache);
+int   planet_gpu_cache_count(const void *cache);
+/* The reference's per-leaf loop (main.cpp:655-660) for one frame's leaf list, bookkeeping only
+ * (HOST, no device needed): per quad the texrect it would draw with, in order, with the
+ * reference's probe order, LRU choice, fallback rule and budget accounting
+ * (generations_per_frame = 100 at main.cpp:653); *n_generate = maps that must be generated. */
+int   planet_gpu_cache_plan_frame(void *cache, const planet_gpu_quad *h_quads, int64_t n,
+                                  int generations_per_frame, planet_gpu_texrect *h_rects, int64_t *n_generate);
+/* plan + ONE batched K2 launch that generates every miss into its pool slot.  h_rects (HOST) gets
+ * the texrects; d_rects (DEVICE, may be NULL) a copy for planet_gpu_shade_cached. */
+int   planet_gpu_cache_frame(void *cache, const planet_gpu_params *p, const planet_gpu_quad *h_quads,
+                             int64_t n, int max_lod, int generations_per_frame,
+                             planet_gpu_texrect *h_rects, planet_gpu_texrect *d_rects, void *stream);
+const float *planet_gpu_cache_pool(void *cache);      /* DEVICE pointer to slot 0 */
+/* copies the maps in the given pool slots to HOST memory (n x dim x dim floats); synchronous */
+int   planet_gpu_cache_read_slots(void *cache, const int32_t *slots, int64_t n, float *h_out);
+/* K3 reading each quad's map through its texrect: bilinear GL_LINEAR / CLAMP_TO_EDGE sampling
+ * (render.cpp:429-433) at mix(corners0, corners1, UV.xy) and +-pixel_size (main.cpp:334-346, 358),
+ * i.e. what the shader does when the map is the parent's.  dim = patch_verts + 2. */
+int planet_gpu_shade_cached(const planet_gpu_params *p, const planet_gpu_quad *d_quads, int64_t nquads,
+                            const double *cam_pos, const float *d_pool, const planet_gpu_texrect *d_rects,
+                            float max_skirt, float *d_pos4, float *d_nrm4, void *stream);
+
 /* ---- host-buffer convenience (what a reference-side caller with host memory uses) ---- */
 /* batched GenerateHeightMap with HOST quads and HOST output: H2D quads, K2, D2H heights;
  * returns after the data is in h_out.  d_mirror (DEVICE pointer, may be NULL) additionally

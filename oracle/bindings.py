@@ -93,6 +93,7 @@ class PortOracle:
             "orc_max_lod": (i, [d, i]), "orc_max_skirt_size": (f, [d, i]),
             "orc_skirt_size_for_quad": (f, [f, u64]),
             "orc_shade_patches": (None, [vp, l, vp, vp, i, f, vp, vp]),
+            "orc_shade_patches_rect": (None, [vp, l, vp, vp, vp, vp, i, f, vp, vp]),
             "orc_perlin_tables": (None, [vp, vp]),
         }
         for name, (res, args) in sig.items():
@@ -184,6 +185,22 @@ class PortOracle:
         return pos, nrm
 
 
+    def shade_patches_rect(self, quads, cam_pos, pool, slots, rects, n=30, max_skirt=None, radius=RADIUS):
+        """GLSL stage through texture rects (cache / parent fallback): rects float32[nq, 6]."""
+        quads = np.ascontiguousarray(quads, QUAD_DTYPE)
+        pool = np.ascontiguousarray(pool, np.float32)
+        slots = np.ascontiguousarray(slots, np.int32)
+        rects = np.ascontiguousarray(rects, np.float32).reshape(len(quads), 6)
+        cam = np.ascontiguousarray(cam_pos, np.float64)
+        if max_skirt is None:
+            max_skirt = self.max_skirt_size(radius, n)
+        nv = self.L.orc_patch_vertex_count(n)
+        pos = np.empty((len(quads), nv, 4), np.float32); nrm = np.empty_like(pos)
+        self.L.orc_shade_patches_rect(_p(quads), len(quads), _p(cam), _p(pool), _p(slots), _p(rects), n,
+                                      max_skirt, _p(pos), _p(nrm))
+        return pos, nrm
+
+
 class RefOracle:
     """The reference's own code (oracle/ref_oracle.cpp includes /root/reference/main.cpp)."""
     kind = "reference"
@@ -218,6 +235,9 @@ class RefOracle:
             "ref_root_quads": (i, [d, vp]), "ref_split_quad": (i, [d, vp, vp]),
             "ref_uniform_quads": (l, [d, i, i, vp]),
             "ref_render_frame": (l, [d, vp]), "ref_frame_quads": (l, [vp, l]),
+            "ref_render_next_frame": (l, [d, vp]), "ref_reset_cache": (None, []),
+            "ref_captured_draw_texture": (l, [l]), "ref_captured_height_map_id": (l, [l]),
+            "ref_cache_count": (i, []),
             "ref_run_reference_main": (i, [C.c_char_p]),
             "ref_captured_height_map_count": (l, []),
             "ref_captured_height_map": (i, [l, vp, vp, vp]),
@@ -312,6 +332,22 @@ class RefOracle:
         n = self.L.ref_render_frame(radius, _p(cam))
         quads = np.zeros(n, QUAD_DTYPE); self.L.ref_frame_quads(_p(quads), n)
         return quads, self.captured_height_maps(), self.captured_draws()
+
+    def render_next_frame(self, cam_pos, params=None, radius=RADIUS):
+        """The next frame of a sequence (cache, LRU ticks and render_tick carry over).  Returns
+        (leaf quads, {texture id: height map} generated this frame, draw uniforms, texture id per draw)."""
+        self._set(params)
+        cam = np.ascontiguousarray(cam_pos, np.float64)
+        n = self.L.ref_render_next_frame(radius, _p(cam))
+        quads = np.zeros(n, QUAD_DTYPE); self.L.ref_frame_quads(_p(quads), n)
+        maps = self.captured_height_maps()
+        ids = [self.L.ref_captured_height_map_id(k) for k in range(len(maps))]
+        draws = self.captured_draws()
+        tex = np.array([self.L.ref_captured_draw_texture(k) for k in range(len(draws))], np.int64)
+        return quads, dict(zip(ids, maps)), draws, tex
+
+    def reset_cache(self):
+        self.L.ref_reset_cache()
 
     def run_reference_main(self, scratch_dir):
         """The reference's real main() for one headless frame (its local `Perlin` functor)."""

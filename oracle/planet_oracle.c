@@ -511,19 +511,46 @@ static glsl_V glsl_interpolate(glsl_V v0, glsl_V v1, float t)          /* main.c
  * ((1.5+vx)/dim, (1.5+vy)/dim) is the centre of texel (vx+1, vy+1)
  * (main.cpp:196-199, 358), so GL_LINEAR filtering reduces to a direct read and
  * the four normal taps are the 4-neighbours (main.cpp:338-346). */
+static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* texture(HeightMap, uv).r with GL_LINEAR / GL_CLAMP_TO_EDGE (render.cpp:429-433) in exact
+ * fp32 (real GPUs quantise the weights to 8 bits; unpinned like the rest of the shader) */
+static float glsl_texture(const float *H, int dim, float u, float v)
+{
+    float x = u * (float)dim - 0.5f, y = v * (float)dim - 0.5f;
+    float x0 = floorf(x), y0 = floorf(y);
+    float fx = x - x0, fy = y - y0;
+    int ix0 = clampi((int)x0, 0, dim - 1), ix1 = clampi((int)x0 + 1, 0, dim - 1);
+    int iy0 = clampi((int)y0, 0, dim - 1), iy1 = clampi((int)y0 + 1, 0, dim - 1);
+    float a = H[iy0 * dim + ix0], b = H[iy0 * dim + ix1], c = H[iy1 * dim + ix0], d = H[iy1 * dim + ix1];
+    float top = a + (b - a) * fx, bot = c + (d - c) * fx;
+    return top + (bot - top) * fy;
+}
+
+/* rect == NULL: the quad's own map, direct texel reads.  Otherwise rect = {corners0.xy,
+ * corners1.xy, pixel_size.xy} as GetHeightMapForQuad returns them (main.cpp:196-199, 214-235). */
 static void glsl_vertex(const glsl_V c[4], const float *H, int dim, int n,
                         float ux, float uy, float skirt, int tx, int ty,
-                        float skirt_size, float *pos4, float *nrm4)
+                        float skirt_size, const float *rect, float *pos4, float *nrm4)
 {
     glsl_V p = glsl_interpolate(c[0], c[1], ux);              /* main.cpp:354 */
     glsl_V q = glsl_interpolate(c[2], c[3], ux);              /* main.cpp:355 */
     glsl_V v = glsl_interpolate(p, q, uy);                    /* main.cpp:356 */
 
-    float height = H[ty * dim + tx] - skirt_size * skirt;     /* main.cpp:360 */
+    float hc, x0, x1, y0, y1;
+    if (rect) {                                                /* main.cpp:339-344, 358 */
+        float tu = rect[0] * (1.0f - ux) + rect[2] * ux, tv = rect[1] * (1.0f - uy) + rect[3] * uy;
+        hc = glsl_texture(H, dim, tu, tv);
+        x0 = glsl_texture(H, dim, tu - rect[4], tv); x1 = glsl_texture(H, dim, tu + rect[4], tv);
+        y0 = glsl_texture(H, dim, tu, tv - rect[5]); y1 = glsl_texture(H, dim, tu, tv + rect[5]);
+    } else {
+        hc = H[ty * dim + tx];
+        x0 = H[ty * dim + tx - 1]; x1 = H[ty * dim + tx + 1];
+        y0 = H[(ty - 1) * dim + tx]; y1 = H[(ty + 1) * dim + tx];
+    }
+    float height = hc - skirt_size * skirt;                    /* main.cpp:360 */
     f3 pq = f3_sub(q.p, p.p);
     float xyscale = f3_length(pq) / (float)(n - 1);            /* main.cpp:361 (29.0 = n-1) */
-    float x0 = H[ty * dim + tx - 1], x1 = H[ty * dim + tx + 1];
-    float y0 = H[(ty - 1) * dim + tx], y1 = H[(ty + 1) * dim + tx];
     f3 nt = { x0 - x1, 2.0f * xyscale, y0 - y1 };
     nt = f3_normalize(nt);                                     /* main.cpp:345 */
 
@@ -545,8 +572,8 @@ static void glsl_vertex(const glsl_V c[4], const float *H, int dim, int n,
     nrm4[0] = N.x; nrm4[1] = N.y; nrm4[2] = N.z; nrm4[3] = sqrtf(light);
 }
 
-void orc_shade_patch(const orc_quad *q, const double *cam_pos, const float *heights,
-                     int n, float skirt_size, float *pos4, float *nrm4)
+static void shade_patch(const orc_quad *q, const double *cam_pos, const float *heights,
+                        int n, float skirt_size, const float *rect, float *pos4, float *nrm4)
 {
     int dim = n + 2, nv = orc_patch_vertex_count(n);
     glsl_V c[4];
@@ -571,8 +598,26 @@ void orc_shade_patch(const orc_quad *q, const double *cam_pos, const float *heig
     for (int x = 0; x < n; ++x, ++k) { tex[2 * k] = x + 1; tex[2 * k + 1] = n; }
     for (k = 0; k < nv; k++)
         glsl_vertex(c, heights, dim, n, uv[3 * k], uv[3 * k + 1], uv[3 * k + 2],
-                    tex[2 * k], tex[2 * k + 1], skirt_size, pos4 + 4 * k, nrm4 + 4 * k);
+                    tex[2 * k], tex[2 * k + 1], skirt_size, rect, pos4 + 4 * k, nrm4 + 4 * k);
     free(uv); free(tex);
+}
+
+void orc_shade_patch(const orc_quad *q, const double *cam_pos, const float *heights,
+                     int n, float skirt_size, float *pos4, float *nrm4)
+{
+    shade_patch(q, cam_pos, heights, n, skirt_size, 0, pos4, nrm4);
+}
+
+/* the cache path: quad i samples pool slot slots[i] through rects[6*i..] (main.cpp:191-237) */
+void orc_shade_patches_rect(const orc_quad *quads, long nquads, const double *cam_pos,
+                            const float *pool, const int *slots, const float *rects, int n,
+                            float max_skirt, float *pos4, float *nrm4)
+{
+    int dim = n + 2, nv = orc_patch_vertex_count(n);
+    for (long i = 0; i < nquads; i++)
+        shade_patch(quads + i, cam_pos, pool + (size_t)slots[i] * dim * dim, n,
+                    orc_skirt_size_for_quad(max_skirt, quads[i].id), rects + 6 * i,
+                    pos4 + (size_t)i * nv * 4, nrm4 + (size_t)i * nv * 4);
 }
 
 void orc_shade_patches(const orc_quad *quads, long nquads, const double *cam_pos,

@@ -101,6 +101,12 @@ void orc_shade_patch(const orc_quad *q, const double *cam_pos, const float *heig
                      int n, float skirt_size, float *pos4, float *nrm4);
 void orc_shade_patches(const orc_quad *quads, long nquads, const double *cam_pos,
                        const float *heights, int n, float max_skirt, float *pos4, float *nrm4);
+/* same through the cache's texture rects: quad i samples pool slot slots[i] with GL_LINEAR /
+ * CLAMP_TO_EDGE at mix(corners0, corners1, UV.xy); rects = 6 floats per quad
+ * (corners0.xy, corners1.xy, pixel_size.xy) as GetHeightMapForQuad returns (main.cpp:191-237) */
+void orc_shade_patches_rect(const orc_quad *quads, long nquads, const double *cam_pos,
+                            const float *pool, const int *slots, const float *rects, int n,
+                            float max_skirt, float *pos4, float *nrm4);
 
 #ifdef __cplusplus
 }

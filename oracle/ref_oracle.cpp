@@ -356,11 +356,27 @@ long ref_uniform_quads(double radius, int face, int depth, void *out)
 }
 
 /* ---- one frame of RenderPlanet with our planet + the configurable functor ---- */
+static long render_frame_impl(double radius, const double *cam_pos, bool cold_cache);
 long ref_render_frame(double radius, const double *cam_pos)
+{
+    return render_frame_impl(radius, cam_pos, true);    /* cold cache: every leaf generates */
+}
+/* the next frame of a sequence: the height-map cache (main.cpp:75-102, 191-278), its LRU ticks
+ * and render_tick carry over; captured height maps / draws are those of this frame only */
+long ref_render_next_frame(double radius, const double *cam_pos)
+{
+    return render_frame_impl(radius, cam_pos, false);
+}
+void ref_reset_cache()
+{
+    g_planet.cache = HeightMapCache{};
+    g_planet.render_tick = 0;
+}
+static long render_frame_impl(double radius, const double *cam_pos, bool cold_cache)
 {
     if (!ensure_planet(radius)) return -1;
     fakegl::reset_frame();
-    g_planet.cache = HeightMapCache{};   /* cold cache: every leaf generates */
+    if (cold_cache) g_planet.cache = HeightMapCache{};
     CameraInfo cam = {};
     cam.position = V3d(cam_pos[0], cam_pos[1], cam_pos[2]);
     cam.rotation = Mat3Identity();
@@ -405,6 +421,16 @@ int ref_captured_draw(long i, float *out32)
     out32[31] = (float)d.count;
     return 1;
 }
+/* GL texture name bound at draw i / given to generated height map i (cache identity) */
+long ref_captured_draw_texture(long i)
+{
+    return (i >= 0 && i < (long)fakegl::draws.size()) ? (long)fakegl::draws[i].texture : -1;
+}
+long ref_captured_height_map_id(long i)
+{
+    return (i >= 0 && i < (long)fakegl::height_map_ids.size()) ? (long)fakegl::height_map_ids[i] : -1;
+}
+int ref_cache_count() { return g_planet.cache.count; }
 long ref_captured_buffer_count() { return (long)fakegl::buffers.size(); }
 long ref_captured_buffer(long i, void *out, long cap)
 {

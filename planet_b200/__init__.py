@@ -25,6 +25,15 @@ class PlanetGpuError(RuntimeError):
     pass
 
 
+class TexRect(C.Structure):
+    """planet_gpu_texrect: what GetHeightMapForQuad returns per quad (main.cpp:184-189)."""
+    _fields_ = [("slot", C.c_int32), ("flags", C.c_int32), ("corners", C.c_float * 4), ("pixel_size", C.c_float * 2)]
+
+
+TEXRECT_DTYPE = np.dtype([("slot", np.int32), ("flags", np.int32), ("corners", np.float32, 4), ("pixel_size", np.float32, 2)])
+TEXRECT_HIT, TEXRECT_GENERATED, TEXRECT_PARENT = 0, 1, 2
+
+
 class Params(C.Structure):
     """planet_gpu_params (include/planet_gpu.h) -- the reference's constants, SURVEY App. D."""
     _fields_ = [("radius", C.c_double), ("patch_verts", C.c_int32), ("noise_kind", C.c_int32),
@@ -68,6 +77,14 @@ def lib():
             "planet_gpu_max_skirt_size": (f, [d, i]),
             "planet_gpu_select_lod": (i, [pp, vp, i, vp, i64, C.POINTER(i64), vp]),
             "planet_gpu_shade": (i, [pp, vp, i64, vp, vp, f, vp, vp, vp]),
+            "planet_gpu_cache_create": (vp, [i, i, i, i]),
+            "planet_gpu_cache_destroy": (None, [vp]),
+            "planet_gpu_cache_count": (i, [vp]),
+            "planet_gpu_cache_plan_frame": (i, [vp, vp, i64, i, vp, C.POINTER(i64)]),
+            "planet_gpu_cache_frame": (i, [vp, pp, vp, i64, i, i, vp, vp, vp]),
+            "planet_gpu_cache_pool": (vp, [vp]),
+            "planet_gpu_cache_read_slots": (i, [vp, vp, i64, vp]),
+            "planet_gpu_shade_cached": (i, [pp, vp, i64, vp, vp, vp, f, vp, vp, vp]),
             "planet_gpu_generate_height_maps_host": (i, [pp, vp, i64, i, i, vp, vp]),
             "planet_gpu_measure_fp32_peak": (i, [d, C.POINTER(d), C.POINTER(d)]),
             "planet_gpu_launch_count": (i64, []),
@@ -87,7 +104,10 @@ EXPORTED_SYMBOLS = [
     "planet_gpu_quads_from_ids", "planet_gpu_patch_mesh", "planet_gpu_patch_vertex_count",
     "planet_gpu_patch_index_count", "planet_gpu_strip_index", "planet_gpu_uniform_leaf_id",
     "planet_gpu_max_lod", "planet_gpu_max_skirt_size",
-    "planet_gpu_select_lod", "planet_gpu_shade", "planet_gpu_generate_height_maps_host", "planet_gpu_measure_fp32_peak",
+    "planet_gpu_select_lod", "planet_gpu_shade", "planet_gpu_generate_height_maps_host",
+    "planet_gpu_cache_create", "planet_gpu_cache_destroy", "planet_gpu_cache_count",
+    "planet_gpu_cache_plan_frame", "planet_gpu_cache_frame", "planet_gpu_cache_pool",
+    "planet_gpu_cache_read_slots", "planet_gpu_shade_cached", "planet_gpu_measure_fp32_peak",
     "planet_gpu_launch_count",
 ]
 
@@ -291,3 +311,69 @@ def get_height_at(p, depth, max_depth):
     """The reference-shaped call: float GetHeightAt(const Vec3d&, int, int)."""
     v = np.ascontiguousarray(p, np.float64)
     return lib().planet_gpu_get_height_at(v.ctypes.data, depth, max_depth)
+
+
+class HeightMapCache:
+    """Device-resident pool with the reference's cache semantics (main.cpp:75-102, 191-278)."""
+
+    def __init__(self, dim=32, cache_max=1024, map_max=1499, extra_slots=1024):
+        self.dim, self.extra = dim, extra_slots
+        self.handle = lib().planet_gpu_cache_create(dim, cache_max, map_max, extra_slots)
+        if not self.handle:
+            raise PlanetGpuError(lib().planet_gpu_last_error().decode())
+        self.pool_slots = cache_max + extra_slots
+
+    def close(self):
+        if self.handle:
+            lib().planet_gpu_cache_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    @property
+    def count(self):
+        return lib().planet_gpu_cache_count(self.handle)
+
+    def plan_frame(self, quads_np, generations_per_frame=100):
+        """Host bookkeeping only: (texrects, number of maps to generate)."""
+        q = np.ascontiguousarray(quads_np, QUAD_DTYPE)
+        rects = np.zeros(len(q), TEXRECT_DTYPE)
+        n_gen = C.c_int64(0)
+        _check(lib().planet_gpu_cache_plan_frame(self.handle, q.ctypes.data, len(q), generations_per_frame,
+                                                 rects.ctypes.data, C.byref(n_gen)))
+        return rects, n_gen.value
+
+    def frame(self, quads_np, max_lod, params=None, generations_per_frame=100, stream=None):
+        """Plan + one batched K2 launch for the misses.  Returns (host texrects, device texrects)."""
+        torch = _torch()
+        params = params or default_params()
+        q = np.ascontiguousarray(quads_np, QUAD_DTYPE)
+        rects = np.zeros(len(q), TEXRECT_DTYPE)
+        d_rects = torch.empty((len(q), 8), dtype=torch.int32, device="cuda")
+        _check(lib().planet_gpu_cache_frame(self.handle, C.byref(params), q.ctypes.data, len(q), max_lod,
+                                            generations_per_frame, rects.ctypes.data, d_rects.data_ptr(), _stream(stream)))
+        return rects, d_rects
+
+    def pool_ptr(self):
+        return lib().planet_gpu_cache_pool(self.handle)
+
+    def read_slots(self, slots):
+        """Host copy of the maps in the given pool slots: float32[n, dim, dim]."""
+        s = np.ascontiguousarray(slots, np.int32)
+        out = np.empty((len(s), self.dim, self.dim), np.float32)
+        _check(lib().planet_gpu_cache_read_slots(self.handle, s.ctypes.data, len(s), out.ctypes.data))
+        return out
+
+
+def shade_cached(quads, cache, d_rects, cam_pos, params=None, max_skirt=-1.0, stream=None):
+    """K3 through the cache's texrects (bilinear sampling, parent fallback)."""
+    torch = _torch()
+    params = params or default_params()
+    n = quads.shape[0]
+    nv = patch_vertex_count(params.patch_verts)
+    pos = torch.empty((n, nv, 4), dtype=torch.float32, device="cuda")
+    nrm = torch.empty((n, nv, 4), dtype=torch.float32, device="cuda")
+    cam = (C.c_double * 3)(*[float(c) for c in cam_pos])
+    _check(lib().planet_gpu_shade_cached(C.byref(params), quads.data_ptr(), n, cam, cache.pool_ptr(), d_rects.data_ptr(),
+                                         max_skirt, pos.data_ptr(), nrm.data_ptr(), _stream(stream)))
+    return pos, nrm

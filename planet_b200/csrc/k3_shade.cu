@@ -90,11 +90,27 @@ enum { C_PPX, C_PPY, C_PPZ, C_PNX, C_PNY, C_PNZ, C_PQX, C_PQY, C_PQZ, C_DNX, C_D
 // One WARP per quad: warps never wait for each other (no block barrier), so one warp's
 // column phase overlaps the other warps' vertex phases.  Per-warp shared memory:
 //   [4 corner uniforms | COL_ARRAYS x np column floats | (n+2)^2 staged heights]
-template <bool STAGE>      // STAGE: height map staged in shared memory (else taps read global via L1)
+// GL_LINEAR + GL_CLAMP_TO_EDGE fetch of a dim x dim R32F texture (render.cpp:429-433) at (u, v)
+__device__ __forceinline__ float sample_bilinear(const float *tex, int dim, float u, float v)
+{
+    float x = u * (float)dim - 0.5f, y = v * (float)dim - 0.5f;
+    float x0 = floorf(x), y0 = floorf(y);
+    float fx = x - x0, fy = y - y0;
+    int ix0 = min(max((int)x0, 0), dim - 1), ix1 = min(max((int)x0 + 1, 0), dim - 1);
+    int iy0 = min(max((int)y0, 0), dim - 1), iy1 = min(max((int)y0 + 1, 0), dim - 1);
+    float a = tex[iy0 * dim + ix0], b = tex[iy0 * dim + ix1], c = tex[iy1 * dim + ix0], d = tex[iy1 * dim + ix1];
+    float top = fmaf(b - a, fx, a), bot = fmaf(d - c, fx, c);
+    return fmaf(bot - top, fy, top);
+}
+
+// STAGE: height map staged in shared memory (else taps read global via L1).
+// RECT:  each quad reads its map through a texrect (pool slot + corners + pixel size) with
+//        bilinear filtering -- the cache / parent-fallback path (main.cpp:191-237, 334-346, 358).
+template <bool STAGE, bool RECT>
 __global__ void __launch_bounds__(THREADS)
 k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, double cam_y, double cam_z,
-        const float *__restrict__ heights, float max_skirt, float4 *__restrict__ pos4,
-        float4 *__restrict__ nrm4, int warp_smem_bytes)
+        const float *__restrict__ heights, const planet_gpu_texrect *__restrict__ rects, float max_skirt,
+        float4 *__restrict__ pos4, float4 *__restrict__ nrm4, int warp_smem_bytes)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int dim = n + 2, dim2 = dim * dim, w = n + 2, nv = n * n + 4 * n;
@@ -114,7 +130,9 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
 
     const int64_t wstride = (int64_t)gridDim.x * nwarps;
     for (int64_t qi = (int64_t)blockIdx.x * nwarps + warp; qi < nquads; qi += wstride) {
-        const float *H = heights + qi * dim2;
+        planet_gpu_texrect rect = {};
+        if (RECT) rect = rects[qi];
+        const float *H = heights + (RECT ? (int64_t)rect.slot : qi) * dim2;
         __syncwarp();                                                // previous quad fully shaded
         // ---- A: uniforms + height map staging ------------------------------------------------
         if (lane < 4) {
@@ -210,7 +228,17 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
                 }
                 const int ti = row_off + vx + 1;                     // texel (vx+1, vy+1)
                 float hc, hl, hr, hu, hd;
-                if (STAGE) { hc = s_h[ti]; hl = s_h[ti - 1]; hr = s_h[ti + 1]; hu = s_h[ti - dim]; hd = s_h[ti + dim]; }
+                if (RECT) {
+                    // uv = mix(corners0, corners1, UV.xy), taps at +-pixel_size (main.cpp:339-344, 358)
+                    const float ux = s_uv[vx];                       // UV.x (skirt literals 0.0f / 1.0f coincide)
+                    const float u = rect.corners[0] * (1.0f - ux) + rect.corners[2] * ux;
+                    const float v = rect.corners[1] * omt + rect.corners[3] * t;
+                    hc = sample_bilinear(s_h, dim, u, v);
+                    hl = sample_bilinear(s_h, dim, u - rect.pixel_size[0], v);
+                    hr = sample_bilinear(s_h, dim, u + rect.pixel_size[0], v);
+                    hu = sample_bilinear(s_h, dim, u, v - rect.pixel_size[1]);
+                    hd = sample_bilinear(s_h, dim, u, v + rect.pixel_size[1]);
+                } else if (STAGE) { hc = s_h[ti]; hl = s_h[ti - 1]; hr = s_h[ti + 1]; hu = s_h[ti - dim]; hd = s_h[ti + dim]; }
                 else { hc = __ldg(H + ti); hl = __ldg(H + ti - 1); hr = __ldg(H + ti + 1); hu = __ldg(H + ti - dim); hd = __ldg(H + ti + dim); }
                 const float height = hc - skirt_size * skirt;        // main.cpp:360
                 float3 nt = normalize(f3(hl - hr, s_col[C_XYS * np + vx], hu - hd));   // main.cpp:339-345
@@ -234,7 +262,8 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
 } // namespace shade
 
 int launch_shade(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads, const double *cam,
-                 const float *d_heights, float max_skirt, float *d_pos4, float *d_nrm4, cudaStream_t stream)
+                 const float *d_heights, const planet_gpu_texrect *d_rects, float max_skirt, float *d_pos4,
+                 float *d_nrm4, cudaStream_t stream)
 {
     if (nquads == 0) return 0;
     const int n = p->patch_verts;
@@ -245,6 +274,8 @@ int launch_shade(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads
     const size_t hbytes = (size_t)dim * dim * sizeof(float);
     const size_t budget = 200 * 1024;
     const int stage = (col_bytes + hbytes) <= budget;               // else the stencil reads go to L1/L2
+    if (d_rects && !stage)
+        return set_error(PLANET_E_UNSUPPORTED, "planet_gpu_shade_cached: a %d x %d map does not fit shared memory", dim, dim);
     const size_t per_warp = col_bytes + (stage ? hbytes : 0);
     int want_warps = shade::WARPS;
     if (const char *e = getenv("PLANET_K3_WARPS")) want_warps = std::max(1, std::min(shade::WARPS, atoi(e)));   // tuning knob
@@ -255,21 +286,24 @@ int launch_shade(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     static size_t configured[64] = {};                               // per device
     if (smem > 48 * 1024 && smem > configured[dev & 63]) {
-        PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev & 63] = smem;
     }
     int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(6, 2048 / (warps * 32)), budget / smem));
     if (const char *e = getenv("PLANET_K3_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));   // tuning knob
     int grid = (int)std::min<int64_t>((nquads + warps - 1) / warps, (int64_t)sms * per_sm);
-    if (stage)
-        shade::k_shade<true><<<grid, warps * 32, smem, stream>>>(
-            d_quads, nquads, n, cam[0], cam[1], cam[2], d_heights, max_skirt,
-            reinterpret_cast<float4 *>(d_pos4), reinterpret_cast<float4 *>(d_nrm4), (int)per_warp);
+    float4 *pos = reinterpret_cast<float4 *>(d_pos4), *nrm = reinterpret_cast<float4 *>(d_nrm4);
+    if (d_rects)
+        shade::k_shade<true, true><<<grid, warps * 32, smem, stream>>>(
+            d_quads, nquads, n, cam[0], cam[1], cam[2], d_heights, d_rects, max_skirt, pos, nrm, (int)per_warp);
+    else if (stage)
+        shade::k_shade<true, false><<<grid, warps * 32, smem, stream>>>(
+            d_quads, nquads, n, cam[0], cam[1], cam[2], d_heights, nullptr, max_skirt, pos, nrm, (int)per_warp);
     else
-        shade::k_shade<false><<<grid, warps * 32, smem, stream>>>(
-            d_quads, nquads, n, cam[0], cam[1], cam[2], d_heights, max_skirt,
-            reinterpret_cast<float4 *>(d_pos4), reinterpret_cast<float4 *>(d_nrm4), (int)per_warp);
+        shade::k_shade<false, false><<<grid, warps * 32, smem, stream>>>(
+            d_quads, nquads, n, cam[0], cam[1], cam[2], d_heights, nullptr, max_skirt, pos, nrm, (int)per_warp);
     count_launch();
     return check_cuda(cudaGetLastError(), "shade kernel launch");
 }

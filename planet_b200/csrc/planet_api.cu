@@ -20,8 +20,8 @@ int launch_noise(const double *, int64_t, int, double, float, int, int, float *,
 int launch_tessellate_uniform(const planet_gpu_params *, int, int64_t, int64_t, Quad *, uint32_t *, cudaStream_t);
 int launch_quads_from_ids(const planet_gpu_params *, const uint64_t *, int64_t, Quad *, cudaStream_t);
 int launch_patch_mesh(int, float *, uint32_t *, cudaStream_t);
-int launch_shade(const planet_gpu_params *, const Quad *, int64_t, const double *, const float *, float,
-                 float *, float *, cudaStream_t);
+int launch_shade(const planet_gpu_params *, const Quad *, int64_t, const double *, const float *,
+                 const planet_gpu_texrect *, float, float *, float *, cudaStream_t);
 int launch_select_lod(const planet_gpu_params *, const double *, int, Quad *, int64_t, int64_t *, cudaStream_t);
 uint32_t host_strip_index(int, int);
 uint64_t host_uniform_leaf_id(int64_t, int);
@@ -418,7 +418,21 @@ int planet_gpu_shade(const planet_gpu_params *p, const planet_gpu_quad *d_quads,
     if (nquads < 0 || (nquads > 0 && (!d_quads || !d_heights || !cam_pos)))
         return set_error(PLANET_E_INVALID, "NULL buffer");
     if (max_skirt < 0.0f) max_skirt = planet_gpu_max_skirt_size(p->radius, p->patch_verts);
-    return launch_shade(p, (const Quad *)d_quads, nquads, cam_pos, d_heights, max_skirt, d_pos4, d_nrm4,
+    return launch_shade(p, (const Quad *)d_quads, nquads, cam_pos, d_heights, nullptr, max_skirt, d_pos4, d_nrm4,
+                        (cudaStream_t)stream);
+}
+
+int planet_gpu_shade_cached(const planet_gpu_params *p, const planet_gpu_quad *d_quads, int64_t nquads,
+                            const double *cam_pos, const float *d_pool, const planet_gpu_texrect *d_rects,
+                            float max_skirt, float *d_pos4, float *d_nrm4, void *stream)
+{
+    if (!ensure_init()) return PLANET_E_NO_DEVICE;
+    int rc = validate_params(p);
+    if (rc) return rc;
+    if (nquads < 0 || (nquads > 0 && (!d_quads || !d_pool || !d_rects || !cam_pos)))
+        return set_error(PLANET_E_INVALID, "NULL buffer");
+    if (max_skirt < 0.0f) max_skirt = planet_gpu_max_skirt_size(p->radius, p->patch_verts);
+    return launch_shade(p, (const Quad *)d_quads, nquads, cam_pos, d_pool, d_rects, max_skirt, d_pos4, d_nrm4,
                         (cudaStream_t)stream);
 }
 

@@ -1,0 +1,109 @@
+"""the height-map cache (main.cpp:75-102, 191-278).
+
+CPU half: the host bookkeeping (planet_gpu_cache_plan_frame) against the reference's own
+GetHeightMapForQuad run over a camera path that exercises hits, budget-exhausted parent
+fallback and LRU eviction.  GPU half: the generated pool contents and the texrect shading."""
+import numpy as np
+import pytest
+
+import planet_b200 as pb
+from oracle.bindings import RADIUS, height_params
+
+
+def camera_path():
+    """Start far out (few coarse leaves), jump down to the surface (more than 100 new leaves in one
+    frame -> parent fallback), then travel round the planet (cache fills beyond 1 024 -> LRU)."""
+    R = RADIUS
+    cams = [np.array([0.0, 0.0, -3.0 * R]), np.array([0.0, 0.0, -R - 200000.0]), np.array([0.0, 0.0, -R - 10.0]),
+            np.array([0.0, 0.0, -R - 10.0]), np.array([0.0, 0.0, -R - 3000.0])]
+    for k in range(1, 26):                                  # a great-circle tour at 10 m altitude
+        a = 2 * np.pi * k / 25
+        cams.append(np.array([np.sin(a) * (R + 10.0), 0.3 * R * np.sin(3 * a), -np.cos(a) * (R + 10.0)]))
+        cams[-1] *= (R + 10.0) / np.linalg.norm(cams[-1])
+    return cams
+
+
+def reference_frames(ref):
+    """Per frame: leaf quads, the id of the quad whose map each draw sampled, corners, pixel size."""
+    ref.reset_cache()
+    owner = {}                                              # GL texture name -> QuadID it was generated for
+    frames = []
+    for cam in camera_path():
+        quads, maps, draws, tex = ref.render_next_frame(cam, height_params())
+        # a texture generated this frame belongs to the first quad of the frame drawn with it
+        for q, t, d in zip(quads, tex, draws):
+            t = int(t)
+            if t in maps and t not in owner:
+                owner[t] = int(q["id"])
+        frames.append(dict(cam=cam, quads=quads, owners=np.array([owner[int(t)] for t in tex], np.uint64),
+                           corners=draws[:, 25:29].copy(), pixel=draws[:, 29:31].copy(), generated=len(maps),
+                           maps=maps, tex=tex))
+    return frames
+
+
+@pytest.fixture(scope="module")
+def frames(ref):
+    return reference_frames(ref)
+
+
+def test_path_exercises_fallback_and_eviction(frames, ref):
+    fallback = sum(int((f["pixel"][:, 0] != np.float32(1.0 / 32)).sum()) for f in frames)
+    total_generated = sum(f["generated"] for f in frames)
+    assert fallback > 0, "camera path never hit the budget-exhausted parent fallback"
+    assert total_generated > 1024 + 100, "camera path never filled the cache (no LRU eviction)"
+    assert ref.L.ref_cache_count() == 1024
+
+
+def test_plan_frame_makes_the_reference_decisions(frames):
+    """Same map owner (own / parent / which cached quad), same corners and pixel size, bit for bit."""
+    cache = pb.HeightMapCache(32, 1024, 1499, extra_slots=1024)
+    slot_owner = {}
+    for k, f in enumerate(frames):
+        rects, n_gen = cache.plan_frame(f["quads"], 100)
+        assert n_gen == f["generated"], (k, n_gen, f["generated"])
+        for q, r in zip(f["quads"], rects):
+            if r["flags"] == pb.TEXRECT_GENERATED:
+                slot_owner[int(r["slot"])] = int(q["id"])
+        owners = np.array([slot_owner[int(s)] for s in rects["slot"]], np.uint64)
+        assert (owners == f["owners"]).all(), k
+        assert rects["corners"].tobytes() == f["corners"].tobytes(), k
+        assert rects["pixel_size"].tobytes() == f["pixel"].tobytes(), k
+        want_parent = f["pixel"][:, 0] != np.float32(1.0 / 32)
+        assert ((rects["flags"] == pb.TEXRECT_PARENT) == want_parent).all(), k
+    assert cache.count == 1024
+    cache.close()
+
+
+def test_pool_exhaustion_is_an_error_not_a_corruption(frames):
+    cache = pb.HeightMapCache(32, 8, 11, extra_slots=4)
+    with pytest.raises(pb.PlanetGpuError, match="pool exhausted"):
+        cache.plan_frame(frames[2]["quads"], 100)
+    cache.close()
+
+
+@pytest.mark.gpu
+def test_cache_frames_generate_the_reference_maps_and_shade_through_texrects(frames, gpu, port):
+    cache = gpu.HeightMapCache(32, 1024, 1499, extra_slots=1024)
+    p = gpu.default_params()                                 # EXACT: maps must be the reference's bits
+    for k, f in enumerate(frames[:8]):
+        rects, d_rects = cache.frame(f["quads"], 18, p, 100)
+        gen = rects["flags"] == gpu.TEXRECT_GENERATED
+        if gen.any():
+            got = cache.read_slots(rects["slot"][gen])
+            want = np.stack([f["maps"][int(t)] for t in f["tex"][gen]])
+            assert got.tobytes() == want.tobytes(), k        # one batched K2 launch == 1 GenerateHeightMap per quad
+        # shading through the texrects (own maps and parent fallbacks) against the GLSL restatement
+        dq = gpu.quads_to_device(f["quads"])
+        pos, nrm = gpu.shade_cached(dq, cache, d_rects, f["cam"], p)
+        pool = cache.read_slots(np.arange(cache.pool_slots, dtype=np.int32))
+        r6 = np.concatenate([rects["corners"], rects["pixel_size"]], axis=1)
+        wpos, wnrm = port.shade_patches_rect(f["quads"], f["cam"], pool, rects["slot"], r6)
+        a, b = nrm.cpu().numpy()[..., :3].astype(np.float64), wnrm[..., :3].astype(np.float64)
+        ang = np.arctan2(np.linalg.norm(np.cross(a, b), axis=-1), (a * b).sum(-1))
+        assert ang.max() <= 1e-4, (k, ang.max())
+        # bilinear weights carry ~1 ulp of fp32 texture-coordinate rounding (FMA vs not): the height
+        # error scales with the map's slope, so bound it by 1e-5 of each map's height range
+        dh = np.abs(pos.cpu().numpy()[..., 3].astype(np.float64) - wpos[..., 3]).max(axis=1)
+        rng = np.ptp(pool[rects["slot"]].reshape(len(rects), -1), axis=1)
+        assert (dh <= 1e-5 * rng + 1e-3).all(), (k, dh.max())
+    cache.close()
