@@ -42,3 +42,21 @@ def test_reference_call_sites_through_function_pointers(driver, golden, tmp_path
     orc = PortOracle()
     corner = np.array([[orc.get_height_at(p, 0, 1, height_params()) for p in q["p"]] for q in quads], np.float32)
     assert (as_bits(out[:, 1024:]) == as_bits(corner)).all()   # GetHeightAt(p, 0, 1), bit-exact
+
+
+@pytest.mark.gpu
+def test_headless_frame_program_matches_the_reference_frame_counts(tmp_path, gpu):
+    """planet_b200/host/planet_frame.cpp: InitPlanet + RenderPlanet on the GPU, in C++."""
+    exe = str(tmp_path / "planet_frame")
+    host = os.path.join(ROOT, "planet_b200", "host")
+    lib_dir = os.path.join(ROOT, "planet_b200")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", os.path.join(host, "planet_frame.cpp"),
+                           "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include",
+                           "-L" + lib_dir, "-lplanet_gpu", "-L/usr/local/cuda/lib64", "-lcudart",
+                           "-Wl,-rpath," + lib_dir, "-o", exe])
+    out = subprocess.run([exe, "3"], capture_output=True, text=True, check=True).stdout
+    assert "max_lod: 18" in out and "patch: 1020 verts / 2036 indices" in out
+    lines = [l for l in out.splitlines() if l.startswith("tris:")]
+    # the reference's first frame: 117 leaf quads, 117 * 29 * 29 * 2 triangles, all generated
+    assert lines[0].startswith("tris: 196794, quads: 117, generated: 117, parent fallback: 0, cached: 117")
+    assert len(lines) == 3 and "vertex 0: pos" in out
