@@ -110,6 +110,10 @@ k_noise_exact(const double *__restrict__ xyz, int64_t n, int kind, double lacuna
 // =====================================================================================
 namespace fast {
 
+#ifndef PLANET_K2_UNROLL
+#define PLANET_K2_UNROLL 1
+#endif
+constexpr int K2_UNROLL = PLANET_K2_UNROLL;   // octave-loop unroll factor (build-time tuning knob)
 constexpr int THREADS = 512;
 constexpr int S = 2;                          // consecutive samples per thread (one f32x2 pair)
 constexpr int TILE = THREADS * S;             // samples per CTA iteration
@@ -299,6 +303,7 @@ __device__ __forceinline__ void fractal_loop(const unsigned char *t12_lane, cons
         }
     } else {                                                         // main.cpp:699-704
         f2 acc = splat(0.0f);
+#pragma unroll K2_UNROLL
         for (int k = 0; k < omax; k++) {
             f2 n = noise_octave2<REPL>(t12_lane, t3_lane, p[0], p[1], k);
             if (GUARD) {
