@@ -204,6 +204,20 @@ def run_ours(args, rank, local_rank, world):
     t_k3 = np.array([m[2].elapsed_time(m[3]) for m in marks])
     t_step = np.array([m[0].elapsed_time(m[3]) for m in marks])
 
+    # ---- the same K2 batch in EXACT arithmetic (bit-identical to the reference), for the record ----
+    p_exact = pb.fbm_params(octaves=OCTAVES, gain=GAIN, precision=pb.EXACT, seed_offset=seed)
+    ppe = C.byref(p_exact)
+    ex_t = []
+    for i in range(5):
+        a, b_ = ev(), ev()
+        a.record()
+        pb._check(L.planet_gpu_generate_height_maps(ppe, quads.data_ptr(), nq, DIM, MAX_LOD, heights.data_ptr(), sp))
+        b_.record(); torch.cuda.synchronize()
+        if i >= 2:
+            ex_t.append(a.elapsed_time(b_))
+    ms_k2_exact = float(np.mean(ex_t))
+    k2()                                                               # restore the FAST heights for K3 / e2e
+
     # ---- e2e: the reference-facing host-buffer call (H2D quads, K2, D2H heights) + K3 on device ----
     h_quads = torch.empty((nq, 13), dtype=torch.int64).pin_memory()
     h_quads.copy_(quads.cpu())
@@ -264,7 +278,8 @@ def run_ours(args, rank, local_rank, world):
                        "quads_per_gpu": nq, "vertices_per_gpu": VERTS_PER_GPU, "precision": "FAST",
                        "l2": "256 MiB buffer written between timed steps (L2 flush); step working set 730 MB",
                        "step": "K1 tessellate + K2 heights + K3 shade"},
-            "ms": {"k1_tessellate": ms_k1, "k2_heights": ms_k2, "k3_shade": ms_k3},
+            "ms": {"k1_tessellate": ms_k1, "k2_heights": ms_k2, "k3_shade": ms_k3,
+                   "k2_heights_exact_mode": ms_k2_exact},
             "roofline": {"kernel": "k_height_maps_fast<768,32>", "bound": "fp32", "achieved": k2_tf, "peak": fp32_tf,
                          "unit": "TFLOP/s", "frac": k2_tf / fp32_tf,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full

@@ -88,6 +88,21 @@ def test_noise_against_oracle_on_seeded_points(gpu, port):
         assert np.abs(fa.astype(np.float64) - want).max() <= REL_TOL * amp_sum(gain, o)
 
 
+def test_points_kernels_at_scale_fast_vs_exact(gpu):
+    """1.3 M points take the replicated-table points kernel; FAST must track EXACT everywhere."""
+    import torch
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    pts = (torch.rand((1_300_000, 3), generator=g, device="cuda", dtype=torch.float64) - 0.5) * 140.0
+    for kind, gain, o in ((FBM, 0.5, 8), (RIDGED, 0.55, 12)):
+        ex = gpu.noise(pts, kind=kind, gain=gain, octaves=o, precision=gpu.EXACT)
+        fa = gpu.noise(pts, kind=kind, gain=gain, octaves=o, precision=gpu.FAST)
+        assert (ex.double() - fa.double()).abs().max().item() <= REL_TOL * amp_sum(gain, o)
+    sphere = pts / pts.norm(dim=1, keepdim=True) * 6371000.0
+    p_ex, p_fa = gpu.default_params(), gpu.default_params(precision=gpu.FAST)
+    ex = gpu.heights_at(sphere, 9, 18, p_ex); fa = gpu.heights_at(sphere, 9, 18, p_fa)
+    assert (ex.double() - fa.double()).abs().max().item() <= REL_TOL * 8848.0 * amp_sum(0.55, 12)
+
+
 # ---------------------------------------------------------------------------------------------
 # K1: QuadIDs, corners, patch mesh, merged index buffer -- all bit-exact
 # ---------------------------------------------------------------------------------------------
