@@ -105,6 +105,14 @@ void  planet_gpu_generate_height_map(float *data, int dim, const void *quad, int
 int planet_gpu_generate_height_maps(const planet_gpu_params *p, const planet_gpu_quad *d_quads,
                                     int64_t nquads, int dim, int max_depth, float *d_out,
                                     void *stream);
+/* K2 with the multi-GPU gather fused in: identical to planet_gpu_generate_height_maps, and every
+ * height is additionally stored to the same offset of up to 7 peer buffers (peer_out: HOST array
+ * of n_peers DEVICE pointers, typically this rank's shard inside each peer GPU's gathered buffer,
+ * mapped with CUDA IPC / peer access).  The stores travel over NVLink while the kernel computes;
+ * the buffers are complete once every rank's kernel has finished. */
+int planet_gpu_generate_height_maps_gathered(const planet_gpu_params *p, const planet_gpu_quad *d_quads,
+                                             int64_t nquads, int dim, int max_depth, float *d_out,
+                                             float *const *peer_out, int n_peers, void *stream);
 /* batched Gen::GetHeightAt (main.cpp:118-121): n points (xyz doubles), one (depth, max_depth) */
 int planet_gpu_heights_at(const planet_gpu_params *p, const double *d_xyz, int64_t n, int depth,
                           int max_depth, float *d_out, void *stream);

@@ -64,6 +64,7 @@ def lib():
             "planet_gpu_get_height_at": (f, [vp, i, i]),
             "planet_gpu_generate_height_map": (None, [vp, i, vp, i]),
             "planet_gpu_generate_height_maps": (i, [pp, vp, i64, i, i, vp, vp]),
+            "planet_gpu_generate_height_maps_gathered": (i, [pp, vp, i64, i, i, vp, vp, i, vp]),
             "planet_gpu_heights_at": (i, [pp, vp, i64, i, i, vp, vp]),
             "planet_gpu_noise": (i, [vp, i64, i, d, f, i, i, vp, vp]),
             "planet_gpu_tessellate_uniform": (i, [pp, i, i64, i64, vp, vp, vp]),
@@ -100,7 +101,7 @@ EXPORTED_SYMBOLS = [
     "planet_gpu_abi_version", "planet_gpu_default_params", "planet_gpu_init", "planet_gpu_shutdown",
     "planet_gpu_last_error", "planet_gpu_device_info", "planet_gpu_set_params",
     "planet_gpu_get_height_at", "planet_gpu_generate_height_map", "planet_gpu_generate_height_maps",
-    "planet_gpu_heights_at", "planet_gpu_noise", "planet_gpu_tessellate_uniform",
+    "planet_gpu_generate_height_maps_gathered", "planet_gpu_heights_at", "planet_gpu_noise", "planet_gpu_tessellate_uniform",
     "planet_gpu_quads_from_ids", "planet_gpu_patch_mesh", "planet_gpu_patch_vertex_count",
     "planet_gpu_patch_index_count", "planet_gpu_strip_index", "planet_gpu_uniform_leaf_id",
     "planet_gpu_max_lod", "planet_gpu_max_skirt_size",
@@ -239,6 +240,17 @@ def generate_height_maps(quads, dim, max_depth, params=None, out=None, stream=No
         out = torch.empty((n, dim, dim), dtype=torch.float32, device="cuda")
     _check(lib().planet_gpu_generate_height_maps(C.byref(params), quads.data_ptr(), n, dim, max_depth,
                                                  out.data_ptr(), _stream(stream)))
+    return out
+
+
+def generate_height_maps_gathered(quads, dim, max_depth, out, peer_outs, params=None, stream=None):
+    """K2 with the all-gather fused in: `out` is this rank's shard inside its own gathered buffer,
+    `peer_outs` the same shard inside each peer's (IPC-mapped) gathered buffer."""
+    params = params or default_params()
+    n = quads.shape[0]
+    arr = (C.c_void_p * max(len(peer_outs), 1))(*[t.data_ptr() for t in peer_outs])
+    _check(lib().planet_gpu_generate_height_maps_gathered(C.byref(params), quads.data_ptr(), n, dim, max_depth,
+                                                          out.data_ptr(), arr, len(peer_outs), _stream(stream)))
     return out
 
 

@@ -44,6 +44,12 @@
 
 namespace planet {
 
+// Fused gather (multi-GPU): besides its own buffer, a kernel can store every height straight
+// into the same position of up to 7 peers' buffers (CUDA-IPC mapped, NVLink peer stores), so the
+// all-gather of finished patches costs 7 extra store instructions per thread instead of a
+// collective after the kernel.
+struct PeerOut { float *ptr[7]; int n; };
+
 // =====================================================================================
 // EXACT kernels
 // =====================================================================================
@@ -56,7 +62,7 @@ __device__ __forceinline__ void stage_small_tables(unsigned char *s_perm, float 
 
 __global__ void __launch_bounds__(256)
 k_height_maps_exact(const Quad *__restrict__ quads, int64_t total, int dim, HeightCfg cfg,
-                    float *__restrict__ out)
+                    float *__restrict__ out, PeerOut peers)
 {
     __shared__ unsigned char s_perm[256];
     __shared__ float s_grad[48];
@@ -70,7 +76,11 @@ k_height_maps_exact(const Quad *__restrict__ quads, int64_t total, int dim, Heig
         int y = r / dim, x = r - y * dim;
         Quad quad = quads[q];
         d3 p = exact::sample_point(quad, x, y, div);
-        out[i] = exact::height(s_perm, s_grad, cfg, p, (int)quad_depth(quad.id));
+        float h = exact::height(s_perm, s_grad, cfg, p, (int)quad_depth(quad.id));
+        out[i] = h;
+#pragma unroll
+        for (int r = 0; r < 7; r++)
+            if (r < peers.n) peers.ptr[r][i] = h;
     }
 }
 
@@ -358,7 +368,7 @@ template <int NTHREADS, int REPL>
 __global__ void __launch_bounds__(NTHREADS, REPL == 32 ? 1 : 2)
 k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, HeightCfg cfg,
                    float *__restrict__ out, int64_t nwtiles, int out_aligned8,
-                   uint64_t magic_dim, uint64_t magic_dim2)
+                   uint64_t magic_dim, uint64_t magic_dim2, PeerOut peers)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     using L = Layout<REPL>;
@@ -477,14 +487,23 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
                 fractal<REPL>(t12_lane, t3_lane, p, oct, cfg.kind, cfg.gain, value);
             }
 
-            float *dst = out + base + i0;                                    // base + i0 is even
+            const int64_t o = base + i0;                                     // even
             if (out_aligned8 && i0 + 1 < n_here) {
-                __stcs(reinterpret_cast<float2 *>(dst),
-                       make_float2(value[0] * cfg.height_scale, value[1] * cfg.height_scale));
+                const float2 h2 = make_float2(value[0] * cfg.height_scale, value[1] * cfg.height_scale);
+                __stcs(reinterpret_cast<float2 *>(out + o), h2);
+#pragma unroll
+                for (int r = 0; r < 7; r++)                                  // NVLink peer stores (fused gather)
+                    if (r < peers.n) __stcs(reinterpret_cast<float2 *>(peers.ptr[r] + o), h2);
             } else {
 #pragma unroll
                 for (int sidx = 0; sidx < S; sidx++)
-                    if (i0 + sidx < n_here) dst[sidx] = value[sidx] * cfg.height_scale;
+                    if (i0 + sidx < n_here) {
+                        const float h = value[sidx] * cfg.height_scale;
+                        out[o + sidx] = h;
+#pragma unroll
+                        for (int r = 0; r < 7; r++)
+                            if (r < peers.n) peers.ptr[r][o + sidx] = h;
+                    }
             }
         }
 
@@ -616,8 +635,18 @@ static bool fast_applicable(double lacunarity, int max_octaves)
     return lacunarity == 2.0 && max_octaves <= 32;
 }
 
+int launch_height_maps_gathered(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads, int dim,
+                                int max_depth, float *d_out, const PeerOut &peers, cudaStream_t stream);
+
 int launch_height_maps(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads, int dim,
                        int max_depth, float *d_out, cudaStream_t stream)
+{
+    PeerOut none = {};
+    return launch_height_maps_gathered(p, d_quads, nquads, dim, max_depth, d_out, none, stream);
+}
+
+int launch_height_maps_gathered(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads, int dim,
+                                int max_depth, float *d_out, const PeerOut &peers, cudaStream_t stream)
 {
     HeightCfg cfg = make_cfg(p, max_depth);
     int64_t total = nquads * (int64_t)dim * dim;
@@ -634,23 +663,24 @@ int launch_height_maps(const planet_gpu_params *p, const Quad *d_quads, int64_t 
         int64_t nwtiles = (total + fast::WTILE - 1) / fast::WTILE;
         const uint64_t one40 = 1ull << 40;
         const uint64_t m1 = (one40 + dim - 1) / dim, m2 = (one40 + (uint64_t)dim * dim - 1) / ((uint64_t)dim * dim);
-        const int al = (reinterpret_cast<uintptr_t>(d_out) & 7) == 0;
+        int al = (reinterpret_cast<uintptr_t>(d_out) & 7) == 0;
+        for (int r = 0; r < peers.n; r++) al = al && (reinterpret_cast<uintptr_t>(peers.ptr[r]) & 7) == 0;
         if (total <= k2_small_max()) {
             // latency path: compact tables (6 KB), 256-thread CTAs spread over the whole chip
             int grid = (int)std::min<int64_t>((nwtiles + 7) / 8, (int64_t)sm_count() * 8);
             fast::k_height_maps_fast<256, 1><<<grid, 256, fast::smem_bytes<1>(256), stream>>>(
-                d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2);
+                d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2, peers);
         } else {
             const int nt = k2_threads();
             int grid = (int)std::min<int64_t>((nwtiles + nt / 32 - 1) / (nt / 32), sm_count());
             const size_t sm = fast::smem_bytes<32>(nt);
-            if (nt == 512) fast::k_height_maps_fast<512, 32><<<grid, 512, sm, stream>>>(d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2);
-            else           fast::k_height_maps_fast<768, 32><<<grid, 768, sm, stream>>>(d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2);
+            if (nt == 512) fast::k_height_maps_fast<512, 32><<<grid, 512, sm, stream>>>(d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2, peers);
+            else           fast::k_height_maps_fast<768, 32><<<grid, 768, sm, stream>>>(d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2, peers);
         }
     } else {
         int64_t blocks = (total + 255) / 256;
         int grid = (int)std::min<int64_t>(blocks, (int64_t)sm_count() * 8);
-        k_height_maps_exact<<<grid, 256, 0, stream>>>(d_quads, total, dim, cfg, d_out);
+        k_height_maps_exact<<<grid, 256, 0, stream>>>(d_quads, total, dim, cfg, d_out, peers);
     }
     count_launch();
     return check_cuda(cudaGetLastError(), "height map kernel launch");

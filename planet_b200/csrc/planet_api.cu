@@ -15,6 +15,8 @@ namespace planet {
 
 // launchers (k1_tessellate.cu, k2_heights.cu, k3_shade.cu)
 int launch_height_maps(const planet_gpu_params *, const Quad *, int64_t, int, int, float *, cudaStream_t);
+struct PeerOut { float *ptr[7]; int n; };
+int launch_height_maps_gathered(const planet_gpu_params *, const Quad *, int64_t, int, int, float *, const PeerOut &, cudaStream_t);
 int launch_heights_at(const planet_gpu_params *, const double *, int64_t, int, int, float *, cudaStream_t);
 int launch_noise(const double *, int64_t, int, double, float, int, int, float *, cudaStream_t);
 int launch_tessellate_uniform(const planet_gpu_params *, int, int64_t, int64_t, Quad *, uint32_t *, cudaStream_t);
@@ -335,6 +337,25 @@ int planet_gpu_generate_height_maps(const planet_gpu_params *p, const planet_gpu
     if (rc) return rc;
     if (nquads < 0 || (nquads > 0 && (!d_quads || !d_out))) return set_error(PLANET_E_INVALID, "NULL buffer");
     return launch_height_maps(p, (const Quad *)d_quads, nquads, dim, max_depth, d_out, (cudaStream_t)stream);
+}
+
+int planet_gpu_generate_height_maps_gathered(const planet_gpu_params *p, const planet_gpu_quad *d_quads,
+                                             int64_t nquads, int dim, int max_depth, float *d_out,
+                                             float *const *peer_out, int n_peers, void *stream)
+{
+    if (!ensure_init()) return PLANET_E_NO_DEVICE;
+    int rc = check_height_args(p, dim, max_depth);
+    if (rc) return rc;
+    if (nquads < 0 || (nquads > 0 && (!d_quads || !d_out))) return set_error(PLANET_E_INVALID, "NULL buffer");
+    if (n_peers < 0 || n_peers > 7 || (n_peers > 0 && !peer_out))
+        return set_error(PLANET_E_INVALID, "n_peers %d outside [0, 7]", n_peers);
+    PeerOut peers = {};
+    peers.n = n_peers;
+    for (int r = 0; r < n_peers; r++) {
+        if (!peer_out[r]) return set_error(PLANET_E_INVALID, "peer_out[%d] is NULL", r);
+        peers.ptr[r] = peer_out[r];
+    }
+    return launch_height_maps_gathered(p, (const Quad *)d_quads, nquads, dim, max_depth, d_out, peers, (cudaStream_t)stream);
 }
 
 int planet_gpu_heights_at(const planet_gpu_params *p, const double *d_xyz, int64_t n, int depth,

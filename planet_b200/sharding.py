@@ -41,3 +41,79 @@ def gather_patches(local, n_units=None):
     out = torch.empty((world * cmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, padded)
     return torch.cat([out[r * cmax:r * cmax + c] for r, c in enumerate(all_counts)])
+
+
+class PeerGather:
+    """All-gather of finished patches by direct peer writes over NVLink, overlapped with compute.
+
+    Every rank owns a full-size `gathered` buffer; the buffers are mapped into all ranks of the
+    node through CUDA IPC.  As soon as a chunk of a rank's shard is finished on the compute
+    stream, `push()` enqueues one device-to-device copy per peer on a side stream (copy engines,
+    no SM time), so the transfer of chunk c runs under the kernels of chunk c+1.  `finish()`
+    drains the side stream and synchronises the ranks.  Same result as one NCCL all-gather at the
+    end, without the serial 0.8 ms (8 GPUs, 67 MB shards).
+    """
+
+    def __init__(self, shard_shape, dtype=torch.float32, device=None):
+        if not dist.is_initialized():
+            raise RuntimeError("PeerGather needs an initialised process group")
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.shard_rows = shard_shape[0]
+        full = (self.world * shard_shape[0],) + tuple(shard_shape[1:])
+        self.gathered = torch.empty(full, dtype=dtype, device=self.device)
+        # exchange IPC handles of the gathered buffers
+        handle = self.gathered.untyped_storage()._share_cuda_()
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle)
+        self.peers = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.peers.append(self.gathered)
+                continue
+            storage = torch.UntypedStorage._new_shared_cuda(*((self.device.index,) + tuple(h[1:])))
+            t = torch.empty(0, dtype=dtype, device=self.device).set_(storage, 0, full)
+            self.peers.append(t)
+        # one side stream per peer so copies to different peers use different copy engines / links
+        self.side = [torch.cuda.Stream(device=self.device) for _ in range(max(self.world - 1, 1))]
+        dist.barrier()
+
+    def my_rows(self):
+        lo = self.rank * self.shard_rows
+        return lo, lo + self.shard_rows
+
+    def local_shard(self):
+        """The slice of this rank's own gathered buffer that its kernels should write into."""
+        lo, hi = self.my_rows()
+        return self.gathered[lo:hi]
+
+    def peer_shards(self):
+        """This rank's shard inside every PEER's gathered buffer (for kernels that store to peers
+        themselves, e.g. planet_gpu_generate_height_maps_gathered)."""
+        lo, hi = self.my_rows()
+        return [self.peers[(self.rank + k) % self.world][lo:hi] for k in range(1, self.world)]
+
+    def push(self, row_lo, row_hi, compute_stream=None):
+        """Rows [row_lo, row_hi) of the local shard are complete on `compute_stream`: copy them into
+        every peer's gathered buffer on the side stream."""
+        compute_stream = compute_stream or torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(compute_stream)
+        lo, _ = self.my_rows()
+        src = self.gathered[lo + row_lo: lo + row_hi]
+        for k in range(1, self.world):                          # staggered: rank r's k-th stream feeds peer r+k
+            r = (self.rank + k) % self.world
+            st = self.side[k - 1]
+            st.wait_event(ev)
+            with torch.cuda.stream(st):
+                self.peers[r][lo + row_lo: lo + row_hi].copy_(src, non_blocking=True)
+
+    def finish(self, compute_stream=None):
+        compute_stream = compute_stream or torch.cuda.current_stream(self.device)
+        for st in self.side:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            compute_stream.wait_event(ev)
+        torch.cuda.synchronize(self.device)
+        dist.barrier()                                          # every peer's writes into my buffer have landed
+        return self.gathered

@@ -532,3 +532,23 @@ def test_c4_shape_against_the_oracle(gpu, port):
     want = port.generate_height_maps(hq, 52, 18, orc_params(p), nthreads=4)
     assert np.abs(to_np(maps)[sel].astype(np.float64) - want).max() <= REL_TOL * 8848.0 * amp_sum(0.5, 12)
     check_shade(gpu, port, hq[:3], to_np(maps)[sel][:3], np.array([0.0, 0.0, -6371010.0]), n=50)
+
+
+def test_k2_fused_gather_stores_identical_bytes_to_every_peer(gpu):
+    """planet_gpu_generate_height_maps_gathered: the peer buffers (here: 7 more buffers on this GPU,
+    on an 8-GPU box: CUDA-IPC-mapped buffers of the other ranks) get exactly the local bytes."""
+    import torch
+    for prec, nq, dim in ((gpu.FAST, 3000, 32), (gpu.FAST, 40, 33), (gpu.EXACT, 64, 32)):
+        p = gpu.fbm_params(8, 0.5, prec)
+        quads = gpu.tessellate_uniform(6, first=100, nquads=nq)
+        want = gpu.generate_height_maps(quads, dim, 18, p)
+        for n_peers in (1, 7):
+            out = torch.zeros_like(want)
+            peers = [torch.full_like(want, -1.0) for _ in range(n_peers)]
+            gpu.generate_height_maps_gathered(quads, dim, 18, out, peers, p)
+            torch.cuda.synchronize()
+            assert torch.equal(out, want)
+            for t_ in peers:
+                assert torch.equal(t_, want)
+    with pytest.raises(gpu.PlanetGpuError, match="n_peers"):
+        gpu.generate_height_maps_gathered(quads, 32, 18, want, [want] * 8, p)
