@@ -277,6 +277,8 @@ def run_ours(args, rank, local_rank, world):
         fused_step_ms = float(np.mean(ts))
         k2(); dist.all_gather_into_tensor(allh, heights); torch.cuda.synchronize()
         gather_identical = bool(torch.equal(pg.gathered, allh))
+        del shard, peer_shards
+        pg.close()
 
     # max over ranks (device-timed)
     stats = torch.tensor([t_step.mean(), t_k1.mean(), t_k2.mean(), t_k3.mean(), e2e_ms,

@@ -78,6 +78,13 @@ class PeerGather:
         self.side = [torch.cuda.Stream(device=self.device) for _ in range(max(self.world - 1, 1))]
         dist.barrier()
 
+    def close(self):
+        """Drop the mappings of the peers' buffers before the owning processes go away."""
+        torch.cuda.synchronize(self.device)
+        dist.barrier()
+        self.peers = []
+        dist.barrier()
+
     def my_rows(self):
         lo = self.rank * self.shard_rows
         return lo, lo + self.shard_rows

@@ -552,3 +552,45 @@ def test_k2_fused_gather_stores_identical_bytes_to_every_peer(gpu):
                 assert torch.equal(t_, want)
     with pytest.raises(gpu.PlanetGpuError, match="n_peers"):
         gpu.generate_height_maps_gathered(quads, 32, 18, want, [want] * 8, p)
+
+
+def test_randomised_configurations_against_the_oracle(gpu, port):
+    """40 random (dim, octaves, gain, kind, seed offset, depth, batch) draws: EXACT bit-exact,
+    FAST within the stated tolerance -- through whichever table layout the batch size selects."""
+    rng = np.random.default_rng(20261018)
+    for trial in range(40):
+        dim = int(rng.choice([4, 5, 6, 7, 8, 9, 15, 16, 17, 31, 32, 33, 47, 64, 70]))
+        octaves = int(rng.integers(1, 21))
+        gain = float(rng.choice([0.3, 0.5, 0.55, 0.7, 0.9]))
+        kind = int(rng.choice([gpu.FBM, gpu.RIDGED]))
+        depth = int(rng.integers(0, 9))
+        nq = int(rng.integers(1, 40))
+        first = int(rng.integers(0, 6 * 4 ** depth - min(nq, 6 * 4 ** depth) + 1))
+        nq = min(nq, 6 * 4 ** depth - first)
+        seed = tuple(rng.uniform(-500, 500, 3)) if trial % 3 == 0 else (0.0, 0.0, 0.0)
+        scale = float(rng.choice([1e-5, 1e-5, 3e-6, 4e-5]))
+        quads = gpu.tessellate_uniform(depth, first=first, nquads=nq)
+        hq = gpu.quads_to_host(quads)
+        for prec in (gpu.EXACT, gpu.FAST):
+            p = gpu.default_params(noise_kind=kind, gain=gain, fixed_octaves=octaves, precision=prec,
+                                   coord_scale=scale, seed_offset=seed)
+            got = to_np(gpu.generate_height_maps(quads, dim, 18, p))
+            if seed == (0.0, 0.0, 0.0):
+                want = port.generate_height_maps(hq, dim, 18, orc_params(p))
+            else:
+                # the oracle has no seed: evaluate the fractal on the kernel's own (scaled + shifted) points
+                want = np.empty_like(got)
+                div = 1.0 / (dim - 3)
+                u = (np.arange(dim) - 1) * div
+                for k, q in enumerate(hq):
+                    p0 = q["p"][0][None, :] + (q["p"][1] - q["p"][0])[None, :] * u[:, None]
+                    p1 = q["p"][2][None, :] + (q["p"][3] - q["p"][2])[None, :] * u[:, None]
+                    pts = p0[None, :, :] + (p1 - p0)[None, :, :] * u[:, None, None]        # [y, x, 3]
+                    pts = pts * scale + np.array(seed)
+                    want[k] = (port.fractal(pts.reshape(-1, 3), kind, 2.0, gain, octaves) * np.float32(8848.0)).reshape(dim, dim)
+            tol = REL_TOL * 8848.0 * amp_sum(gain, octaves)
+            if prec == gpu.EXACT:
+                assert got.tobytes() == want.tobytes(), (trial, dim, octaves, gain, kind, depth, seed)
+            else:
+                err = np.abs(got.astype(np.float64) - want).max()
+                assert err <= tol, (trial, dim, octaves, gain, kind, depth, seed, err, tol)
