@@ -239,7 +239,7 @@ def run_ours(args, rank, local_rank, world):
     # ---- gather of finished patches (K4) ------------------------------------------------------
     # (a) NCCL all_gather_into_tensor after the step; (b) the gather fused into K2: every height is
     # also stored to the peers' IPC-mapped gathered buffers over NVLink while the kernel computes.
-    gather_ms, fused_step_ms, gather_identical = None, None, None
+    gather_ms, fused_step_ms, gather_identical, fused_error = None, None, None, None
     if world > 1:
         from planet_b200.sharding import PeerGather
         allh = torch.empty((world * nq, DIM, DIM), dtype=torch.float32, device=dev)
@@ -254,35 +254,48 @@ def run_ours(args, rank, local_rank, world):
         barrier()
         gather_ms = g0.elapsed_time(g1) / 5
 
-        pg = PeerGather((nq, DIM, DIM), device=dev)
-        shard, peer_shards = pg.local_shard(), pg.peer_shards()
-        peer_arr = (C.c_void_p * len(peer_shards))(*[t.data_ptr() for t in peer_shards])
+        fused_error = None
+        pg = None
+        try:                                                        # mapping the peers' buffers (CUDA IPC)
+            pg = PeerGather((nq, DIM, DIM), device=dev)
+        except Exception as exc:                                    # noqa: BLE001
+            fused_error = f"{type(exc).__name__}: {exc}"[:200]
+        ok = torch.tensor([0 if pg is None else 1], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)                   # all ranks take the same branch
+        try:
+            if ok.item() == 0:
+                raise RuntimeError(fused_error or "a peer rank could not map the gathered buffers")
+            shard, peer_shards = pg.local_shard(), pg.peer_shards()
+            peer_arr = (C.c_void_p * len(peer_shards))(*[t.data_ptr() for t in peer_shards])
 
-        def fused_step():
-            k1()
-            pb._check(L.planet_gpu_generate_height_maps_gathered(pp, quads.data_ptr(), nq, DIM, MAX_LOD, shard.data_ptr(),
-                                                                 peer_arr, len(peer_shards), sp))
-            pb._check(L.planet_gpu_shade(pp, quads.data_ptr(), nq, camv, shard.data_ptr(), -1.0,
-                                         pos.data_ptr(), nrm.data_ptr(), sp))
-            pg.finish(stream)
+            def fused_step():
+                k1()
+                pb._check(L.planet_gpu_generate_height_maps_gathered(pp, quads.data_ptr(), nq, DIM, MAX_LOD, shard.data_ptr(),
+                                                                     peer_arr, len(peer_shards), sp))
+                pb._check(L.planet_gpu_shade(pp, quads.data_ptr(), nq, camv, shard.data_ptr(), -1.0,
+                                             pos.data_ptr(), nrm.data_ptr(), sp))
+                pg.finish(stream)
 
-        for _ in range(3):
-            fused_step()
-        ts = []
-        for _ in range(args.steps):
-            barrier()
-            a, b_ = ev(), ev()
-            a.record(); fused_step(); b_.record(); torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b_))
-        fused_step_ms = float(np.mean(ts))
-        k2(); dist.all_gather_into_tensor(allh, heights); torch.cuda.synchronize()
-        gather_identical = bool(torch.equal(pg.gathered, allh))
-        del shard, peer_shards
-        pg.close()
+            for _ in range(3):
+                fused_step()
+            ts = []
+            for _ in range(args.steps):
+                barrier()
+                a, b_ = ev(), ev()
+                a.record(); fused_step(); b_.record(); torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b_))
+            fused_step_ms = float(np.mean(ts))
+            k2(); dist.all_gather_into_tensor(allh, heights); torch.cuda.synchronize()
+            gather_identical = bool(torch.equal(pg.gathered, allh))
+            del shard, peer_shards
+            pg.close()
+        except Exception as exc:                                    # noqa: BLE001 -- e.g. CUDA IPC unavailable on this box
+            fused_error = f"{type(exc).__name__}: {exc}"[:200]
+            fused_step_ms, gather_identical = None, None
 
     # max over ranks (device-timed)
     stats = torch.tensor([t_step.mean(), t_k1.mean(), t_k2.mean(), t_k3.mean(), e2e_ms,
-                          gather_ms or 0.0, fused_step_ms or 0.0, 0.0 if gather_identical else 1.0],
+                          gather_ms or 0.0, fused_step_ms if fused_step_ms else 1e9, 0.0 if gather_identical else 1.0],
                          dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
@@ -335,14 +348,17 @@ def run_ours(args, rank, local_rank, world):
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
-        if world > 1:
+        nccl_gather = {"value": total_verts / ((ms_step + gather_ms) * 1e-3) if world > 1 else None, "gather_ms": gather_ms,
+                       "collective": "nccl all_gather_into_tensor of height maps after the step"}
+        if world > 1 and fused_step_ms >= 1e8:                       # peer mapping failed on some rank: NCCL only
+            line["with_gather"] = dict(nccl_gather, unit="vertices/s", note="fused peer-store gather unavailable: " + str(fused_error))
+        elif world > 1:
             line["with_gather"] = {
                 "value": total_verts / (fused_step_ms * 1e-3), "unit": "vertices/s", "ms_per_step": fused_step_ms,
                 "method": "gather fused into K2: heights stored to every peer's CUDA-IPC-mapped buffer over NVLink "
                           "while the kernel computes (planet_gpu_generate_height_maps_gathered) + one barrier",
                 "bytes_per_gpu": nq * DIM * DIM * 4, "identical_to_nccl_all_gather": gather_bad == 0.0,
-                "nccl": {"value": total_verts / ((ms_step + gather_ms) * 1e-3), "gather_ms": gather_ms,
-                         "collective": "nccl all_gather_into_tensor of height maps after the step"}}
+                "nccl": nccl_gather}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
