@@ -245,6 +245,13 @@ static struct LodScratch {
     void *buf = nullptr; size_t cap = 0;
 } g_lod;
 
+void release_lod_scratch()                                            // planet_gpu_shutdown
+{
+    std::lock_guard<std::mutex> lock(g_lod_mutex);
+    if (g_lod.buf) cudaFree(g_lod.buf);
+    g_lod.buf = nullptr; g_lod.cap = 0;
+}
+
 int launch_select_lod(const planet_gpu_params *p, const double *cam, int max_lod, Quad *d_out,
                       int64_t capacity, int64_t *count, cudaStream_t stream)
 {

@@ -30,7 +30,10 @@
 //  * 768-thread CTAs, one per SM (192 KB of tables), persistent; warps take 128-sample
 //    tiles round-robin; each thread owns 2 consecutive texels and carries them as one
 //    packed f32x2 pair: every FADD/FMUL/FFMA of fade, gradient dots, lerps and the octave
-//    accumulation is an FADD2/FMUL2/FFMA2 -- half the issue slots (the kernel is issue-bound).
+//    accumulation is an FADD2/FMUL2/FFMA2.  Measured (tools/microbench2.cu): a packed op
+//    holds the issue port for two cycles, so this halves instruction count and register
+//    pressure but not issue time -- the kernel is issue-bound at ~117 slots per
+//    octave-sample (DESIGN.md, K2 roofline).
 //  * Per-tile prologue: one thread per touched quad turns the 104-byte Quad into the
 //    bilinear form P = A + B x + y (C + D x) per axis in doubles pre-scaled by 2^55
 //    (same sample points as main.cpp:132-146 up to 1 ulp of double), so a sample's

@@ -27,6 +27,7 @@ int launch_shade(const planet_gpu_params *, const Quad *, int64_t, const double 
 int launch_select_lod(const planet_gpu_params *, const double *, int, Quad *, int64_t, int64_t *, cudaStream_t);
 uint32_t host_strip_index(int, int);
 uint64_t host_uniform_leaf_id(int64_t, int);
+void release_lod_scratch();
 
 // ---- state ------------------------------------------------------------------------------
 static thread_local char t_error[512] = "";
@@ -210,6 +211,7 @@ void planet_gpu_shutdown(void)
         for (auto &e : g_stage.chunk_done) if (e) cudaEventDestroy(e);
     }
     g_stage = Staging();
+    release_lod_scratch();
     g_ready = false;
 }
 
@@ -291,28 +293,36 @@ int planet_gpu_generate_height_maps_host(const planet_gpu_params *p, const plane
     float *d_out = d_mirror ? d_mirror : (float *)g_stage.d_out;
     // Caller memory may be pageable; cudaMemcpyAsync then stages through the driver's own
     // pinned buffers.  Callers that want full PCIe rate pass cudaHostRegister'ed memory.
-    PLANET_CUDA(cudaMemcpyAsync(g_stage.d_in, h_quads, in_bytes, cudaMemcpyHostToDevice, g_stage.stream));
     // The output (dim*dim*4 bytes per quad) dominates the PCIe traffic, so large batches run as
     // a pipeline: kernel on chunk c while chunk c-1 drains to the host on the copy stream.
     const int chunks = nquads >= 4096 ? 8 : nquads >= 256 ? 4 : 1;
     const size_t per_quad = (size_t)dim * dim;
-    for (int c = 0; c < chunks; c++) {
-        const int64_t lo = nquads * c / chunks, hi = nquads * (c + 1) / chunks;
-        if (hi == lo) continue;
-        rc = launch_height_maps(p, (const Quad *)g_stage.d_in + lo, hi - lo, dim, max_depth,
-                                d_out + lo * per_quad, g_stage.stream);
-        if (rc) return rc;
-        cudaStream_t cs = chunks > 1 ? g_stage.copy_stream : g_stage.stream;
-        if (chunks > 1) {
-            PLANET_CUDA(cudaEventRecord(g_stage.chunk_done[c], g_stage.stream));
-            PLANET_CUDA(cudaStreamWaitEvent(cs, g_stage.chunk_done[c], 0));
+    auto enqueue = [&]() -> int {
+        PLANET_CUDA(cudaMemcpyAsync(g_stage.d_in, h_quads, in_bytes, cudaMemcpyHostToDevice, g_stage.stream));
+        for (int c = 0; c < chunks; c++) {
+            const int64_t lo = nquads * c / chunks, hi = nquads * (c + 1) / chunks;
+            if (hi == lo) continue;
+            int r = launch_height_maps(p, (const Quad *)g_stage.d_in + lo, hi - lo, dim, max_depth,
+                                       d_out + lo * per_quad, g_stage.stream);
+            if (r) return r;
+            cudaStream_t cs = chunks > 1 ? g_stage.copy_stream : g_stage.stream;
+            if (chunks > 1) {
+                PLANET_CUDA(cudaEventRecord(g_stage.chunk_done[c], g_stage.stream));
+                PLANET_CUDA(cudaStreamWaitEvent(cs, g_stage.chunk_done[c], 0));
+            }
+            PLANET_CUDA(cudaMemcpyAsync(h_out + lo * per_quad, d_out + lo * per_quad,
+                                        (size_t)(hi - lo) * per_quad * sizeof(float), cudaMemcpyDeviceToHost, cs));
         }
-        PLANET_CUDA(cudaMemcpyAsync(h_out + lo * per_quad, d_out + lo * per_quad,
-                                    (size_t)(hi - lo) * per_quad * sizeof(float), cudaMemcpyDeviceToHost, cs));
-    }
-    PLANET_CUDA(cudaStreamSynchronize(g_stage.stream));
-    if (chunks > 1) PLANET_CUDA(cudaStreamSynchronize(g_stage.copy_stream));
-    return 0;
+        return 0;
+    };
+    rc = enqueue();
+    // Drain both streams whatever happened: copies already queued write into the caller's
+    // buffer, which must not be touched after this call returns.
+    cudaError_t e1 = cudaStreamSynchronize(g_stage.stream);
+    cudaError_t e2 = chunks > 1 ? cudaStreamSynchronize(g_stage.copy_stream) : cudaSuccess;
+    if (rc) return rc;
+    if (e1 != cudaSuccess) return check_cuda(e1, "height maps (host path)");
+    return check_cuda(e2, "height maps D2H");
 }
 
 void planet_gpu_generate_height_map(float *data, int dim, const void *quad, int max_depth)
