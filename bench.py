@@ -218,17 +218,18 @@ def run_ours(args, rank, local_rank, world):
     ms_k2_exact = float(np.mean(ex_t))
     k2()                                                               # restore the FAST heights for K3 / e2e
 
-    # ---- e2e: the reference-facing host-buffer call (H2D quads, K2, D2H heights) + K3 on device ----
+    # ---- e2e: the host-buffer call a reference-side caller makes: H2D quads, K2, D2H heights, and
+    # K3 on the device-resident maps (the GL texture's role) while the last maps cross PCIe ----
     h_quads = torch.empty((nq, 13), dtype=torch.int64).pin_memory()
     h_quads.copy_(quads.cpu())
     h_out = torch.empty((nq, DIM, DIM), dtype=torch.float32).pin_memory()
+    cam3 = (C.c_double * 3)(*cam)
     e2e_t = []
     for i in range(3 + args.steps):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        pb._check(L.planet_gpu_generate_height_maps_host(pp, h_quads.data_ptr(), nq, DIM, MAX_LOD,
-                                                         h_out.data_ptr(), heights.data_ptr()))
-        k3()                                           # consumes the device-resident mirror (the GL texture's role)
+        pb._check(L.planet_gpu_terrain_host(pp, h_quads.data_ptr(), nq, MAX_LOD, cam3, -1.0, h_out.data_ptr(),
+                                            heights.data_ptr(), pos.data_ptr(), nrm.data_ptr()))
         torch.cuda.synchronize()
         if i >= 3:
             e2e_t.append(time.perf_counter() - t0)
@@ -344,7 +345,7 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": total_verts / (e2e_ms * 1e-3), "unit": "vertices/s",
                     "h2d_bytes_per_step": nq * 104, "d2h_bytes_per_step": nq * DIM * DIM * 4,
                     "ms_per_step": e2e_ms,
-                    "path": "planet_gpu_generate_height_maps_host (pinned host quads -> pinned host heights) + K3"},
+                    "path": "planet_gpu_terrain_host: pinned host quads -> K2 -> pinned host heights (8-chunk pipeline) + K3 on the resident maps"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }

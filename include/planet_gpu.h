@@ -214,6 +214,15 @@ int planet_gpu_generate_height_maps_host(const planet_gpu_params *p, const plane
                                          int64_t nquads, int dim, int max_depth, float *h_out,
                                          float *d_mirror);
 
+/* One frame's worth of the whole path for a caller with HOST quads: H2D quads, K2 (dim =
+ * patch_verts + 2), the height maps to h_heights (what the reference uploads with glTexImage2D,
+ * main.cpp:245) AND resident in d_heights, then K3 (main.cpp:348-380) into d_pos4 / d_nrm4 on the
+ * device while the last height maps are still crossing PCIe.  Returns when everything is done.
+ * cam_pos: 3 host doubles; max_skirt < 0 = planet_gpu_max_skirt_size(radius, patch_verts). */
+int planet_gpu_terrain_host(const planet_gpu_params *p, const planet_gpu_quad *h_quads, int64_t nquads,
+                            int max_depth, const double *cam_pos, float max_skirt, float *h_heights,
+                            float *d_heights, float *d_pos4, float *d_nrm4);
+
 /* ---- measurement helpers ------------------------------------------------------------- */
 /* dependent-free FFMA loop on every SM for about `ms` milliseconds; returns achieved
  * FP32 TFLOP/s (2 flop per FFMA) and the elapsed device time; the FP32 roofline

@@ -87,6 +87,7 @@ def lib():
             "planet_gpu_cache_read_slots": (i, [vp, vp, i64, vp]),
             "planet_gpu_shade_cached": (i, [pp, vp, i64, vp, vp, vp, f, vp, vp, vp]),
             "planet_gpu_generate_height_maps_host": (i, [pp, vp, i64, i, i, vp, vp]),
+            "planet_gpu_terrain_host": (i, [pp, vp, i64, i, vp, f, vp, vp, vp, vp]),
             "planet_gpu_measure_fp32_peak": (i, [d, C.POINTER(d), C.POINTER(d)]),
             "planet_gpu_launch_count": (i64, []),
         }
@@ -106,6 +107,7 @@ EXPORTED_SYMBOLS = [
     "planet_gpu_patch_index_count", "planet_gpu_strip_index", "planet_gpu_uniform_leaf_id",
     "planet_gpu_max_lod", "planet_gpu_max_skirt_size",
     "planet_gpu_select_lod", "planet_gpu_shade", "planet_gpu_generate_height_maps_host",
+    "planet_gpu_terrain_host",
     "planet_gpu_cache_create", "planet_gpu_cache_destroy", "planet_gpu_cache_count",
     "planet_gpu_cache_plan_frame", "planet_gpu_cache_frame", "planet_gpu_cache_pool",
     "planet_gpu_cache_read_slots", "planet_gpu_shade_cached", "planet_gpu_measure_fp32_peak",
@@ -305,6 +307,29 @@ def generate_height_maps_host(quads_np, dim, max_depth, params=None, out=None, m
                                                       out.ctypes.data,
                                                       mirror.data_ptr() if mirror is not None else None))
     return out
+
+
+def terrain_host(quads_np, max_depth, cam_pos, params=None, max_skirt=-1.0, out=None, heights=None,
+                 pos=None, nrm=None):
+    """Host quads in; height maps out on the host AND resident on the device, displaced positions +
+    normals on the device (K3 runs while the last maps cross PCIe).  Returns (out, heights, pos, nrm)."""
+    torch = _torch()
+    params = params or default_params()
+    q = np.ascontiguousarray(quads_np, QUAD_DTYPE)
+    n, dim = len(q), params.patch_verts + 2
+    nv = patch_vertex_count(params.patch_verts)
+    if out is None:
+        out = np.empty((n, dim, dim), np.float32)
+    if heights is None:
+        heights = torch.empty((n, dim, dim), dtype=torch.float32, device="cuda")
+    if pos is None:
+        pos = torch.empty((n, nv, 4), dtype=torch.float32, device="cuda")
+    if nrm is None:
+        nrm = torch.empty((n, nv, 4), dtype=torch.float32, device="cuda")
+    cam = (C.c_double * 3)(*[float(c) for c in cam_pos])
+    _check(lib().planet_gpu_terrain_host(C.byref(params), q.ctypes.data, n, max_depth, cam, max_skirt,
+                                         out.ctypes.data, heights.data_ptr(), pos.data_ptr(), nrm.data_ptr()))
+    return out, heights, pos, nrm
 
 
 def set_params(params):

@@ -274,9 +274,13 @@ float planet_gpu_get_height_at(const double *p, int depth, int max_depth)
     return result;
 }
 
-int planet_gpu_generate_height_maps_host(const planet_gpu_params *p, const planet_gpu_quad *h_quads,
-                                         int64_t nquads, int dim, int max_depth, float *h_out,
-                                         float *d_mirror)
+// shared body of the two host-buffer calls: H2D quads, K2 in chunks with the D2H of finished
+// chunks overlapped on the copy stream, optionally K3 on the resident maps while the last
+// chunks still drain
+struct ShadeArgs { const double *cam_pos; float max_skirt; float *d_pos4, *d_nrm4; };
+
+static int host_pipeline(const planet_gpu_params *p, const planet_gpu_quad *h_quads, int64_t nquads, int dim,
+                         int max_depth, float *h_out, float *d_mirror, const ShadeArgs *shade)
 {
     if (!ensure_init()) return PLANET_E_NO_DEVICE;
     int rc = check_height_args(p, dim, max_depth);
@@ -313,6 +317,9 @@ int planet_gpu_generate_height_maps_host(const planet_gpu_params *p, const plane
             PLANET_CUDA(cudaMemcpyAsync(h_out + lo * per_quad, d_out + lo * per_quad,
                                         (size_t)(hi - lo) * per_quad * sizeof(float), cudaMemcpyDeviceToHost, cs));
         }
+        if (shade)                                                    // K3 reads the resident maps; the PCIe drain goes on beside it
+            return launch_shade(p, (const Quad *)g_stage.d_in, nquads, shade->cam_pos, d_out, nullptr,
+                                shade->max_skirt, shade->d_pos4, shade->d_nrm4, g_stage.stream);
         return 0;
     };
     rc = enqueue();
@@ -323,6 +330,25 @@ int planet_gpu_generate_height_maps_host(const planet_gpu_params *p, const plane
     if (rc) return rc;
     if (e1 != cudaSuccess) return check_cuda(e1, "height maps (host path)");
     return check_cuda(e2, "height maps D2H");
+}
+
+int planet_gpu_generate_height_maps_host(const planet_gpu_params *p, const planet_gpu_quad *h_quads,
+                                         int64_t nquads, int dim, int max_depth, float *h_out,
+                                         float *d_mirror)
+{
+    return host_pipeline(p, h_quads, nquads, dim, max_depth, h_out, d_mirror, nullptr);
+}
+
+int planet_gpu_terrain_host(const planet_gpu_params *p, const planet_gpu_quad *h_quads, int64_t nquads,
+                            int max_depth, const double *cam_pos, float max_skirt, float *h_heights,
+                            float *d_heights, float *d_pos4, float *d_nrm4)
+{
+    int rc = validate_params(p);
+    if (rc) return rc;
+    if (!cam_pos || !d_heights) return set_error(PLANET_E_INVALID, "NULL argument");
+    if (max_skirt < 0.0f) max_skirt = planet_gpu_max_skirt_size(p->radius, p->patch_verts);
+    const ShadeArgs shade = { cam_pos, max_skirt, d_pos4, d_nrm4 };
+    return host_pipeline(p, h_quads, nquads, p->patch_verts + 2, max_depth, h_heights, d_heights, &shade);
 }
 
 void planet_gpu_generate_height_map(float *data, int dim, const void *quad, int max_depth)

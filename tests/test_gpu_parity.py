@@ -300,6 +300,25 @@ def test_host_batch_path_equals_device_path(gpu, golden):
     assert host.tobytes() == dev.tobytes()
 
 
+@pytest.mark.parametrize("nquads", [117, 1024, 6144])           # 1, 4 and 8 pipeline chunks
+def test_terrain_host_equals_separate_calls(gpu, nquads):
+    """planet_gpu_terrain_host = generate_height_maps_host + shade, byte for byte (K3 only
+    overlaps the PCIe drain; it must still see every finished map)."""
+    torch = gpu._torch()
+    p = gpu.fbm_params(octaves=8, gain=0.5, precision=gpu.FAST)
+    depth = 6
+    first = 4 ** depth + 11
+    dq = gpu.tessellate_uniform(depth, first, nquads, p)
+    quads = to_np(dq).view(gpu.QUAD_DTYPE).reshape(-1)
+    cam = (0.0, 0.0, 3.0 * p.radius)
+    out, heights, pos, nrm = gpu.terrain_host(quads, 18, cam, p)
+    want_h = gpu.generate_height_maps_host(quads, 32, 18, p)
+    assert out.tobytes() == want_h.tobytes()
+    assert to_np(heights).tobytes() == want_h.tobytes()
+    want_pos, want_nrm = gpu.shade(dq, heights, cam, p)
+    assert torch.equal(pos, want_pos) and torch.equal(nrm, want_nrm)
+
+
 def test_seed_offset_is_a_coordinate_shift(gpu, port):
     rng = np.random.default_rng(3)
     pts = rng.normal(size=(4096, 3)); pts = pts / np.linalg.norm(pts, axis=1, keepdims=True) * 6371000.0
