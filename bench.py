@@ -108,6 +108,7 @@ def cpu_reference_run(nquads, threads, repeats=1):
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     assert np.isfinite(maps).all()
+    cpu_reference_run.last_maps = maps
     return nquads * DIM * DIM / best, orc.kind, best
 
 
@@ -216,6 +217,7 @@ def run_ours(args, rank, local_rank, world):
         if i >= 2:
             ex_t.append(a.elapsed_time(b_))
     ms_k2_exact = float(np.mean(ex_t))
+    exact_maps_host = heights.cpu().numpy() if (rank == 0 and world == 1) else None
     k2()                                                               # restore the FAST heights for K3 / e2e
 
     # ---- e2e: the host-buffer call a reference-side caller makes: H2D quads, K2, D2H heights, and
@@ -313,6 +315,10 @@ def run_ours(args, rank, local_rank, world):
         total_verts = VERTS_PER_GPU * world
         cores = host_cores()
         cpu_v, cpu_kind, cpu_s = cpu_reference_run(QUADS_PER_FACE, cores)
+        # both sides computed the same thing: the CPU maps are the bytes the EXACT-mode kernel produced
+        same_bytes = None if exact_maps_host is None else (
+            exact_maps_host.tobytes() == np.ascontiguousarray(cpu_reference_run.last_maps).tobytes())
+        cpu1_v, _, cpu1_s = cpu_reference_run(1024, 1)                      # what the reference itself does: one thread
         line = {
             "metric": METRIC, "value": total_verts / (ms_step * 1e-3), "unit": "vertices/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
@@ -341,7 +347,10 @@ def run_ours(args, rank, local_rank, world):
                             "bytes": k3_bytes, "peak_source": peak_src},
             "cpu_baseline": {"value": cpu_v, "unit": "vertices/s", "cores": cores, "kind": cpu_kind,
                              "sample": f"{QUADS_PER_FACE} quads x {DIM}^2 (full C2 batch), GenerateHeightMap only, "
-                                       f"{cpu_s:.2f} s wall"},
+                                       f"{cpu_s:.2f} s wall",
+                             "single_thread_value": cpu1_v,
+                             "single_thread_sample": f"1024 quads x {DIM}^2, {cpu1_s:.2f} s wall",
+                             "same_bytes_as_gpu_exact_mode": same_bytes},
             "e2e": {"value": total_verts / (e2e_ms * 1e-3), "unit": "vertices/s",
                     "h2d_bytes_per_step": nq * 104, "d2h_bytes_per_step": nq * DIM * DIM * 4,
                     "ms_per_step": e2e_ms,
