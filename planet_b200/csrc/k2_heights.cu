@@ -143,6 +143,7 @@ template <int REPL> struct Layout {
     static constexpr int LOG12 = REPL == 32 ? 7 : REPL == 16 ? 6 : REPL == 8 ? 5 : REPL == 4 ? 4 : REPL == 2 ? 3 : 2;
     static constexpr int LOG3 = LOG12 + 1;
 };
+constexpr uint32_t ONE_BITS = 0x3F800000u;                 // float 1.0, see splice_mantissa
 constexpr double FIX_ONE = 36028797018963968.0;           // 2^55
 constexpr double FIX_WRAP = 256.0 * 36028797018963968.0;  // 2^63: one period of cell & 255
 
@@ -235,13 +236,23 @@ __device__ __forceinline__ f2 lerp2(f2 a, f2 b, f2 t) { return fma2(sub2(b, a), 
 
 struct Fixed3 { uint32_t xlo, xhi, ylo, yhi, zlo, zhi; };
 
+// (w & 0x007FFFFF) | one_bits as ONE LOP3.  one_bits is 0x3F800000 (float 1.0) handed down from a
+// kernel argument: written as two immediates the compiler needs two LOP3 (one immediate slot per
+// instruction), and this runs three times per octave-sample in an issue-bound loop.
+__device__ __forceinline__ float splice_mantissa(uint32_t w, uint32_t one_bits)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, 0x007FFFFF, %2, 0xEA;" : "=r"(d) : "r"(w), "r"(one_bits));
+    return __uint_as_float(d);
+}
+
 // hash chain R(R(R(ix)+iy)+iz) of one sample for octave k (perlin.h:45): returns the four
 // {z, z+1} gradient-code pairs of the (x, y) columns 00, 10, 01, 11 and the three fractions
 struct Hashed { uint2 e00, e10, e01, e11; float mx, my, mz; };
 
 template <int REPL>
 __device__ __forceinline__ Hashed hash_octave(const unsigned char *t12_lane, const unsigned char *t3_lane,
-                                              const Fixed3 &p, int k)
+                                              const Fixed3 &p, int k, uint32_t one_bits)
 {
     using L = Layout<REPL>;
     constexpr int T12_ROW = L::T12_ROW, T3_ROW = L::T3_ROW;
@@ -250,9 +261,9 @@ __device__ __forceinline__ Hashed hash_octave(const unsigned char *t12_lane, con
     uint32_t wy = __funnelshift_l(p.ylo, p.yhi, k);
     uint32_t wz = __funnelshift_l(p.zlo, p.zhi, k);
     Hashed h;
-    h.mx = __uint_as_float((wx & 0x007FFFFFu) | 0x3F800000u);       // 1 + fraction, 23 bits
-    h.my = __uint_as_float((wy & 0x007FFFFFu) | 0x3F800000u);
-    h.mz = __uint_as_float((wz & 0x007FFFFFu) | 0x3F800000u);
+    h.mx = splice_mantissa(wx, one_bits);                           // 1 + fraction, 23 bits
+    h.my = splice_mantissa(wy, one_bits);
+    h.mz = splice_mantissa(wz, one_bits);
     uint32_t cx = (wx >> (23 - L::LOG12)) & (255u << L::LOG12);     // (cell & 255) * T12_ROW
     uint32_t cy = (wy >> (23 - L::LOG12)) & (255u << L::LOG12);
     uint32_t cz = (wz >> (23 - L::LOG3)) & (255u << L::LOG3);       // (cell & 255) * T3_ROW
@@ -270,10 +281,10 @@ __device__ __forceinline__ Hashed hash_octave(const unsigned char *t12_lane, con
 // 2 * PerlinNoise3 of octave k for the thread's two samples (perlin.h:50-88)
 template <int REPL>
 __device__ __forceinline__ f2 noise_octave2(const unsigned char *t12_lane, const unsigned char *t3_lane,
-                                            const Fixed3 &pa, const Fixed3 &pb, int k)
+                                            const Fixed3 &pa, const Fixed3 &pb, int k, uint32_t one_bits)
 {
-    Hashed A = hash_octave<REPL>(t12_lane, t3_lane, pa, k);
-    Hashed B = hash_octave<REPL>(t12_lane, t3_lane, pb, k);
+    Hashed A = hash_octave<REPL>(t12_lane, t3_lane, pa, k, one_bits);
+    Hashed B = hash_octave<REPL>(t12_lane, t3_lane, pb, k, one_bits);
     f2 mx = pack(A.mx, B.mx), my = pack(A.my, B.my), mz = pack(A.mz, B.mz);
     f2 x0 = add2(mx, splat(-1.0f)), x1 = add2(mx, splat(-2.0f));    // fraction, fraction - 1 (exact)
     f2 y0 = add2(my, splat(-1.0f)), y1 = add2(my, splat(-2.0f));
@@ -296,7 +307,7 @@ __device__ __forceinline__ f2 noise_octave2(const unsigned char *t12_lane, const
 template <int REPL, bool GUARD>
 __device__ __forceinline__ void fractal_loop(const unsigned char *t12_lane, const unsigned char *t3_lane,
                                              const Fixed3 (&p)[S], const int (&octaves)[S], int omax,
-                                             int kind, float gain, float (&value)[S])
+                                             int kind, float gain, uint32_t one_bits, float (&value)[S])
 {
     float half_amp = 0.5f;
     if (kind == PLANET_NOISE_RIDGED) {                               // main.cpp:716-731
@@ -304,7 +315,7 @@ __device__ __forceinline__ void fractal_loop(const unsigned char *t12_lane, cons
         value[0] = value[1] = 0.0f;
         for (int k = 0; k < omax; k++) {
             float n[S];
-            unpack(noise_octave2<REPL>(t12_lane, t3_lane, p[0], p[1], k), n[0], n[1]);
+            unpack(noise_octave2<REPL>(t12_lane, t3_lane, p[0], p[1], k, one_bits), n[0], n[1]);
 #pragma unroll
             for (int s = 0; s < S; s++) {
                 float v = fmaf(-0.5f, fabsf(n[s]), 1.0f);           // offset - |noise|
@@ -318,7 +329,7 @@ __device__ __forceinline__ void fractal_loop(const unsigned char *t12_lane, cons
         f2 acc = splat(0.0f);
 #pragma unroll K2_UNROLL
         for (int k = 0; k < omax; k++) {
-            f2 n = noise_octave2<REPL>(t12_lane, t3_lane, p[0], p[1], k);
+            f2 n = noise_octave2<REPL>(t12_lane, t3_lane, p[0], p[1], k, one_bits);
             if (GUARD) {
                 float lo, hi, alo, ahi;
                 unpack(fma2(n, splat(half_amp), acc), lo, hi);
@@ -336,11 +347,11 @@ __device__ __forceinline__ void fractal_loop(const unsigned char *t12_lane, cons
 template <int REPL>
 __device__ __forceinline__ void fractal(const unsigned char *t12_lane, const unsigned char *t3_lane,
                                         const Fixed3 (&p)[S], const int (&octaves)[S], int kind,
-                                        float gain, float (&value)[S])
+                                        float gain, uint32_t one_bits, float (&value)[S])
 {
     int omax = max(octaves[0], octaves[1]);
-    if (octaves[0] == octaves[1]) fractal_loop<REPL, false>(t12_lane, t3_lane, p, octaves, omax, kind, gain, value);
-    else                          fractal_loop<REPL, true>(t12_lane, t3_lane, p, octaves, omax, kind, gain, value);
+    if (octaves[0] == octaves[1]) fractal_loop<REPL, false>(t12_lane, t3_lane, p, octaves, omax, kind, gain, one_bits, value);
+    else                          fractal_loop<REPL, true>(t12_lane, t3_lane, p, octaves, omax, kind, gain, one_bits, value);
 }
 
 // reduce a scaled coordinate (units of 2^-55) to one period and convert to fixed point
@@ -367,14 +378,20 @@ constexpr int SUB = 2;
 constexpr int WTILE = 32 * S * SUB;                      // 128 samples per warp tile
 constexpr int MAX_WTILE_QUADS = WTILE / 16 + 2;          // dim >= 4
 
-template <int NTHREADS, int REPL>
+// GATHER is a template flag, not a run-time test of peers.n: with the peer pointers live in the
+// plain kernel the octave loop grew by 14 address adds (register pressure), 6 % of the run time.
+template <int NTHREADS, int REPL, bool GATHER>
 __global__ void __launch_bounds__(NTHREADS, REPL == 32 ? 1 : 2)
 k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, HeightCfg cfg,
                    float *__restrict__ out, int64_t nwtiles, int out_aligned8,
-                   uint64_t magic_dim, uint64_t magic_dim2, PeerOut peers)
+                   uint64_t magic_dim, uint64_t magic_dim2, uint32_t one_bits, PeerOut peers)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     using L = Layout<REPL>;
+    // the peer pointers wait in shared memory until the stores: held in registers across the
+    // octave loop they cost it 14 rematerialised address adds
+    __shared__ float *s_peer[7];
+    if (GATHER && threadIdx.x < 7) s_peer[threadIdx.x] = peers.ptr[threadIdx.x];
     build_tables<REPL>(smem);
     __syncthreads();
 
@@ -487,25 +504,29 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
             if (cfg.kind == PLANET_NOISE_ZERO) {
                 value[0] = value[1] = 0.0f;
             } else {
-                fractal<REPL>(t12_lane, t3_lane, p, oct, cfg.kind, cfg.gain, value);
+                fractal<REPL>(t12_lane, t3_lane, p, oct, cfg.kind, cfg.gain, one_bits, value);
             }
 
             const int64_t o = base + i0;                                     // even
             if (out_aligned8 && i0 + 1 < n_here) {
                 const float2 h2 = make_float2(value[0] * cfg.height_scale, value[1] * cfg.height_scale);
                 __stcs(reinterpret_cast<float2 *>(out + o), h2);
+                if constexpr (GATHER) {
 #pragma unroll
-                for (int r = 0; r < 7; r++)                                  // NVLink peer stores (fused gather)
-                    if (r < peers.n) __stcs(reinterpret_cast<float2 *>(peers.ptr[r] + o), h2);
+                    for (int r = 0; r < 7; r++)                              // NVLink peer stores (fused gather)
+                        if (r < peers.n) __stcs(reinterpret_cast<float2 *>(((float *volatile *)s_peer)[r] + o), h2);
+                }
             } else {
 #pragma unroll
                 for (int sidx = 0; sidx < S; sidx++)
                     if (i0 + sidx < n_here) {
                         const float h = value[sidx] * cfg.height_scale;
                         out[o + sidx] = h;
+                        if constexpr (GATHER) {
 #pragma unroll
-                        for (int r = 0; r < 7; r++)
-                            if (r < peers.n) peers.ptr[r][o + sidx] = h;
+                            for (int r = 0; r < 7; r++)
+                                if (r < peers.n) ((float *volatile *)s_peer)[r][o + sidx] = h;
+                        }
                     }
             }
         }
@@ -521,7 +542,7 @@ template <int REPL>
 __global__ void __launch_bounds__(THREADS, REPL == 32 ? 1 : 2)
 k_points_fast(const double *__restrict__ xyz, int64_t n, int kind, float gain, int octaves,
               double coord_scale, double sx, double sy, double sz, float height_scale,
-              float *__restrict__ out, int64_t ntiles)
+              float *__restrict__ out, int64_t ntiles, uint32_t one_bits)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     build_tables<REPL>(smem);
@@ -552,7 +573,7 @@ k_points_fast(const double *__restrict__ xyz, int64_t n, int kind, float gain, i
             oct[s] = octaves;
         }
         float value[S];
-        fractal<REPL>(t12_lane, t3_lane, p, oct, kind, gain, value);
+        fractal<REPL>(t12_lane, t3_lane, p, oct, kind, gain, one_bits, value);
 #pragma unroll
         for (int s = 0; s < S; s++)
             if (idx[s] < n) out[idx[s]] = value[s] * height_scale;
@@ -611,9 +632,13 @@ static int prepare_fast()
 {
     const int dev = current_device();
     if (!g_fast_attr_set[dev]) {
-        PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_fast<512, 32>,
+        PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_fast<512, 32, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
-        PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_fast<768, 32>,
+        PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_fast<768, 32, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
+        PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_fast<512, 32, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
+        PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_fast<768, 32, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
         PLANET_CUDA(cudaFuncSetAttribute(fast::k_points_fast<32>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
@@ -628,7 +653,7 @@ static void launch_points(int grid, cudaStream_t stream, const double *d_xyz, in
                           int64_t ntiles)
 {
     fast::k_points_fast<REPL><<<grid, fast::THREADS, fast::smem_bytes<REPL>(fast::THREADS), stream>>>(
-        d_xyz, n, kind, gain, octaves, scale, sx, sy, sz, hs, d_out, ntiles);
+        d_xyz, n, kind, gain, octaves, scale, sx, sy, sz, hs, d_out, ntiles, fast::ONE_BITS);
 }
 
 // FAST handles the lattice split as shifts, which needs lacunarity == 2 and every octave's
@@ -668,17 +693,19 @@ int launch_height_maps_gathered(const planet_gpu_params *p, const Quad *d_quads,
         const uint64_t m1 = (one40 + dim - 1) / dim, m2 = (one40 + (uint64_t)dim * dim - 1) / ((uint64_t)dim * dim);
         int al = (reinterpret_cast<uintptr_t>(d_out) & 7) == 0;
         for (int r = 0; r < peers.n; r++) al = al && (reinterpret_cast<uintptr_t>(peers.ptr[r]) & 7) == 0;
+        const bool gather = peers.n > 0;
         if (total <= k2_small_max()) {
             // latency path: compact tables (6 KB), 256-thread CTAs spread over the whole chip
             int grid = (int)std::min<int64_t>((nwtiles + 7) / 8, (int64_t)sm_count() * 8);
-            fast::k_height_maps_fast<256, 1><<<grid, 256, fast::smem_bytes<1>(256), stream>>>(
-                d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2, peers);
+            auto kern = gather ? fast::k_height_maps_fast<256, 1, true> : fast::k_height_maps_fast<256, 1, false>;
+            kern<<<grid, 256, fast::smem_bytes<1>(256), stream>>>(d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2, fast::ONE_BITS, peers);
         } else {
             const int nt = k2_threads();
             int grid = (int)std::min<int64_t>((nwtiles + nt / 32 - 1) / (nt / 32), sm_count());
             const size_t sm = fast::smem_bytes<32>(nt);
-            if (nt == 512) fast::k_height_maps_fast<512, 32><<<grid, 512, sm, stream>>>(d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2, peers);
-            else           fast::k_height_maps_fast<768, 32><<<grid, 768, sm, stream>>>(d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2, peers);
+            auto kern = nt == 512 ? (gather ? fast::k_height_maps_fast<512, 32, true> : fast::k_height_maps_fast<512, 32, false>)
+                                  : (gather ? fast::k_height_maps_fast<768, 32, true> : fast::k_height_maps_fast<768, 32, false>);
+            kern<<<grid, nt, sm, stream>>>(d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2, fast::ONE_BITS, peers);
         }
     } else {
         int64_t blocks = (total + 255) / 256;

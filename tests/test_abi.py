@@ -101,3 +101,22 @@ def test_vector_call_surface_on_the_host(tmp_path):
                            os.path.join(ROOT, "tests", "call_surface_host_test.cu")])
     out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
     assert "call surface ok" in out
+
+
+def test_k2_octave_loop_has_not_grown():
+    """K2 is issue-bound, so its run time tracks the instruction count of the octave loop.  The
+    count is read from the built library with cuobjdump (no GPU): fBm 171, ridged 178, and the
+    two mixed-octave-count variants 176 / 180 when this bound was set.  A change that adds
+    registers to the kernel (e.g. live pointers across the loop) shows up here first."""
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from sass_loops import octave_loops
+    found = octave_loops()
+    assert len(found) == 2, sorted(found)                    # plain and fused-gather instantiations
+    for name, loops in found.items():
+        counts = sorted(n for n, _ in loops)
+        assert len(counts) == 4, (name, counts)
+        assert counts[0] <= 173 and counts[-1] <= 183, (name, counts)
