@@ -38,7 +38,8 @@ namespace shade {
 
 constexpr int THREADS = 128;        // 4 warps per CTA, up to 6 CTAs per SM: best of the sweep in tools/k3_sweep.py
 constexpr int WARPS = THREADS / 32;
-constexpr int COL_ARRAYS = 17;       // floats kept per column (SoA)
+constexpr int COL_STRIDE = 20;       // floats per column record (17 used): 80 B keeps LDS.128 aligned and
+                                     // 8 consecutive records of a quarter-warp fall in 8 distinct bank groups
 
 struct V { float3 p, n; };                                          // main.cpp:298
 
@@ -47,7 +48,11 @@ __device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x 
 __device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
 __device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
 __device__ __forceinline__ float dot(float3 a, float3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
-__device__ __forceinline__ float3 normalize(float3 a) { return a * rsqrtf(dot(a, a)); }
+// MUFU.RSQ / MUFU.SQRT alone: rsqrtf()/sqrtf() wrap them in denormal scaling and a Newton step
+// (4 and 12 instructions); every argument here is a squared length or >= 0.001
+__device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float3 normalize(float3 a) { return a * rsqrt_fast(dot(a, a)); }
 __device__ __forceinline__ float3 cross(float3 a, float3 b)
 {
     return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
@@ -82,14 +87,13 @@ __device__ V interpolate(const V &v0, const V &v1, float t)
     return r;
 }
 
-// SoA column record: index of each array inside s_col (each array holds n floats, padded)
-// (q is kept as the deltas q.p - p.p and q.n - p.n: the linear branch is then 6 FMAs)
-enum { C_PPX, C_PPY, C_PPZ, C_PNX, C_PNY, C_PNZ, C_PQX, C_PQY, C_PQZ, C_DNX, C_DNY, C_DNZ,
-       C_XYS, C_TH2, C_ITAN, C_ISIN, C_HLEN };
+// Column record: five float4 groups, read with LDS.128 (q is kept as the deltas q.p - p.p and
+// q.n - p.n: the linear branch is then 6 FMAs).  The fifth group is only read on the slerp branch.
+//   0: p.p.xyz, th2    1: p.n.xyz, 2*xyscale    2: (q.p - p.p).xyz, hlen    3: (q.n - p.n).xyz, itan    4: isin
 
 // One WARP per quad: warps never wait for each other (no block barrier), so one warp's
 // column phase overlaps the other warps' vertex phases.  Per-warp shared memory:
-//   [4 corner uniforms | COL_ARRAYS x np column floats | (n+2)^2 staged heights]
+//   [4 corner uniforms | np column records of COL_STRIDE floats | (n+2)^2 staged heights]
 // GL_LINEAR + GL_CLAMP_TO_EDGE fetch of a dim x dim R32F texture (render.cpp:429-433) at (u, v)
 __device__ __forceinline__ float sample_bilinear(const float *tex, int dim, float u, float v)
 {
@@ -119,8 +123,8 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
     float *s_uv = reinterpret_cast<float *>(smem);                   // np floats, shared by the block
     unsigned char *mine = smem + np * sizeof(float) + (size_t)warp * warp_smem_bytes;
     V *s_corner = reinterpret_cast<V *>(mine);                       // 4 x 24 B (in 128 B)
-    float *s_col = reinterpret_cast<float *>(mine + 128);            // COL_ARRAYS x np floats
-    float *s_h = s_col + COL_ARRAYS * np;                            // dim2 floats (if staged)
+    float4 *s_col = reinterpret_cast<float4 *>(mine + 128);          // np records x COL_STRIDE floats
+    float *s_h = reinterpret_cast<float *>(s_col) + COL_STRIDE * np; // dim2 floats (if staged)
     const double div = __ddiv_rn(1.0, (double)(n - 1));              // main.cpp:404
     const unsigned magic_w = (unsigned)(((1ull << 32) + (unsigned)w - 1) / (unsigned)w);   // ceil(2^32 / w)
 
@@ -161,11 +165,6 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
             V q = interpolate(s_corner[2], s_corner[3], ux);         // main.cpp:355
             float3 pq = q.p - p.p;
             float len = sqrtf(dot(pq, pq));
-            s_col[C_PPX * np + x] = p.p.x; s_col[C_PPY * np + x] = p.p.y; s_col[C_PPZ * np + x] = p.p.z;
-            s_col[C_PNX * np + x] = p.n.x; s_col[C_PNY * np + x] = p.n.y; s_col[C_PNZ * np + x] = p.n.z;
-            s_col[C_PQX * np + x] = pq.x; s_col[C_PQY * np + x] = pq.y; s_col[C_PQZ * np + x] = pq.z;
-            s_col[C_DNX * np + x] = q.n.x - p.n.x; s_col[C_DNY * np + x] = q.n.y - p.n.y; s_col[C_DNZ * np + x] = q.n.z - p.n.z;
-            s_col[C_XYS * np + x] = 2.0f * (len / (float)(n - 1));   // 2*xyscale, main.cpp:345,361 (29.0 == n-1)
             // column-constant part of v = interpolate(p, q, UV.y), main.cpp:310-326
             float d = dot(p.n, q.n);
             float th2 = -1.0f, itan = 0.f, isin = 0.f;
@@ -175,8 +174,12 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
                 itan = 1.0f / tanf(theta);
                 isin = 1.0f / sinf(theta);
             }
-            s_col[C_TH2 * np + x] = th2; s_col[C_ITAN * np + x] = itan; s_col[C_ISIN * np + x] = isin;
-            s_col[C_HLEN * np + x] = 0.5f * len;                     // length((q.p - p.p) * 0.5)
+            float4 *rec = s_col + x * (COL_STRIDE / 4);
+            rec[0] = make_float4(p.p.x, p.p.y, p.p.z, th2);
+            rec[1] = make_float4(p.n.x, p.n.y, p.n.z, 2.0f * (len / (float)(n - 1)));   // 2*xyscale, main.cpp:345,361 (29.0 == n-1)
+            rec[2] = make_float4(pq.x, pq.y, pq.z, 0.5f * len);                         // w: length((q.p - p.p) * 0.5)
+            rec[3] = make_float4(q.n.x - p.n.x, q.n.y - p.n.y, q.n.z - p.n.z, itan);
+            rec[4] = make_float4(isin, 0.f, 0.f, 0.f);
         }
         __syncwarp();
         // ---- C: the warp walks the patch rows ----------------------------------------------------
@@ -194,23 +197,21 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
         for (int i0 = 0; i0 < nv; i0 += 32) {
             const int i = i0 + lane;
             if (i < nv) {
-                int vx, vy; float skirt;
-                if (i < n) { vx = i; vy = 0; skirt = 1.0f; }
-                else if (i < n + n * w) {
-                    const int r = i - n;
-                    vy = (int)__umulhi((unsigned)r, magic_w);             // r / w, exact for r < 2^16, w <= 256
-                    const int c = r - vy * w;
-                    vx = min(max(c - 1, 0), n - 1);
-                    skirt = (c == 0 || c == w - 1) ? 1.0f : 0.0f;
-                } else { vx = i - n - n * w; vy = n - 1; skirt = 1.0f; }
+                // Slot -> (row, column).  Padding the top and bottom skirt rows (n slots each) to the
+                // w slots of a body row makes the patch a (n+2) x w grid: virtual index = slot + 1,
+                // + 1 more past the top row, + 1 more past the last body row.
+                const int vi = i + 1 + (i >= n) + (i >= n + n * w);
+                const int vrow = (int)__umulhi((unsigned)vi, magic_w);        // vi / w, exact for vi < 2^16, w <= 256
+                const int c = vi - vrow * w;
+                const int vx = min(max(c - 1, 0), n - 1), vy = min(max(vrow - 1, 0), n - 1);
+                const float skirt = (vrow == 0 || vrow == n + 1 || c == 0 || c == w - 1) ? 1.0f : 0.0f;
                 const float t = s_uv[vy], omt = 1.0f - t;
                 const int row_off = (vy + 1) * dim;
-                const int c = 0, row_slot = i;                            // output slot = i
-                const float3 pp = f3(s_col[C_PPX * np + vx], s_col[C_PPY * np + vx], s_col[C_PPZ * np + vx]);
-                const float3 pn = f3(s_col[C_PNX * np + vx], s_col[C_PNY * np + vx], s_col[C_PNZ * np + vx]);
-                const float3 pq = f3(s_col[C_PQX * np + vx], s_col[C_PQY * np + vx], s_col[C_PQZ * np + vx]);
-                const float3 dn = f3(s_col[C_DNX * np + vx], s_col[C_DNY * np + vx], s_col[C_DNZ * np + vx]);
-                const float th2 = s_col[C_TH2 * np + vx];
+                const float4 *rec = s_col + vx * (COL_STRIDE / 4);
+                const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
+                const float3 pp = f3(r0.x, r0.y, r0.z), pn = f3(r1.x, r1.y, r1.z);
+                const float3 pq = f3(r2.x, r2.y, r2.z), dn = f3(r3.x, r3.y, r3.z);
+                const float th2 = r0.w;
                 // v = interpolate(p, q, UV.y)                      // main.cpp:356
                 float3 vp, vn;
                 if (th2 < 0.0f) {                                    // interpolate_linear, main.cpp:300-308
@@ -221,10 +222,10 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
                     const float3 qn = pn + dn;
                     vn = normalize(pn * sinf(omt * th2) + qn * sinf(t * th2));
                     float gamma = th2 * 0.5f - th2 * t;
-                    float itan = s_col[C_ITAN * np + vx];
+                    float itan = r3.w;
                     float x = 1.0f - tanf(gamma) * itan;
-                    float y = s_col[C_ISIN * np + vx] - itan / cosf(gamma);
-                    vp = pp + pq * (0.5f * x) + vn * (y * s_col[C_HLEN * np + vx]);
+                    float y = rec[4].x - itan / cosf(gamma);
+                    vp = pp + pq * (0.5f * x) + vn * (y * r2.w);
                 }
                 const int ti = row_off + vx + 1;                     // texel (vx+1, vy+1)
                 float hc, hl, hr, hu, hd;
@@ -241,7 +242,7 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
                 } else if (STAGE) { hc = s_h[ti]; hl = s_h[ti - 1]; hr = s_h[ti + 1]; hu = s_h[ti - dim]; hd = s_h[ti + dim]; }
                 else { hc = __ldg(H + ti); hl = __ldg(H + ti - 1); hr = __ldg(H + ti + 1); hu = __ldg(H + ti - dim); hd = __ldg(H + ti + dim); }
                 const float height = hc - skirt_size * skirt;        // main.cpp:360
-                float3 nt = normalize(f3(hl - hr, s_col[C_XYS * np + vx], hu - hd));   // main.cpp:339-345
+                float3 nt = normalize(f3(hl - hr, r1.w, hu - hd));   // main.cpp:339-345
                 float3 tg = normalize(cross(vn, pq));                // main.cpp:363
                 // main.cpp:364-365 normalise bi = cross(t, n) and mat3(t, n, bi) * normal as well; t, n
                 // are unit and orthogonal by construction and |normal| = 1, so both lengths are
@@ -252,8 +253,8 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
                 // fragment stage at the vertex: l = normalize(0,1,-1), main.cpp:374-378
                 const float inv_sqrt2 = 0.70710678118654752f;
                 float light = 0.001f + fmaxf((N.y - N.z) * inv_sqrt2, 0.0f);
-                if (pos_q) __stcs(pos_q + row_slot + c, make_float4(pos.x, pos.y, pos.z, height));
-                if (nrm_q) __stcs(nrm_q + row_slot + c, make_float4(N.x, N.y, N.z, sqrtf(light)));
+                if (pos_q) __stcs(pos_q + i, make_float4(pos.x, pos.y, pos.z, height));
+                if (nrm_q) __stcs(nrm_q + i, make_float4(N.x, N.y, N.z, sqrt_fast(light)));
             }
         }
     }
@@ -270,13 +271,13 @@ int launch_shade(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads
     if (n < 2 || n > 254)
         return set_error(PLANET_E_UNSUPPORTED, "planet_gpu_shade: patch_verts %d outside [2, 254]", n);
     const int dim = n + 2, np = (n + 31) & ~31;
-    const size_t col_bytes = 128 + (size_t)shade::COL_ARRAYS * np * sizeof(float);
+    const size_t col_bytes = 128 + (size_t)shade::COL_STRIDE * np * sizeof(float);
     const size_t hbytes = (size_t)dim * dim * sizeof(float);
     const size_t budget = 200 * 1024;
     const int stage = (col_bytes + hbytes) <= budget;               // else the stencil reads go to L1/L2
     if (d_rects && !stage)
         return set_error(PLANET_E_UNSUPPORTED, "planet_gpu_shade_cached: a %d x %d map does not fit shared memory", dim, dim);
-    const size_t per_warp = col_bytes + (stage ? hbytes : 0);
+    const size_t per_warp = (col_bytes + (stage ? hbytes : 0) + 15) & ~(size_t)15;   // records are read as float4
     int want_warps = shade::WARPS;
     if (const char *e = getenv("PLANET_K3_WARPS")) want_warps = std::max(1, std::min(shade::WARPS, atoi(e)));   // tuning knob
     int warps = (int)std::max<size_t>(1, std::min<size_t>(want_warps, (budget - np * sizeof(float)) / per_warp));
