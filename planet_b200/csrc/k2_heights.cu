@@ -354,6 +354,127 @@ __device__ __forceinline__ void fractal(const unsigned char *t12_lane, const uns
     else                          fractal_loop<REPL, true>(t12_lane, t3_lane, p, octaves, omax, kind, gain, one_bits, value);
 }
 
+// ---- EXACT arithmetic on the replicated tables ------------------------------------------
+// Every rounding of perlin.h:50-88 as in exact::noise3 (planet_common.cuh) -- custom floor,
+// double fraction, quintic in double, x-1 formed in double, unfused float lerps -- but the hash
+// chain and the gradient fetch come from the lane-replicated tables above: 10 conflict-free
+// LDS instead of 14 byte loads + 24 float loads with ~3-way conflicts, no `& 255` / `* 3` index
+// arithmetic.  Two identities keep the bits: (1) gradient components are 0 or +-1, so every
+// product of the dot is exact and x*g0 + y*g1 + z*g2 with separate roundings equals the same sum
+// written as two FMAs; (2) the table codes decode to 2*v, so the value is 2*noise, and scaling
+// by two commutes with every rounding on the way (no value here is near the denormal range).
+// Returns 2 * PerlinNoise3(x, y, z).
+__device__ __forceinline__ float corner_exact2(uint32_t g, float x, float y, float z)
+{
+    const float gx = __uint_as_float(g & 0xFF000000u);
+    const float gy = __uint_as_float(__byte_perm(g, 0, 0x1444));
+    const float gz = __uint_as_float(g << 24);
+    return __fmaf_rn(z, gz, __fmaf_rn(y, gy, __fmul_rn(x, gx)));     // perlin.h:47
+}
+
+template <int REPL>
+__device__ __forceinline__ float noise3_exact2(const unsigned char *t12_lane, const unsigned char *t3_lane,
+                                               double x, double y, double z)
+{
+    using L = Layout<REPL>;
+    constexpr int T12_ROW = L::T12_ROW;
+    const int ix = exact::cell(x), iy = exact::cell(y), iz = exact::cell(z);     // perlin.h:52-55
+    x = __dsub_rn(x, (double)ix);
+    y = __dsub_rn(y, (double)iy);
+    z = __dsub_rn(z, (double)iz);
+    const float u = exact::fade(x), v = exact::fade(y), w = exact::fade(z);
+    const float x0 = __double2float_rn(x), x1 = __double2float_rn(__dadd_rn(x, -1.0));   // perlin.h:68-75
+    const float y0 = __double2float_rn(y), y1 = __double2float_rn(__dadd_rn(y, -1.0));
+    const float z0 = __double2float_rn(z), z1 = __double2float_rn(__dadd_rn(z, -1.0));
+    const uint32_t cx = ((uint32_t)ix & 255u) << L::LOG12;           // PerlinRandom's `& 255`, perlin.h:40
+    const uint32_t cy = ((uint32_t)iy & 255u) << L::LOG12;
+    const uint32_t cz = ((uint32_t)iz & 255u) << L::LOG3;
+    const uint32_t a0 = lds_u16(t12_lane, cx), a1 = lds_u16(t12_lane, cx + T12_ROW);
+    const uint32_t b00 = lds_u16(t12_lane, a0 + cy + 2), b01 = lds_u16(t12_lane, a0 + cy + 2 + T12_ROW);
+    const uint32_t b10 = lds_u16(t12_lane, a1 + cy + 2), b11 = lds_u16(t12_lane, a1 + cy + 2 + T12_ROW);
+    const uint2 e00 = lds_v2(t3_lane, b00 + cz), e10 = lds_v2(t3_lane, b10 + cz);
+    const uint2 e01 = lds_v2(t3_lane, b01 + cz), e11 = lds_v2(t3_lane, b11 + cz);
+    const float g0 = corner_exact2(e00.x, x0, y0, z0), g1 = corner_exact2(e10.x, x1, y0, z0);
+    const float g2 = corner_exact2(e01.x, x0, y1, z0), g3 = corner_exact2(e11.x, x1, y1, z0);
+    const float g4 = corner_exact2(e00.y, x0, y0, z1), g5 = corner_exact2(e10.y, x1, y0, z1);
+    const float g6 = corner_exact2(e01.y, x0, y1, z1), g7 = corner_exact2(e11.y, x1, y1, z1);
+    const float l0 = exact::lerp(g0, g1, u), l1 = exact::lerp(g2, g3, u);
+    const float l2 = exact::lerp(g4, g5, u), l3 = exact::lerp(g6, g7, u);
+    return exact::lerp(exact::lerp(l0, l1, v), exact::lerp(l2, l3, v), w);   // perlin.h:77-86
+}
+
+// Perlin::operator() (main.cpp:825-832) over noise3_exact2; same operation order as exact::height
+template <int REPL>
+__device__ __forceinline__ float height_exact_tab(const unsigned char *t12_lane, const unsigned char *t3_lane,
+                                                  const HeightCfg &c, d3 p, int depth)
+{
+    if (c.kind == PLANET_NOISE_ZERO) return 0.0f;
+    const int octaves = octaves_for(c.fixed_octaves, depth, c.max_depth);
+    p = exact::mul(p, c.coord_scale);
+    if (c.has_seed) {
+        p.x = __dadd_rn(p.x, c.seed[0]); p.y = __dadd_rn(p.y, c.seed[1]); p.z = __dadd_rn(p.z, c.seed[2]);
+    }
+    double frequency = 1.0;
+    float amplitude = 1.0f, weight = 1.0f, value = 0.0f;
+    const bool ridged = c.kind == PLANET_NOISE_RIDGED;
+    for (int i = 0; i < octaves; ++i) {
+        float n = __fmul_rn(0.5f, noise3_exact2<REPL>(t12_lane, t3_lane, __dmul_rn(p.x, frequency),
+                                                      __dmul_rn(p.y, frequency), __dmul_rn(p.z, frequency)));
+        if (ridged) {                                                // main.cpp:716-731
+            n = fabsf(n);
+            n = __fsub_rn(1.0f, n);
+            n = __fmul_rn(n, n);
+            value = __fadd_rn(value, __fmul_rn(__fmul_rn(n, amplitude), weight));
+            weight = n;
+        } else {                                                     // main.cpp:699-704
+            value = __fadd_rn(value, __fmul_rn(n, amplitude));
+        }
+        frequency = __dmul_rn(frequency, c.lacunarity);
+        amplitude = __fmul_rn(amplitude, c.gain);
+    }
+    return __fmul_rn(value, c.height_scale);
+}
+
+// GenerateHeightMap (main.cpp:123-151) in EXACT arithmetic for large batches: persistent CTAs,
+// one per SM, one sample per thread per pass, consecutive threads on consecutive texels.
+template <int NTHREADS, bool GATHER>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_height_maps_exact_tab(const Quad *__restrict__ quads, int64_t total, int dim, HeightCfg cfg,
+                        float *__restrict__ out, uint64_t magic_dim, PeerOut peers)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    using L = Layout<32>;
+    build_tables<32>(smem);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const unsigned char *t12_lane = smem + lane * 4;
+    const unsigned char *t3_lane = smem + L::T12_BYTES + lane * 8;
+    const uint32_t dim2 = (uint32_t)dim * (uint32_t)dim;
+    const double div = __ddiv_rn(1.0, (double)(dim - 3));            // main.cpp:134
+    // i = q * dim2 + r is advanced incrementally: one 64-bit division per thread, none per sample
+    const int64_t i0 = blockIdx.x * (int64_t)NTHREADS + threadIdx.x;
+    const uint32_t step = gridDim.x * NTHREADS;
+    const uint32_t step_q = step / dim2, step_r = step - step_q * dim2;
+    int64_t q = i0 / dim2;
+    uint32_t r = (uint32_t)(i0 - q * dim2);
+    for (int64_t i = i0; i < total; i += step) {
+        const uint32_t y = (uint32_t)(((uint64_t)r * magic_dim) >> 40), x = r - y * (uint32_t)dim;   // exact: r < dim^2, dim <= 8192
+        const Quad *quad = quads + q;
+        Quad qd;
+        qd.p[0] = quad->p[0]; qd.p[1] = quad->p[1]; qd.p[2] = quad->p[2]; qd.p[3] = quad->p[3];
+        const d3 p = exact::sample_point(qd, (int)x, (int)y, div);
+        const float h = height_exact_tab<32>(t12_lane, t3_lane, cfg, p, (int)quad_depth(quad->id));
+        out[i] = h;
+        if constexpr (GATHER) {
+#pragma unroll
+            for (int k = 0; k < 7; k++)
+                if (k < peers.n) peers.ptr[k][i] = h;
+        }
+        q += step_q; r += step_r;
+        if (r >= dim2) { r -= dim2; q++; }
+    }
+}
+
 // reduce a scaled coordinate (units of 2^-55) to one period and convert to fixed point
 __device__ __forceinline__ void to_fixed(double v, uint32_t &lo, uint32_t &hi)
 {
@@ -642,6 +763,10 @@ static int prepare_fast()
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
         PLANET_CUDA(cudaFuncSetAttribute(fast::k_points_fast<32>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
+        PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_exact_tab<1024, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
+        PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_exact_tab<1024, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
         g_fast_attr_set[dev] = true;
     }
     return 0;
@@ -707,6 +832,15 @@ int launch_height_maps_gathered(const planet_gpu_params *p, const Quad *d_quads,
                                   : (gather ? fast::k_height_maps_fast<768, 32, true> : fast::k_height_maps_fast<768, 32, false>);
             kern<<<grid, nt, sm, stream>>>(d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2, fast::ONE_BITS, peers);
         }
+    } else if (total > k2_small_max() && dim <= 8192) {
+        // EXACT arithmetic, large batch: same roundings on the replicated tables (1 CTA per SM)
+        int rc = prepare_fast();
+        if (rc) return rc;
+        constexpr int NT = 1024;
+        const uint64_t m1 = ((1ull << 40) + dim - 1) / dim;
+        int grid = (int)std::min<int64_t>((total + NT - 1) / NT, sm_count());
+        auto kern = peers.n > 0 ? fast::k_height_maps_exact_tab<NT, true> : fast::k_height_maps_exact_tab<NT, false>;
+        kern<<<grid, NT, fast::Layout<32>::TABLES + 2048, stream>>>(d_quads, total, dim, cfg, d_out, m1, peers);
     } else {
         int64_t blocks = (total + 255) / 256;
         int grid = (int)std::min<int64_t>(blocks, (int64_t)sm_count() * 8);

@@ -557,7 +557,7 @@ def test_k2_fused_gather_stores_identical_bytes_to_every_peer(gpu):
     """planet_gpu_generate_height_maps_gathered: the peer buffers (here: 7 more buffers on this GPU,
     on an 8-GPU box: CUDA-IPC-mapped buffers of the other ranks) get exactly the local bytes."""
     import torch
-    for prec, nq, dim in ((gpu.FAST, 3000, 32), (gpu.FAST, 40, 33), (gpu.EXACT, 64, 32)):
+    for prec, nq, dim in ((gpu.FAST, 3000, 32), (gpu.FAST, 40, 33), (gpu.EXACT, 64, 32), (gpu.EXACT, 1100, 32)):
         p = gpu.fbm_params(8, 0.5, prec)
         quads = gpu.tessellate_uniform(6, first=100, nquads=nq)
         want = gpu.generate_height_maps(quads, dim, 18, p)
@@ -571,6 +571,34 @@ def test_k2_fused_gather_stores_identical_bytes_to_every_peer(gpu):
                 assert torch.equal(t_, want)
     with pytest.raises(gpu.PlanetGpuError, match="n_peers"):
         gpu.generate_height_maps_gathered(quads, 32, 18, want, [want] * 8, p)
+
+
+def test_exact_large_batches_use_the_table_kernel_and_keep_every_bit(gpu, port):
+    """Above PLANET_K2_SMALL_MAX samples EXACT mode runs k_height_maps_exact_tab (replicated tables,
+    FMA dots on exact products, doubled gradient codes).  It must stay bit-identical to the
+    reference: checked against the oracle and, for what the oracle cannot express (seed offsets),
+    against the small-batch kernel, which is the line-by-line exact:: code."""
+    import torch
+    cases = [
+        dict(kind=gpu.FBM, gain=0.5, fixed_octaves=8, dim=32, depth=6, first=777, nq=1500),
+        dict(kind=gpu.RIDGED, gain=0.55, fixed_octaves=0, dim=33, depth=6, first=3, nq=1100),      # default functor, odd dim
+        dict(kind=gpu.FBM, gain=0.7, fixed_octaves=5, dim=110, depth=2, first=0, nq=96, lacunarity=2.5, precision=gpu.FAST),
+    ]
+    for c in cases:
+        p = gpu.default_params(noise_kind=c["kind"], gain=c["gain"], fixed_octaves=c["fixed_octaves"],
+                               lacunarity=c.get("lacunarity", 2.0), precision=c.get("precision", gpu.EXACT))
+        quads = gpu.tessellate_uniform(c["depth"], first=c["first"], nquads=c["nq"])
+        assert c["nq"] * c["dim"] ** 2 > 1 << 20
+        got = to_np(gpu.generate_height_maps(quads, c["dim"], 18, p))
+        want = port.generate_height_maps(gpu.quads_to_host(quads), c["dim"], 18, orc_params(p), nthreads=8)
+        assert (as_bits(got) == as_bits(want)).all(), c
+    # seed offset + a scale that puts samples on both sides of the coordinate planes
+    p = gpu.default_params(noise_kind=gpu.RIDGED, gain=0.55, fixed_octaves=12, precision=gpu.EXACT,
+                           coord_scale=3e-6, seed_offset=(-7.25, 0.5, 1e3))
+    quads = gpu.tessellate_uniform(5, first=0, nquads=2048)
+    whole = gpu.generate_height_maps(quads, 32, 18, p)
+    parts = torch.cat([gpu.generate_height_maps(quads[i:i + 512], 32, 18, p) for i in range(0, 2048, 512)])
+    assert torch.equal(whole, parts)
 
 
 def test_randomised_configurations_against_the_oracle(gpu, port):
