@@ -19,6 +19,7 @@
 #include <cuda_runtime_api.h>
 
 #include "planet_host.h"
+#include "planet_buffers.h"
 
 struct Planet                                                        // main.cpp:161-181, GPU-resident
 {
@@ -26,6 +27,7 @@ struct Planet                                                        // main.cpp
     int max_lod;
     float max_skirt_size;
     int patch_verts, vertex_count, index_count;
+    GLuint vertex_buffer, index_buffer;                              // main.cpp:479-480, device memory here
     float *d_patch_vertices;                                         // (u, v, skirt) triples, main.cpp:402-425
     uint32_t *d_patch_indices;                                       // triangle strip, main.cpp:427-474
     planet_gpu_params params;
@@ -48,8 +50,12 @@ static bool InitPlanet(Planet &p, double radius)                     // main.cpp
     p.vertex_count = planet_gpu_patch_vertex_count(p.patch_verts);   // main.cpp:393-394
     p.index_count = planet_gpu_patch_index_count(p.patch_verts);     // main.cpp:395-400
     CHECK(planet_gpu_init(0));
-    CUDA_OK(cudaMalloc((void **)&p.d_patch_vertices, sizeof(float) * 3 * p.vertex_count));
-    CUDA_OK(cudaMalloc((void **)&p.d_patch_indices, sizeof(uint32_t) * p.index_count));
+    // main.cpp:479-480 create the two buffers from CPU arrays; here K1 fills them in place
+    p.vertex_buffer = CreateVertexBuffer(sizeof(float) * 3 * p.vertex_count, nullptr);
+    p.index_buffer = CreateIndexBuffer(sizeof(uint32_t) * p.index_count, nullptr);
+    if (!p.vertex_buffer || !p.index_buffer) { LOG_ERROR("CreateVertexBuffer/CreateIndexBuffer failed"); return false; }
+    p.d_patch_vertices = (float *)MapBuffer(p.vertex_buffer);
+    p.d_patch_indices = (uint32_t *)MapBuffer(p.index_buffer);
     CHECK(planet_gpu_patch_mesh(p.patch_verts, p.d_patch_vertices, p.d_patch_indices, nullptr));   // main.cpp:402-481
     p.max_lod = planet_gpu_max_lod(radius, p.patch_verts);           // main.cpp:497
     p.max_skirt_size = planet_gpu_max_skirt_size(radius, p.patch_verts);   // main.cpp:500
@@ -122,6 +128,7 @@ int main(int argc, char **argv)
     printf("vertex 0: pos (%.3f %.3f %.3f) height %.3f  normal (%.4f %.4f %.4f) light %.4f\n",
            v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
     planet_gpu_cache_destroy(planet.cache);
+    DeleteBuffers();
     planet_gpu_shutdown();
     return 0;
 }
