@@ -45,6 +45,24 @@ print(json.dumps({"config": "C1 lod selection", "quads": int(q1.shape[0]), "ms":
 pipeline("C1 default planet frame, EXACT (bit-identical to the reference)", lambda: q1, p1, 32)
 pipeline("C1 default planet frame, FAST", lambda: q1, pb.default_params(precision=pb.FAST), 32)
 
+# C1 through the reference's own seam: one synchronous call per map / per point, host pointers
+# (what GetHeightMapForQuad and ProcessQuad do, main.cpp:244, 552-555); wall clock per call
+pb.set_params(p1)
+hq1 = pb.quads_to_host(q1)
+buf = np.empty((32, 32), np.float32)
+for _ in range(20): pb.generate_height_map(hq1[0], 32, 18)
+t0 = time.perf_counter()
+for k in range(400): pb.generate_height_map(hq1[k % len(hq1)], 32, 18)
+t_map = (time.perf_counter() - t0) / 400
+pt = np.array([0.0, 0.0, -6371000.0])
+for _ in range(20): pb.get_height_at(pt, 0, 1)
+t0 = time.perf_counter()
+for k in range(400): pb.get_height_at(pt, 0, 1)
+t_pt = (time.perf_counter() - t0) / 400
+print(json.dumps({"config": "C1 legacy seam (HeightMapGenerator's two pointers, synchronous, host buffers)",
+                  "generate_height_map_32x32_us": t_map * 1e6, "get_height_at_us": t_pt * 1e6,
+                  "note": "EXACT arithmetic; includes H2D of the quad, the launch, D2H of the map and the ctypes call"}), flush=True)
+
 # C2: one face, depth 7, fBm 8
 p2 = pb.fbm_params(8, 0.5, pb.FAST)
 pipeline("C2 one face depth 7 fBm-8 FAST", lambda: pb.tessellate_uniform(7, 0, 16384, p2), p2, 32)
