@@ -128,20 +128,24 @@ namespace fast {
 #endif
 constexpr int K2_UNROLL = PLANET_K2_UNROLL;   // octave-loop unroll factor (build-time tuning knob)
 constexpr int THREADS = 512;
-constexpr int S = 2;                          // consecutive samples per thread (one f32x2 pair)
+constexpr int S = 2;                          // consecutive samples per thread (one 8-byte store)
 constexpr int TILE = THREADS * S;             // samples per CTA iteration
 constexpr int ROWS = 512;                     // table index range: perm (<=255) + cell (<=255) + 1
-// Table layout for a replication factor REPL (copies of every entry per row): REPL = 32 gives
-// every lane its own bank (conflict-free, 192 KB, for throughput); REPL = 1 is the compact 6 KB
-// layout whose build costs nothing, used for small batches where latency is what matters.
+// Table layout for a replication factor REPL.  REPL = 32 is the throughput layout (128 KB):
+// every T12 entry 32 times, one copy per bank, and every 16-byte T3 entry 8 times -- an LDS.128
+// is served a quarter-warp at a time, so 8 copies at 16-byte stride put the 8 lanes of a phase
+// in 8 distinct bank groups whatever rows they ask for (tools/microbench3.cu).  REPL = 1 is the
+// compact 10 KB layout whose build costs nothing, for small batches where latency matters.
 template <int REPL> struct Layout {
+    static_assert(REPL == 32 || REPL == 1, "layouts in use");
+    static constexpr int T3_COPIES = REPL == 32 ? 8 : 1;
     static constexpr int T12_ROW = REPL * 4;              // REPL x u32
-    static constexpr int T3_ROW = REPL * 8;               // REPL x {u32 G(i), u32 G(i+1)}
+    static constexpr int T3_ROW = T3_COPIES * 16;         // T3_COPIES x {gx(i)|zc, gy(i), gx(i+1)|zc, gy(i+1)}
     static constexpr int T12_BYTES = ROWS * T12_ROW;      // 64 KB at REPL 32
-    static constexpr int T3_BYTES = ROWS * T3_ROW;        // 128 KB at REPL 32
+    static constexpr int T3_BYTES = ROWS * T3_ROW;        // 64 KB at REPL 32
     static constexpr int TABLES = T12_BYTES + T3_BYTES;
-    static constexpr int LOG12 = REPL == 32 ? 7 : REPL == 16 ? 6 : REPL == 8 ? 5 : REPL == 4 ? 4 : REPL == 2 ? 3 : 2;
-    static constexpr int LOG3 = LOG12 + 1;
+    static constexpr int LOG12 = REPL == 32 ? 7 : 2;
+    static constexpr int LOG3 = REPL == 32 ? 7 : 4;
 };
 constexpr uint32_t ONE_BITS = 0x3F800000u;                 // float 1.0, see splice_mantissa
 constexpr double FIX_ONE = 36028797018963968.0;           // 2^55
@@ -159,47 +163,51 @@ template <int REPL> constexpr int smem_bytes(int nthreads)
 }
 constexpr int SMEM_BYTES = smem_bytes<32>(768);
 
-// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, one issue slot for two lanes) ----
-typedef unsigned long long f2;
-__device__ __forceinline__ f2 pack(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void unpack(f2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f2 splat(float v) { return pack(v, v); }
-__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-
 // shared-memory table reads; `base` is a pointer into the dynamic shared array, so the
-// compiler emits LDS.U16 / LDS.64 with 32-bit addressing and immediate offsets
+// compiler emits LDS.U16 / LDS.128 with 32-bit addressing and immediate offsets
 __device__ __forceinline__ uint32_t lds_u16(const unsigned char *base, uint32_t off)
 {
     return *reinterpret_cast<const unsigned short *>(base + off);
 }
-__device__ __forceinline__ uint2 lds_v2(const unsigned char *base, uint32_t off)
+__device__ __forceinline__ uint4 lds_v4(const unsigned char *base, uint32_t off)
 {
-    return *reinterpret_cast<const uint2 *>(base + off);
+    return *reinterpret_cast<const uint4 *>(base + off);
+}
+// A lane's view of the tables: the (warp-uniform) start of the dynamic shared array plus the
+// byte offsets of the lane's own copies inside a T12 / T3 row.  Keeping the base uniform and the
+// lane part a 32-bit offset lets every lookup be LDS [R + UR + imm]: the lane offset is OR-ed
+// into the cell offset once per axis instead of being added to every address.
+struct LaneTab { const unsigned char *base; uint32_t l12, l3; };
+template <int REPL> __device__ __forceinline__ LaneTab lane_tab(const unsigned char *smem, int lane)
+{
+    using L = Layout<REPL>;
+    return { smem, (uint32_t)(lane % REPL) * 4u, (uint32_t)(lane % L::T3_COPIES) * 16u };
 }
 
 // A gradient vector of perlin.h:30-36 as three byte codes, one per component, each the TOP
-// byte of the float 2*v: 0x00 -> 0.0, 0x40 -> +2.0, 0xC0 -> -2.0.  Component x sits in byte 3
-// (decoded by one AND), y in byte 1 (one PRMT), z in byte 0 (one shift); the factor 2 is
-// exact and is taken back out of the octave amplitude.
+// byte of the float 2*v: 0x00 -> 0.0, 0x40 -> +2.0, 0xC0 -> -2.0 (x in byte 3, y in byte 1, z in
+// byte 0).  The factor 2 is exact and is taken back out of the octave amplitude.
 __device__ __forceinline__ uint32_t grad_code(int h)
 {
     const float *g = g_grad[h & 15];
     auto byte = [](float v) -> uint32_t { return v > 0.f ? 0x40u : (v < 0.f ? 0xC0u : 0x00u); };
     return (byte(g[0]) << 24) | (byte(g[1]) << 8) | byte(g[2]);
 }
+// The table form of a code: gx and gy as finished floats (no decode instruction at the point of
+// use), the z code in the two lowest mantissa bits of gx, so gz = word << 30 is one shift.
+// FAST uses gx as it is (the stowaway bits move it by <= 3 * 2^-23 relative); EXACT masks them.
+__device__ __forceinline__ uint32_t gx_word(uint32_t code) { return (code & 0xFF000000u) | ((code & 0xC0u) >> 6); }
+__device__ __forceinline__ uint32_t gy_word(uint32_t code) { return (code & 0x0000FF00u) << 16; }
 
 // Build the (lane-replicated) tables, perm = table[i & 255]:
-//   T12[i][copy] = (perm*T12_ROW) | (perm*T3_ROW) << 16   next-row byte offsets for levels 1 and 2
-//   T3 [i][copy] = { G(table[i]), G(table[i+1]) }         both z-neighbours' gradients in one LDS.64
+//   T12[i][copy] = (perm*T12_ROW) | (perm*T3_ROW) << 16       next-row byte offsets for levels 1 and 2
+//   T3 [i][copy] = { gx(i)|zc(i), gy(i), gx(i+1)|zc(i+1), gy(i+1) }   both z-neighbours in one LDS.128
 template <int REPL>
 __device__ void build_tables(unsigned char *smem)
 {
     using L = Layout<REPL>;
     uint32_t *t12 = reinterpret_cast<uint32_t *>(smem);
-    uint2 *t3 = reinterpret_cast<uint2 *>(smem + L::T12_BYTES);
+    uint4 *t3 = reinterpret_cast<uint4 *>(smem + L::T12_BYTES);
     // stage {perm, code(perm)} for the 256 table entries in the (not yet used) scratch area
     uint2 *stage = reinterpret_cast<uint2 *>(smem + L::TABLES);
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
@@ -208,31 +216,29 @@ __device__ void build_tables(unsigned char *smem)
     }
     __syncthreads();
     for (int w = threadIdx.x; w < ROWS * REPL; w += blockDim.x) {
-        int i = w / REPL;
-        uint2 e0 = stage[i & 255], e1 = stage[(i + 1) & 255];
-        t12[w] = (e0.x << L::LOG12) | (e0.x << (16 + L::LOG3));       // next-row byte offsets, levels 1 and 2
-        t3[w] = make_uint2(e0.y, e1.y);
+        const uint32_t p = stage[(w / REPL) & 255].x;
+        t12[w] = (p << L::LOG12) | (p << (16 + L::LOG3));              // next-row byte offsets, levels 1 and 2
+    }
+    for (int w = threadIdx.x; w < ROWS * L::T3_COPIES; w += blockDim.x) {
+        const int i = w / L::T3_COPIES;
+        const uint32_t c0 = stage[i & 255].y, c1 = stage[(i + 1) & 255].y;
+        t3[w] = make_uint4(gx_word(c0), gy_word(c0), gx_word(c1), gy_word(c1));
     }
 }
 
-// dot of the decoded gradients of one corner with the corner-relative position, for the
-// thread's two samples at once (perlin.h:43-48).  Exactly one component is zero and the
-// others are +-2, so the sum has a single rounding: 2 * the reference's (x*v0 + y*v1) + z*v2.
-__device__ __forceinline__ f2 corner(uint32_t ga, uint32_t gb, f2 X, f2 Y, f2 Z)
+// dot of one corner's gradient with the corner-relative position (perlin.h:43-48).  Exactly one
+// component is zero and the others are +-2, so the sum has a single rounding: 2 * the
+// reference's (x*v0 + y*v1) + z*v2.
+__device__ __forceinline__ float corner(uint32_t gxw, uint32_t gyw, float X, float Y, float Z)
 {
-    f2 cx = pack(__uint_as_float(ga & 0xFF000000u), __uint_as_float(gb & 0xFF000000u));
-    f2 cy = pack(__uint_as_float(__byte_perm(ga, 0, 0x1444)), __uint_as_float(__byte_perm(gb, 0, 0x1444)));
-    f2 cz = pack(__uint_as_float(ga << 24), __uint_as_float(gb << 24));
-    return fma2(cz, Z, fma2(cy, Y, mul2(cx, X)));
+    return fmaf(__uint_as_float(gxw << 30), Z, fmaf(__uint_as_float(gyw), Y, __uint_as_float(gxw) * X));
 }
 
-__device__ __forceinline__ f2 fade2(f2 t)             // perlin.h:62 in fp32 + FMA
+__device__ __forceinline__ float fade1(float t)       // perlin.h:62 in fp32 + FMA
 {
-    f2 t2 = mul2(t, t);
-    f2 a = fma2(fma2(t, splat(6.0f), splat(-15.0f)), t, splat(10.0f));
-    return mul2(mul2(t2, t), a);
+    return (t * t * t) * fmaf(fmaf(t, 6.0f, -15.0f), t, 10.0f);
 }
-__device__ __forceinline__ f2 lerp2(f2 a, f2 b, f2 t) { return fma2(sub2(b, a), t, a); }
+__device__ __forceinline__ float lerp1(float a, float b, float t) { return fmaf(b - a, t, a); }
 
 struct Fixed3 { uint32_t xlo, xhi, ylo, yhi, zlo, zhi; };
 
@@ -247,12 +253,11 @@ __device__ __forceinline__ float splice_mantissa(uint32_t w, uint32_t one_bits)
 }
 
 // hash chain R(R(R(ix)+iy)+iz) of one sample for octave k (perlin.h:45): returns the four
-// {z, z+1} gradient-code pairs of the (x, y) columns 00, 10, 01, 11 and the three fractions
-struct Hashed { uint2 e00, e10, e01, e11; float mx, my, mz; };
+// {z, z+1} gradient pairs of the (x, y) columns 00, 10, 01, 11 and the three fractions
+struct Hashed { uint4 e00, e10, e01, e11; float mx, my, mz; };
 
 template <int REPL>
-__device__ __forceinline__ Hashed hash_octave(const unsigned char *t12_lane, const unsigned char *t3_lane,
-                                              const Fixed3 &p, int k, uint32_t one_bits)
+__device__ __forceinline__ Hashed hash_octave(const LaneTab &tab, const Fixed3 &p, int k, uint32_t one_bits)
 {
     using L = Layout<REPL>;
     constexpr int T12_ROW = L::T12_ROW, T3_ROW = L::T3_ROW;
@@ -264,94 +269,85 @@ __device__ __forceinline__ Hashed hash_octave(const unsigned char *t12_lane, con
     h.mx = splice_mantissa(wx, one_bits);                           // 1 + fraction, 23 bits
     h.my = splice_mantissa(wy, one_bits);
     h.mz = splice_mantissa(wz, one_bits);
-    uint32_t cx = (wx >> (23 - L::LOG12)) & (255u << L::LOG12);     // (cell & 255) * T12_ROW
-    uint32_t cy = (wy >> (23 - L::LOG12)) & (255u << L::LOG12);
-    uint32_t cz = (wz >> (23 - L::LOG3)) & (255u << L::LOG3);       // (cell & 255) * T3_ROW
-    uint32_t a0 = lds_u16(t12_lane, cx), a1 = lds_u16(t12_lane, cx + T12_ROW);   // R(ix), R(ix+1) (*128)
-    uint32_t b00 = lds_u16(t12_lane, a0 + cy + 2), b01 = lds_u16(t12_lane, a0 + cy + 2 + T12_ROW);
-    uint32_t b10 = lds_u16(t12_lane, a1 + cy + 2), b11 = lds_u16(t12_lane, a1 + cy + 2 + T12_ROW);
-    h.e00 = lds_v2(t3_lane, b00 + cz);                              // R(R(R(ix)+iy)+iz), ..+iz+1
-    h.e10 = lds_v2(t3_lane, b10 + cz);
-    h.e01 = lds_v2(t3_lane, b01 + cz);
-    h.e11 = lds_v2(t3_lane, b11 + cz);
+    // (cell & 255) * row size, with the lane's copy offset OR-ed into the (zero) low bits
+    const uint32_t cx = ((wx >> (23 - L::LOG12)) & (255u << L::LOG12)) | tab.l12;
+    const uint32_t cy = ((wy >> (23 - L::LOG12)) & (255u << L::LOG12)) | tab.l12;
+    const uint32_t cz = ((wz >> (23 - L::LOG3)) & (255u << L::LOG3)) | tab.l3;
+    const unsigned char *t = tab.base;
+    uint32_t a0 = lds_u16(t, cx), a1 = lds_u16(t, cx + T12_ROW);               // R(ix), R(ix+1) (* T12_ROW)
+    uint32_t b00 = lds_u16(t, a0 + cy + 2), b01 = lds_u16(t, a0 + cy + 2 + T12_ROW);
+    uint32_t b10 = lds_u16(t, a1 + cy + 2), b11 = lds_u16(t, a1 + cy + 2 + T12_ROW);
+    h.e00 = lds_v4(t, b00 + cz + L::T12_BYTES);                     // R(R(R(ix)+iy)+iz), ..+iz+1
+    h.e10 = lds_v4(t, b10 + cz + L::T12_BYTES);
+    h.e01 = lds_v4(t, b01 + cz + L::T12_BYTES);
+    h.e11 = lds_v4(t, b11 + cz + L::T12_BYTES);
     (void)T3_ROW;
     return h;
 }
 
-// 2 * PerlinNoise3 of octave k for the thread's two samples (perlin.h:50-88)
+// 2 * PerlinNoise3 of octave k for one sample (perlin.h:50-88)
 template <int REPL>
-__device__ __forceinline__ f2 noise_octave2(const unsigned char *t12_lane, const unsigned char *t3_lane,
-                                            const Fixed3 &pa, const Fixed3 &pb, int k, uint32_t one_bits)
+__device__ __forceinline__ float noise_octave(const LaneTab &tab, const Fixed3 &p, int k, uint32_t one_bits)
 {
-    Hashed A = hash_octave<REPL>(t12_lane, t3_lane, pa, k, one_bits);
-    Hashed B = hash_octave<REPL>(t12_lane, t3_lane, pb, k, one_bits);
-    f2 mx = pack(A.mx, B.mx), my = pack(A.my, B.my), mz = pack(A.mz, B.mz);
-    f2 x0 = add2(mx, splat(-1.0f)), x1 = add2(mx, splat(-2.0f));    // fraction, fraction - 1 (exact)
-    f2 y0 = add2(my, splat(-1.0f)), y1 = add2(my, splat(-2.0f));
-    f2 z0 = add2(mz, splat(-1.0f)), z1 = add2(mz, splat(-2.0f));
-    f2 g0 = corner(A.e00.x, B.e00.x, x0, y0, z0);                   // perlin.h:68-75
-    f2 g1 = corner(A.e10.x, B.e10.x, x1, y0, z0);
-    f2 g2 = corner(A.e01.x, B.e01.x, x0, y1, z0);
-    f2 g3 = corner(A.e11.x, B.e11.x, x1, y1, z0);
-    f2 g4 = corner(A.e00.y, B.e00.y, x0, y0, z1);
-    f2 g5 = corner(A.e10.y, B.e10.y, x1, y0, z1);
-    f2 g6 = corner(A.e01.y, B.e01.y, x0, y1, z1);
-    f2 g7 = corner(A.e11.y, B.e11.y, x1, y1, z1);
-    f2 u = fade2(x0), v = fade2(y0), w = fade2(z0);
-    f2 l0 = lerp2(g0, g1, u), l1 = lerp2(g2, g3, u), l2 = lerp2(g4, g5, u), l3 = lerp2(g6, g7, u);
-    return lerp2(lerp2(l0, l1, v), lerp2(l2, l3, v), w);            // perlin.h:77-86
+    const Hashed h = hash_octave<REPL>(tab, p, k, one_bits);
+    const float x0 = h.mx - 1.0f, x1 = h.mx - 2.0f;                 // fraction, fraction - 1 (exact)
+    const float y0 = h.my - 1.0f, y1 = h.my - 2.0f;
+    const float z0 = h.mz - 1.0f, z1 = h.mz - 2.0f;
+    const float g0 = corner(h.e00.x, h.e00.y, x0, y0, z0);          // perlin.h:68-75
+    const float g1 = corner(h.e10.x, h.e10.y, x1, y0, z0);
+    const float g2 = corner(h.e01.x, h.e01.y, x0, y1, z0);
+    const float g3 = corner(h.e11.x, h.e11.y, x1, y1, z0);
+    const float g4 = corner(h.e00.z, h.e00.w, x0, y0, z1);
+    const float g5 = corner(h.e10.z, h.e10.w, x1, y0, z1);
+    const float g6 = corner(h.e01.z, h.e01.w, x0, y1, z1);
+    const float g7 = corner(h.e11.z, h.e11.w, x1, y1, z1);
+    const float u = fade1(x0), v = fade1(y0), w = fade1(z0);
+    const float l0 = lerp1(g0, g1, u), l1 = lerp1(g2, g3, u), l2 = lerp1(g4, g5, u), l3 = lerp1(g6, g7, u);
+    return lerp1(lerp1(l0, l1, v), lerp1(l2, l3, v), w);            // perlin.h:77-86
 }
 
-// fractal sum over octaves for the two samples (main.cpp:689-734 with FMA).  `half_amp`
-// carries amplitude/2 because noise_octave2 returns 2*noise.
+// fractal sum over octaves for the thread's two samples (main.cpp:689-734 with FMA); the two
+// independent chains interleave in the instruction stream.  `half_amp` carries amplitude/2
+// because noise_octave returns 2*noise.
 template <int REPL, bool GUARD>
-__device__ __forceinline__ void fractal_loop(const unsigned char *t12_lane, const unsigned char *t3_lane,
-                                             const Fixed3 (&p)[S], const int (&octaves)[S], int omax,
+__device__ __forceinline__ void fractal_loop(const LaneTab &tab, const Fixed3 (&p)[S], const int (&octaves)[S], int omax,
                                              int kind, float gain, uint32_t one_bits, float (&value)[S])
 {
     float half_amp = 0.5f;
+    value[0] = value[1] = 0.0f;
     if (kind == PLANET_NOISE_RIDGED) {                               // main.cpp:716-731
         float weight[S] = { 1.0f, 1.0f };
-        value[0] = value[1] = 0.0f;
         for (int k = 0; k < omax; k++) {
-            float n[S];
-            unpack(noise_octave2<REPL>(t12_lane, t3_lane, p[0], p[1], k, one_bits), n[0], n[1]);
 #pragma unroll
             for (int s = 0; s < S; s++) {
-                float v = fmaf(-0.5f, fabsf(n[s]), 1.0f);           // offset - |noise|
+                const float n = noise_octave<REPL>(tab, p[s], k, one_bits);
+                float v = fmaf(-0.5f, fabsf(n), 1.0f);              // offset - |noise|
                 v = v * v;
-                float nv = fmaf(v * (2.0f * half_amp), weight[s], value[s]);
+                const float nv = fmaf(v * (2.0f * half_amp), weight[s], value[s]);
                 if (!GUARD || k < octaves[s]) { value[s] = nv; weight[s] = v; }
             }
             half_amp *= gain;
         }
     } else {                                                         // main.cpp:699-704
-        f2 acc = splat(0.0f);
 #pragma unroll K2_UNROLL
         for (int k = 0; k < omax; k++) {
-            f2 n = noise_octave2<REPL>(t12_lane, t3_lane, p[0], p[1], k, one_bits);
-            if (GUARD) {
-                float lo, hi, alo, ahi;
-                unpack(fma2(n, splat(half_amp), acc), lo, hi);
-                unpack(acc, alo, ahi);
-                acc = pack(k < octaves[0] ? lo : alo, k < octaves[1] ? hi : ahi);
-            } else {
-                acc = fma2(n, splat(half_amp), acc);
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                const float n = noise_octave<REPL>(tab, p[s], k, one_bits);
+                if (!GUARD || k < octaves[s]) value[s] = fmaf(n, half_amp, value[s]);
             }
             half_amp *= gain;                                        // main.cpp:703
         }
-        unpack(acc, value[0], value[1]);
     }
 }
 
 template <int REPL>
-__device__ __forceinline__ void fractal(const unsigned char *t12_lane, const unsigned char *t3_lane,
-                                        const Fixed3 (&p)[S], const int (&octaves)[S], int kind,
+__device__ __forceinline__ void fractal(const LaneTab &tab, const Fixed3 (&p)[S], const int (&octaves)[S], int kind,
                                         float gain, uint32_t one_bits, float (&value)[S])
 {
     int omax = max(octaves[0], octaves[1]);
-    if (octaves[0] == octaves[1]) fractal_loop<REPL, false>(t12_lane, t3_lane, p, octaves, omax, kind, gain, one_bits, value);
-    else                          fractal_loop<REPL, true>(t12_lane, t3_lane, p, octaves, omax, kind, gain, one_bits, value);
+    if (octaves[0] == octaves[1]) fractal_loop<REPL, false>(tab, p, octaves, omax, kind, gain, one_bits, value);
+    else                          fractal_loop<REPL, true>(tab, p, octaves, omax, kind, gain, one_bits, value);
 }
 
 // ---- EXACT arithmetic on the replicated tables ------------------------------------------
@@ -361,20 +357,19 @@ __device__ __forceinline__ void fractal(const unsigned char *t12_lane, const uns
 // LDS instead of 14 byte loads + 24 float loads with ~3-way conflicts, no `& 255` / `* 3` index
 // arithmetic.  Two identities keep the bits: (1) gradient components are 0 or +-1, so every
 // product of the dot is exact and x*g0 + y*g1 + z*g2 with separate roundings equals the same sum
-// written as two FMAs; (2) the table codes decode to 2*v, so the value is 2*noise, and scaling
+// written as two FMAs; (2) the table holds 2*v, so the value is 2*noise, and scaling
 // by two commutes with every rounding on the way (no value here is near the denormal range).
 // Returns 2 * PerlinNoise3(x, y, z).
-__device__ __forceinline__ float corner_exact2(uint32_t g, float x, float y, float z)
+__device__ __forceinline__ float corner_exact2(uint32_t gxw, uint32_t gyw, float x, float y, float z)
 {
-    const float gx = __uint_as_float(g & 0xFF000000u);
-    const float gy = __uint_as_float(__byte_perm(g, 0, 0x1444));
-    const float gz = __uint_as_float(g << 24);
+    const float gx = __uint_as_float(gxw & 0xFF000000u);             // drop the stowaway z code
+    const float gy = __uint_as_float(gyw);
+    const float gz = __uint_as_float(gxw << 30);
     return __fmaf_rn(z, gz, __fmaf_rn(y, gy, __fmul_rn(x, gx)));     // perlin.h:47
 }
 
 template <int REPL>
-__device__ __forceinline__ float noise3_exact2(const unsigned char *t12_lane, const unsigned char *t3_lane,
-                                               double x, double y, double z)
+__device__ __forceinline__ float noise3_exact2(const LaneTab &tab, double x, double y, double z)
 {
     using L = Layout<REPL>;
     constexpr int T12_ROW = L::T12_ROW;
@@ -386,18 +381,19 @@ __device__ __forceinline__ float noise3_exact2(const unsigned char *t12_lane, co
     const float x0 = __double2float_rn(x), x1 = __double2float_rn(__dadd_rn(x, -1.0));   // perlin.h:68-75
     const float y0 = __double2float_rn(y), y1 = __double2float_rn(__dadd_rn(y, -1.0));
     const float z0 = __double2float_rn(z), z1 = __double2float_rn(__dadd_rn(z, -1.0));
-    const uint32_t cx = ((uint32_t)ix & 255u) << L::LOG12;           // PerlinRandom's `& 255`, perlin.h:40
-    const uint32_t cy = ((uint32_t)iy & 255u) << L::LOG12;
-    const uint32_t cz = ((uint32_t)iz & 255u) << L::LOG3;
-    const uint32_t a0 = lds_u16(t12_lane, cx), a1 = lds_u16(t12_lane, cx + T12_ROW);
-    const uint32_t b00 = lds_u16(t12_lane, a0 + cy + 2), b01 = lds_u16(t12_lane, a0 + cy + 2 + T12_ROW);
-    const uint32_t b10 = lds_u16(t12_lane, a1 + cy + 2), b11 = lds_u16(t12_lane, a1 + cy + 2 + T12_ROW);
-    const uint2 e00 = lds_v2(t3_lane, b00 + cz), e10 = lds_v2(t3_lane, b10 + cz);
-    const uint2 e01 = lds_v2(t3_lane, b01 + cz), e11 = lds_v2(t3_lane, b11 + cz);
-    const float g0 = corner_exact2(e00.x, x0, y0, z0), g1 = corner_exact2(e10.x, x1, y0, z0);
-    const float g2 = corner_exact2(e01.x, x0, y1, z0), g3 = corner_exact2(e11.x, x1, y1, z0);
-    const float g4 = corner_exact2(e00.y, x0, y0, z1), g5 = corner_exact2(e10.y, x1, y0, z1);
-    const float g6 = corner_exact2(e01.y, x0, y1, z1), g7 = corner_exact2(e11.y, x1, y1, z1);
+    const uint32_t cx = (((uint32_t)ix & 255u) << L::LOG12) | tab.l12;   // PerlinRandom's `& 255`, perlin.h:40
+    const uint32_t cy = (((uint32_t)iy & 255u) << L::LOG12) | tab.l12;
+    const uint32_t cz = (((uint32_t)iz & 255u) << L::LOG3) | tab.l3;
+    const unsigned char *t = tab.base;
+    const uint32_t a0 = lds_u16(t, cx), a1 = lds_u16(t, cx + T12_ROW);
+    const uint32_t b00 = lds_u16(t, a0 + cy + 2), b01 = lds_u16(t, a0 + cy + 2 + T12_ROW);
+    const uint32_t b10 = lds_u16(t, a1 + cy + 2), b11 = lds_u16(t, a1 + cy + 2 + T12_ROW);
+    const uint4 e00 = lds_v4(t, b00 + cz + L::T12_BYTES), e10 = lds_v4(t, b10 + cz + L::T12_BYTES);
+    const uint4 e01 = lds_v4(t, b01 + cz + L::T12_BYTES), e11 = lds_v4(t, b11 + cz + L::T12_BYTES);
+    const float g0 = corner_exact2(e00.x, e00.y, x0, y0, z0), g1 = corner_exact2(e10.x, e10.y, x1, y0, z0);
+    const float g2 = corner_exact2(e01.x, e01.y, x0, y1, z0), g3 = corner_exact2(e11.x, e11.y, x1, y1, z0);
+    const float g4 = corner_exact2(e00.z, e00.w, x0, y0, z1), g5 = corner_exact2(e10.z, e10.w, x1, y0, z1);
+    const float g6 = corner_exact2(e01.z, e01.w, x0, y1, z1), g7 = corner_exact2(e11.z, e11.w, x1, y1, z1);
     const float l0 = exact::lerp(g0, g1, u), l1 = exact::lerp(g2, g3, u);
     const float l2 = exact::lerp(g4, g5, u), l3 = exact::lerp(g6, g7, u);
     return exact::lerp(exact::lerp(l0, l1, v), exact::lerp(l2, l3, v), w);   // perlin.h:77-86
@@ -405,8 +401,7 @@ __device__ __forceinline__ float noise3_exact2(const unsigned char *t12_lane, co
 
 // Perlin::operator() (main.cpp:825-832) over noise3_exact2; same operation order as exact::height
 template <int REPL>
-__device__ __forceinline__ float height_exact_tab(const unsigned char *t12_lane, const unsigned char *t3_lane,
-                                                  const HeightCfg &c, d3 p, int depth)
+__device__ __forceinline__ float height_exact_tab(const LaneTab &tab, const HeightCfg &c, d3 p, int depth)
 {
     if (c.kind == PLANET_NOISE_ZERO) return 0.0f;
     const int octaves = octaves_for(c.fixed_octaves, depth, c.max_depth);
@@ -418,7 +413,7 @@ __device__ __forceinline__ float height_exact_tab(const unsigned char *t12_lane,
     float amplitude = 1.0f, weight = 1.0f, value = 0.0f;
     const bool ridged = c.kind == PLANET_NOISE_RIDGED;
     for (int i = 0; i < octaves; ++i) {
-        float n = __fmul_rn(0.5f, noise3_exact2<REPL>(t12_lane, t3_lane, __dmul_rn(p.x, frequency),
+        float n = __fmul_rn(0.5f, noise3_exact2<REPL>(tab, __dmul_rn(p.x, frequency),
                                                       __dmul_rn(p.y, frequency), __dmul_rn(p.z, frequency)));
         if (ridged) {                                                // main.cpp:716-731
             n = fabsf(n);
@@ -447,8 +442,7 @@ k_height_maps_exact_tab(const Quad *__restrict__ quads, int64_t total, int dim, 
     build_tables<32>(smem);
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const unsigned char *t12_lane = smem + lane * 4;
-    const unsigned char *t3_lane = smem + L::T12_BYTES + lane * 8;
+    const LaneTab tab = lane_tab<32>(smem, lane);
     const uint32_t dim2 = (uint32_t)dim * (uint32_t)dim;
     const double div = __ddiv_rn(1.0, (double)(dim - 3));            // main.cpp:134
     // i = q * dim2 + r is advanced incrementally: one 64-bit division per thread, none per sample
@@ -463,7 +457,7 @@ k_height_maps_exact_tab(const Quad *__restrict__ quads, int64_t total, int dim, 
         Quad qd;
         qd.p[0] = quad->p[0]; qd.p[1] = quad->p[1]; qd.p[2] = quad->p[2]; qd.p[3] = quad->p[3];
         const d3 p = exact::sample_point(qd, (int)x, (int)y, div);
-        const float h = height_exact_tab<32>(t12_lane, t3_lane, cfg, p, (int)quad_depth(quad->id));
+        const float h = height_exact_tab<32>(tab, cfg, p, (int)quad_depth(quad->id));
         out[i] = h;
         if constexpr (GATHER) {
 #pragma unroll
@@ -519,8 +513,7 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int WARPS = NTHREADS / 32;
     TileQuad *tq = reinterpret_cast<TileQuad *>(smem + L::TABLES) + warp * MAX_WTILE_QUADS;
-    const unsigned char *t12_lane = smem + (lane % REPL) * 4;
-    const unsigned char *t3_lane = smem + L::T12_BYTES + (lane % REPL) * 8;
+    const LaneTab tab = lane_tab<REPL>(smem, lane);
     const uint32_t dim2 = (uint32_t)dim * (uint32_t)dim;
     const bool small_maps = dim2 < (uint32_t)WTILE;          // a warp tile may then span > 2 quads
     const double div = 1.0 / (double)(dim - 3);
@@ -648,7 +641,7 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
             if (cfg.kind == PLANET_NOISE_ZERO) {
                 value[0] = value[1] = 0.0f;
             } else {
-                fractal<REPL>(t12_lane, t3_lane, p, oct, cfg.kind, cfg.gain, one_bits, value);
+                fractal<REPL>(tab, p, oct, cfg.kind, cfg.gain, one_bits, value);
             }
 
             const int64_t o = base + i0;                                     // even
@@ -692,8 +685,7 @@ k_points_fast(const double *__restrict__ xyz, int64_t n, int kind, float gain, i
     build_tables<REPL>(smem);
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const unsigned char *t12_lane = smem + (lane % REPL) * 4;
-    const unsigned char *t3_lane = smem + Layout<REPL>::T12_BYTES + (lane % REPL) * 8;
+    const LaneTab tab = lane_tab<REPL>(smem, lane);
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         // samples of one thread are strided by THREADS so the 24-byte point loads and the
@@ -717,7 +709,7 @@ k_points_fast(const double *__restrict__ xyz, int64_t n, int kind, float gain, i
             oct[s] = octaves;
         }
         float value[S];
-        fractal<REPL>(t12_lane, t3_lane, p, oct, kind, gain, one_bits, value);
+        fractal<REPL>(tab, p, oct, kind, gain, one_bits, value);
 #pragma unroll
         for (int s = 0; s < S; s++)
             if (idx[s] < n) out[idx[s]] = value[s] * height_scale;

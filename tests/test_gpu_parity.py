@@ -292,6 +292,29 @@ def test_reference_shaped_generate_height_map(gpu, golden):
         assert got.tobytes() == golden["frame_height_maps"][k].tobytes()
 
 
+def test_reference_shaped_calls_from_eight_host_threads(gpu, golden):
+    """SURVEY 8b threading: the reference's GenerateHeightMap is a pure function, callable from 8
+    threads at once with identical output; the drop-in serialises on a mutex and must give the same
+    bits whichever thread calls (ctypes drops the GIL for the duration of each call)."""
+    from concurrent.futures import ThreadPoolExecutor
+    quads = quads_from_bytes(golden["frame_quads"])
+    gpu.set_params(gpu.default_params())
+    ks = list(range(0, len(quads), 3))
+    max_lod, want_maps = int(golden["max_lod"]), golden["frame_height_maps"]   # NpzFile is not thread-safe: read first
+
+    def one(k):
+        m = gpu.generate_height_map(quads[k], 32, max_lod)
+        h = gpu.get_height_at(np.array(quads[k]["p"][0]), 0, 1)
+        return k, m.tobytes(), h
+
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        results = list(pool.map(one, ks * 3))
+    want_h = {}
+    for k, m, h in results:
+        assert m == want_maps[k].tobytes(), k
+        assert want_h.setdefault(k, h) == h and np.isfinite(h)
+
+
 def test_host_batch_path_equals_device_path(gpu, golden):
     quads = quads_from_bytes(golden["frame_quads"])
     p = gpu.default_params(precision=gpu.FAST)
