@@ -17,23 +17,23 @@
 //    window of X: W = funnelshift_l(lo, hi, k) -> cell = W[30:23], fraction = W[22:0].
 //    One SHF per axis per octave replaces the reference's fp64 multiply, floor and
 //    subtract; the fraction becomes a float with one LOP3 (mantissa splice) and one FADD.
-//  * The permutation table is staged in shared memory in a lane-replicated layout:
-//    row r of a table holds the same entry 32 times, one copy per bank, so the 14
-//    dependent lookups per octave-sample never bank-conflict no matter how random the
-//    cells are.  Entries are stored pre-scaled as byte offsets of the next row, so a
-//    chained lookup is one IADD + one LDS.  T12 (levels 1,2: 512 rows x 128 B) packs
-//    both scalings as two u16; T3 (level 3: 512 rows x 256 B) holds, per row, the gradient
-//    codes of BOTH z-neighbours (rows i and i+1) so one LDS.64 serves two cube corners:
-//    14 shared-memory wavefronts per octave-sample in total (shared memory moves 128 B/clk
-//    per SM, which would otherwise be the wall).  A code is three bytes, each the top byte
-//    of the float 2*v (v in {0,+-1}), so a component decodes with a single AND/PRMT/shift.
-//  * 768-thread CTAs, one per SM (192 KB of tables), persistent; warps take 128-sample
-//    tiles round-robin; each thread owns 2 consecutive texels and carries them as one
-//    packed f32x2 pair: every FADD/FMUL/FFMA of fade, gradient dots, lerps and the octave
-//    accumulation is an FADD2/FMUL2/FFMA2.  Measured (tools/microbench2.cu): a packed op
-//    holds the issue port for two cycles, so this halves instruction count and register
-//    pressure but not issue time -- the kernel is issue-bound at ~117 slots per
-//    octave-sample (DESIGN.md, K2 roofline).
+//  * The tables are staged in shared memory in a lane-replicated layout, so the 10 dependent
+//    lookups per octave-sample never bank-conflict no matter how random the cells are.
+//    Entries are stored pre-scaled as byte offsets of the next row and the lane's copy offset is
+//    OR-ed into the cell offset once per axis, so a chained lookup is one IADD3 + one
+//    LDS [R + UR + imm].  T12 (levels 1,2: 512 rows x 32 copies x u32) packs both scalings as
+//    two u16.  T3 (level 3: 512 rows x 8 copies x 16 B) holds, per row, the gradients of BOTH
+//    z-neighbours (rows i and i+1) as FINISHED floats {gx, gy, gx', gy'} = 2*v in {0, +-2}: one
+//    LDS.128 serves two cube corners and gx, gy go straight into the FMAs.  gz rides in the two
+//    lowest mantissa bits of gx and costs one shift.  An LDS.128 is served a quarter-warp at a
+//    time, hence 8 copies.  22 shared-memory wavefronts per octave-sample (shared memory moves
+//    128 B/clk per SM: 71 % busy) buy 16 fewer issue slots than byte codes decoded by
+//    AND/PRMT/shift (tools/microbench3.cu; the kernel is issue-bound).
+//  * 768-thread CTAs, one per SM (128 KB of tables), persistent; warps take 128-sample tiles
+//    round-robin; each thread owns 2 consecutive texels whose two independent dependency chains
+//    interleave in the instruction stream.  Plain FP32 FMA: the packed f32x2 forms
+//    (FFMA2/FMUL2/FADD2) hold the issue port for two cycles (tools/microbench2.cu), so they save
+//    no issue time and would need register-pair moves here.  99 instructions per octave-sample.
 //  * Per-tile prologue: one thread per touched quad turns the 104-byte Quad into the
 //    bilinear form P = A + B x + y (C + D x) per axis in doubles pre-scaled by 2^55
 //    (same sample points as main.cpp:132-146 up to 1 ulp of double), so a sample's
