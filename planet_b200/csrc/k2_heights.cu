@@ -17,23 +17,24 @@
 //    window of X: W = funnelshift_l(lo, hi, k) -> cell = W[30:23], fraction = W[22:0].
 //    One SHF per axis per octave replaces the reference's fp64 multiply, floor and
 //    subtract; the fraction becomes a float with one LOP3 (mantissa splice) and one FADD.
-//  * The tables are staged in shared memory in a lane-replicated layout, so the 10 dependent
+//  * The tables are staged in shared memory in a lane-replicated layout, so the 7 dependent
 //    lookups per octave-sample never bank-conflict no matter how random the cells are.
 //    Entries are stored pre-scaled as byte offsets of the next row and the lane's copy offset is
 //    OR-ed into the cell offset once per axis, so a chained lookup is one IADD3 + one
-//    LDS [R + UR + imm].  T12 (levels 1,2: 512 rows x 32 copies x u32) packs both scalings as
-//    two u16.  T3 (level 3: 512 rows x 8 copies x 16 B) holds, per row, the gradients of BOTH
-//    z-neighbours (rows i and i+1) as FINISHED floats {gx, gy, gx', gy'} = 2*v in {0, +-2}: one
-//    LDS.128 serves two cube corners and gx, gy go straight into the FMAs.  gz rides in the two
-//    lowest mantissa bits of gx and costs one shift.  An LDS.128 is served a quarter-warp at a
-//    time, hence 8 copies.  22 shared-memory wavefronts per octave-sample (shared memory moves
-//    128 B/clk per SM: 71 % busy) buy 16 fewer issue slots than byte codes decoded by
-//    AND/PRMT/shift (tools/microbench3.cu; the kernel is issue-bound).
-//  * 768-thread CTAs, one per SM (128 KB of tables), persistent; warps take 128-sample tiles
+//    LDS [R + UR + imm].  Every entry carries its +1 neighbour: P1 and P2 (levels 1, 2) hold
+//    {R(i), R(i+1)} as two pre-scaled u32 (LDS.64), T3 (level 3) holds the gradients of BOTH
+//    z-neighbours as FINISHED floats {gx, gy, gx', gy'} = 2*v in {0, +-2} (LDS.128), so the 8
+//    corners of a cell cost 1 + 2 + 4 loads and gx, gy go straight into the FMAs.  gz rides in
+//    the two lowest mantissa bits of gx and costs one shift.  An LDS.64 / LDS.128 is served a
+//    half / quarter warp at a time, hence 16 / 8 copies per row.  22 shared-memory wavefronts per
+//    octave-sample buy 16 fewer instructions than byte codes decoded by AND/PRMT/shift
+//    (tools/microbench3.cu).  Measured cost model of this kernel: an SM sub-partition spends one
+//    cycle per instruction plus one per shared-memory wavefront of its own loads.
+//  * 768-thread CTAs, one per SM (160 KB of tables), persistent; warps take 128-sample tiles
 //    round-robin; each thread owns 2 consecutive texels whose two independent dependency chains
 //    interleave in the instruction stream.  Plain FP32 FMA: the packed f32x2 forms
 //    (FFMA2/FMUL2/FADD2) hold the issue port for two cycles (tools/microbench2.cu), so they save
-//    no issue time and would need register-pair moves here.  99 instructions per octave-sample.
+//    no issue time and would need register-pair moves here.  96 instructions per octave-sample.
 //  * Per-tile prologue: one thread per touched quad turns the 104-byte Quad into the
 //    bilinear form P = A + B x + y (C + D x) per axis in doubles pre-scaled by 2^55
 //    (same sample points as main.cpp:132-146 up to 1 ulp of double), so a sample's
@@ -131,21 +132,27 @@ constexpr int THREADS = 512;
 constexpr int S = 2;                          // consecutive samples per thread (one 8-byte store)
 constexpr int TILE = THREADS * S;             // samples per CTA iteration
 constexpr int ROWS = 512;                     // table index range: perm (<=255) + cell (<=255) + 1
-// Table layout for a replication factor REPL.  REPL = 32 is the throughput layout (128 KB):
-// every T12 entry 32 times, one copy per bank, and every 16-byte T3 entry 8 times -- an LDS.128
-// is served a quarter-warp at a time, so 8 copies at 16-byte stride put the 8 lanes of a phase
-// in 8 distinct bank groups whatever rows they ask for (tools/microbench3.cu).  REPL = 1 is the
-// compact 10 KB layout whose build costs nothing, for small batches where latency matters.
+// Table layout for a replication factor REPL.  REPL = 32 is the throughput layout (160 KB): an
+// LDS.64 is served a half-warp at a time and an LDS.128 a quarter-warp at a time, so 16 copies of
+// an 8-byte entry and 8 copies of a 16-byte entry put the lanes of every phase in distinct bank
+// groups whatever rows they ask for (tools/microbench3.cu).  REPL = 1 is the compact 14 KB
+// layout whose build costs nothing, for small batches where latency matters.
+//   P1 (level 1, 256 rows): { R(i), R(i+1) } * P_ROW      -- byte offsets of the next P2 row
+//   P2 (level 2, 512 rows): { R(i), R(i+1) } * T3_ROW     -- byte offsets of the next T3 row
+//   T3 (level 3, 512 rows): { gx(i)|zc, gy(i), gx(i+1)|zc, gy(i+1) }
+// where R = perlin_random_table[i & 255].  Every entry carries its +1 neighbour, so the 8
+// corners of a cell cost 1 + 2 + 4 loads.
 template <int REPL> struct Layout {
     static_assert(REPL == 32 || REPL == 1, "layouts in use");
+    static constexpr int P_COPIES = REPL == 32 ? 16 : 1;
     static constexpr int T3_COPIES = REPL == 32 ? 8 : 1;
-    static constexpr int T12_ROW = REPL * 4;              // REPL x u32
-    static constexpr int T3_ROW = T3_COPIES * 16;         // T3_COPIES x {gx(i)|zc, gy(i), gx(i+1)|zc, gy(i+1)}
-    static constexpr int T12_BYTES = ROWS * T12_ROW;      // 64 KB at REPL 32
-    static constexpr int T3_BYTES = ROWS * T3_ROW;        // 64 KB at REPL 32
-    static constexpr int TABLES = T12_BYTES + T3_BYTES;
-    static constexpr int LOG12 = REPL == 32 ? 7 : 2;
-    static constexpr int LOG3 = REPL == 32 ? 7 : 4;
+    static constexpr int P_ROW = P_COPIES * 8, T3_ROW = T3_COPIES * 16;
+    static constexpr int LOGP = REPL == 32 ? 7 : 3, LOG3 = REPL == 32 ? 7 : 4;
+    static constexpr int P1_BYTES = 256 * P_ROW;          // 32 KB at REPL 32
+    static constexpr int P2_BYTES = ROWS * P_ROW;         // 64 KB
+    static constexpr int T3_BYTES = ROWS * T3_ROW;        // 64 KB
+    static constexpr int P2_AT = P1_BYTES, T3_AT = P1_BYTES + P2_BYTES;
+    static constexpr int TABLES = P1_BYTES + P2_BYTES + T3_BYTES;
 };
 constexpr uint32_t ONE_BITS = 0x3F800000u;                 // float 1.0, see splice_mantissa
 constexpr double FIX_ONE = 36028797018963968.0;           // 2^55
@@ -164,24 +171,24 @@ template <int REPL> constexpr int smem_bytes(int nthreads)
 constexpr int SMEM_BYTES = smem_bytes<32>(768);
 
 // shared-memory table reads; `base` is a pointer into the dynamic shared array, so the
-// compiler emits LDS.U16 / LDS.128 with 32-bit addressing and immediate offsets
-__device__ __forceinline__ uint32_t lds_u16(const unsigned char *base, uint32_t off)
+// compiler emits LDS.64 / LDS.128 with 32-bit addressing and immediate offsets
+__device__ __forceinline__ uint2 lds_v2(const unsigned char *base, uint32_t off)
 {
-    return *reinterpret_cast<const unsigned short *>(base + off);
+    return *reinterpret_cast<const uint2 *>(base + off);
 }
 __device__ __forceinline__ uint4 lds_v4(const unsigned char *base, uint32_t off)
 {
     return *reinterpret_cast<const uint4 *>(base + off);
 }
 // A lane's view of the tables: the (warp-uniform) start of the dynamic shared array plus the
-// byte offsets of the lane's own copies inside a T12 / T3 row.  Keeping the base uniform and the
+// byte offsets of the lane's own copies inside a P1/P2 row and a T3 row.  Keeping the base uniform and the
 // lane part a 32-bit offset lets every lookup be LDS [R + UR + imm]: the lane offset is OR-ed
 // into the cell offset once per axis instead of being added to every address.
-struct LaneTab { const unsigned char *base; uint32_t l12, l3; };
+struct LaneTab { const unsigned char *base; uint32_t lp, l3; };
 template <int REPL> __device__ __forceinline__ LaneTab lane_tab(const unsigned char *smem, int lane)
 {
     using L = Layout<REPL>;
-    return { smem, (uint32_t)(lane % REPL) * 4u, (uint32_t)(lane % L::T3_COPIES) * 16u };
+    return { smem, (uint32_t)(lane % L::P_COPIES) * 8u, (uint32_t)(lane % L::T3_COPIES) * 16u };
 }
 
 // A gradient vector of perlin.h:30-36 as three byte codes, one per component, each the TOP
@@ -199,15 +206,14 @@ __device__ __forceinline__ uint32_t grad_code(int h)
 __device__ __forceinline__ uint32_t gx_word(uint32_t code) { return (code & 0xFF000000u) | ((code & 0xC0u) >> 6); }
 __device__ __forceinline__ uint32_t gy_word(uint32_t code) { return (code & 0x0000FF00u) << 16; }
 
-// Build the (lane-replicated) tables, perm = table[i & 255]:
-//   T12[i][copy] = (perm*T12_ROW) | (perm*T3_ROW) << 16       next-row byte offsets for levels 1 and 2
-//   T3 [i][copy] = { gx(i)|zc(i), gy(i), gx(i+1)|zc(i+1), gy(i+1) }   both z-neighbours in one LDS.128
+// Build the (lane-replicated) tables described at Layout
 template <int REPL>
 __device__ void build_tables(unsigned char *smem)
 {
     using L = Layout<REPL>;
-    uint32_t *t12 = reinterpret_cast<uint32_t *>(smem);
-    uint4 *t3 = reinterpret_cast<uint4 *>(smem + L::T12_BYTES);
+    uint2 *p1 = reinterpret_cast<uint2 *>(smem);
+    uint2 *p2 = reinterpret_cast<uint2 *>(smem + L::P2_AT);
+    uint4 *t3 = reinterpret_cast<uint4 *>(smem + L::T3_AT);
     // stage {perm, code(perm)} for the 256 table entries in the (not yet used) scratch area
     uint2 *stage = reinterpret_cast<uint2 *>(smem + L::TABLES);
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
@@ -215,9 +221,11 @@ __device__ void build_tables(unsigned char *smem)
         stage[i] = make_uint2(p, grad_code(p));
     }
     __syncthreads();
-    for (int w = threadIdx.x; w < ROWS * REPL; w += blockDim.x) {
-        const uint32_t p = stage[(w / REPL) & 255].x;
-        t12[w] = (p << L::LOG12) | (p << (16 + L::LOG3));              // next-row byte offsets, levels 1 and 2
+    for (int w = threadIdx.x; w < ROWS * L::P_COPIES; w += blockDim.x) {
+        const int i = w / L::P_COPIES;
+        const uint32_t r0 = stage[i & 255].x, r1 = stage[(i + 1) & 255].x;
+        if (i < 256) p1[w] = make_uint2(r0 << L::LOGP, r1 << L::LOGP);
+        p2[w] = make_uint2(r0 << L::LOG3, r1 << L::LOG3);
     }
     for (int w = threadIdx.x; w < ROWS * L::T3_COPIES; w += blockDim.x) {
         const int i = w / L::T3_COPIES;
@@ -260,7 +268,6 @@ template <int REPL>
 __device__ __forceinline__ Hashed hash_octave(const LaneTab &tab, const Fixed3 &p, int k, uint32_t one_bits)
 {
     using L = Layout<REPL>;
-    constexpr int T12_ROW = L::T12_ROW, T3_ROW = L::T3_ROW;
     // 32-bit windows of the fixed-point coordinate: bits 30..23 = cell & 255, 22..0 = fraction
     uint32_t wx = __funnelshift_l(p.xlo, p.xhi, k);
     uint32_t wy = __funnelshift_l(p.ylo, p.yhi, k);
@@ -270,18 +277,17 @@ __device__ __forceinline__ Hashed hash_octave(const LaneTab &tab, const Fixed3 &
     h.my = splice_mantissa(wy, one_bits);
     h.mz = splice_mantissa(wz, one_bits);
     // (cell & 255) * row size, with the lane's copy offset OR-ed into the (zero) low bits
-    const uint32_t cx = ((wx >> (23 - L::LOG12)) & (255u << L::LOG12)) | tab.l12;
-    const uint32_t cy = ((wy >> (23 - L::LOG12)) & (255u << L::LOG12)) | tab.l12;
+    const uint32_t cx = ((wx >> (23 - L::LOGP)) & (255u << L::LOGP)) | tab.lp;
+    const uint32_t cy = ((wy >> (23 - L::LOGP)) & (255u << L::LOGP)) | tab.lp;
     const uint32_t cz = ((wz >> (23 - L::LOG3)) & (255u << L::LOG3)) | tab.l3;
     const unsigned char *t = tab.base;
-    uint32_t a0 = lds_u16(t, cx), a1 = lds_u16(t, cx + T12_ROW);               // R(ix), R(ix+1) (* T12_ROW)
-    uint32_t b00 = lds_u16(t, a0 + cy + 2), b01 = lds_u16(t, a0 + cy + 2 + T12_ROW);
-    uint32_t b10 = lds_u16(t, a1 + cy + 2), b11 = lds_u16(t, a1 + cy + 2 + T12_ROW);
-    h.e00 = lds_v4(t, b00 + cz + L::T12_BYTES);                     // R(R(R(ix)+iy)+iz), ..+iz+1
-    h.e10 = lds_v4(t, b10 + cz + L::T12_BYTES);
-    h.e01 = lds_v4(t, b01 + cz + L::T12_BYTES);
-    h.e11 = lds_v4(t, b11 + cz + L::T12_BYTES);
-    (void)T3_ROW;
+    const uint2 a = lds_v2(t, cx);                                  // R(ix), R(ix+1)
+    const uint2 b0 = lds_v2(t, a.x + cy + L::P2_AT);                // R(R(ix)+iy), R(R(ix)+iy+1)
+    const uint2 b1 = lds_v2(t, a.y + cy + L::P2_AT);                // the same for ix+1
+    h.e00 = lds_v4(t, b0.x + cz + L::T3_AT);                        // R(R(R(ix)+iy)+iz), ..+iz+1
+    h.e10 = lds_v4(t, b1.x + cz + L::T3_AT);
+    h.e01 = lds_v4(t, b0.y + cz + L::T3_AT);
+    h.e11 = lds_v4(t, b1.y + cz + L::T3_AT);
     return h;
 }
 
@@ -372,7 +378,6 @@ template <int REPL>
 __device__ __forceinline__ float noise3_exact2(const LaneTab &tab, double x, double y, double z)
 {
     using L = Layout<REPL>;
-    constexpr int T12_ROW = L::T12_ROW;
     const int ix = exact::cell(x), iy = exact::cell(y), iz = exact::cell(z);     // perlin.h:52-55
     x = __dsub_rn(x, (double)ix);
     y = __dsub_rn(y, (double)iy);
@@ -381,15 +386,14 @@ __device__ __forceinline__ float noise3_exact2(const LaneTab &tab, double x, dou
     const float x0 = __double2float_rn(x), x1 = __double2float_rn(__dadd_rn(x, -1.0));   // perlin.h:68-75
     const float y0 = __double2float_rn(y), y1 = __double2float_rn(__dadd_rn(y, -1.0));
     const float z0 = __double2float_rn(z), z1 = __double2float_rn(__dadd_rn(z, -1.0));
-    const uint32_t cx = (((uint32_t)ix & 255u) << L::LOG12) | tab.l12;   // PerlinRandom's `& 255`, perlin.h:40
-    const uint32_t cy = (((uint32_t)iy & 255u) << L::LOG12) | tab.l12;
+    const uint32_t cx = (((uint32_t)ix & 255u) << L::LOGP) | tab.lp;    // PerlinRandom's `& 255`, perlin.h:40
+    const uint32_t cy = (((uint32_t)iy & 255u) << L::LOGP) | tab.lp;
     const uint32_t cz = (((uint32_t)iz & 255u) << L::LOG3) | tab.l3;
     const unsigned char *t = tab.base;
-    const uint32_t a0 = lds_u16(t, cx), a1 = lds_u16(t, cx + T12_ROW);
-    const uint32_t b00 = lds_u16(t, a0 + cy + 2), b01 = lds_u16(t, a0 + cy + 2 + T12_ROW);
-    const uint32_t b10 = lds_u16(t, a1 + cy + 2), b11 = lds_u16(t, a1 + cy + 2 + T12_ROW);
-    const uint4 e00 = lds_v4(t, b00 + cz + L::T12_BYTES), e10 = lds_v4(t, b10 + cz + L::T12_BYTES);
-    const uint4 e01 = lds_v4(t, b01 + cz + L::T12_BYTES), e11 = lds_v4(t, b11 + cz + L::T12_BYTES);
+    const uint2 a = lds_v2(t, cx);
+    const uint2 b0 = lds_v2(t, a.x + cy + L::P2_AT), b1 = lds_v2(t, a.y + cy + L::P2_AT);
+    const uint4 e00 = lds_v4(t, b0.x + cz + L::T3_AT), e10 = lds_v4(t, b1.x + cz + L::T3_AT);
+    const uint4 e01 = lds_v4(t, b0.y + cz + L::T3_AT), e11 = lds_v4(t, b1.y + cz + L::T3_AT);
     const float g0 = corner_exact2(e00.x, e00.y, x0, y0, z0), g1 = corner_exact2(e10.x, e10.y, x1, y0, z0);
     const float g2 = corner_exact2(e01.x, e01.y, x0, y1, z0), g3 = corner_exact2(e11.x, e11.y, x1, y1, z0);
     const float g4 = corner_exact2(e00.z, e00.w, x0, y0, z1), g5 = corner_exact2(e10.z, e10.w, x1, y0, z1);
