@@ -292,7 +292,11 @@ int launch_tessellate_uniform(const planet_gpu_params *p, int depth, int64_t fir
         }
         // indices are rebased to the caller's buffer: quad 0 of this call is vertex block 0
         int quad_blocks = d_quads ? (int)std::min<int64_t>((nquads + 255) / 256, sm_count_k1()) : 0;
-        int idx_blocks = (int)std::min<int64_t>(nquads, (int64_t)sm_count_k1() * 6);
+        static const int idx_per_sm = [] {                               // tuning knob: index-stream CTAs per SM
+            const char *e = getenv("PLANET_K1_IDX_PER_SM");
+            return e ? std::max(1, std::min(8, atoi(e))) : 6;
+        }();
+        int idx_blocks = (int)std::min<int64_t>(nquads, (int64_t)sm_count_k1() * idx_per_sm);
         if (vec4) k_tessellate_fused<4><<<quad_blocks + idx_blocks, 256, smem, stream>>>(
                       depth, first, nquads, p->radius, d_quads, quad_blocks, n, nv, ni, d_indices);
         else      k_tessellate_fused<2><<<quad_blocks + idx_blocks, 256, smem, stream>>>(

@@ -651,7 +651,9 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
             const int64_t o = base + i0;                                     // even
             if (regular || (out_aligned8 && i0 + 1 < n_here)) {
                 const float2 h2 = make_float2(value[0] * cfg.height_scale, value[1] * cfg.height_scale);
-                __stcs(reinterpret_cast<float2 *>(out + o), h2);
+                // plain (write-back, evict-normal) store: the maps are K3's input and a C2 batch (67 MB)
+                // fits the 126 MB L2; a streaming store made K3 re-read them from HBM (K3 0.117 -> 0.100 ms)
+                *reinterpret_cast<float2 *>(out + o) = h2;
                 if constexpr (GATHER) {
 #pragma unroll
                     for (int r = 0; r < 7; r++)                              // NVLink peer stores (fused gather)
