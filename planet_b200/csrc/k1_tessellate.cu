@@ -19,6 +19,8 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 
 namespace planet {
 
@@ -166,7 +168,8 @@ __host__ __device__ inline uint32_t strip_index(int k, int n)
 template <int VEC>
 __global__ void __launch_bounds__(256)
 k_tessellate_fused(int depth, int64_t first, int64_t nquads, double radius, Quad *__restrict__ quads,
-                   int quad_blocks, int n, int nv, int ni, uint32_t *__restrict__ indices)
+                   int quad_blocks, int n, int nv, int ni, uint32_t *__restrict__ indices,
+                   const uint32_t *__restrict__ strip)
 {
     extern __shared__ __align__(16) uint32_t s_strip[];
     if ((int)blockIdx.x < quad_blocks) {
@@ -187,7 +190,8 @@ k_tessellate_fused(int depth, int64_t first, int64_t nquads, double radius, Quad
         for (int j = 0; j < KV; j++) {
             const int v = threadIdx.x + j * blockDim.x;
 #pragma unroll
-            for (int e = 0; e < VEC; e++) reg[j][e] = v < nvec ? strip_index(v * VEC + e, n) : 0u;
+            for (int e = 0; e < VEC; e++)                  // the library's cached strip if there is one, else the closed form
+                reg[j][e] = v < nvec ? (strip ? __ldg(strip + v * VEC + e) : strip_index(v * VEC + e, n)) : 0u;
         }
         for (int64_t q = q0; q < nquads; q += qstride) {
             const uint32_t base = (uint32_t)q * (uint32_t)nv;
@@ -207,7 +211,7 @@ k_tessellate_fused(int depth, int64_t first, int64_t nquads, double radius, Quad
         return;
     }
     // large patches: stage the strip in shared memory instead
-    for (int k = threadIdx.x; k < ni; k += blockDim.x) s_strip[k] = strip_index(k, n);
+    for (int k = threadIdx.x; k < ni; k += blockDim.x) s_strip[k] = strip ? __ldg(strip + k) : strip_index(k, n);
     __syncthreads();
     for (int64_t q = q0; q < nquads; q += qstride) {
         const uint32_t base = (uint32_t)q * (uint32_t)nv;
@@ -267,6 +271,45 @@ static int sm_count_k1()
     return n[dev];
 }
 
+// The strip of one patch (main.cpp:427-474), kept in device memory per patch size: evaluating the
+// closed form in every index-stream CTA cost ~3 us of a 30 us launch.  Built on the host (the closed
+// form is __host__ __device__) and uploaded with a synchronous copy, so it is complete before any
+// stream can read it; while a stream is being captured the kernels fall back to the closed form.
+static std::mutex g_strip_mutex;
+static struct StripCache { int n = 0; int dev = -1; uint32_t *d = nullptr; } g_strip;
+
+void release_strip_cache()                                            // planet_gpu_shutdown
+{
+    std::lock_guard<std::mutex> lock(g_strip_mutex);
+    if (g_strip.d) cudaFree(g_strip.d);
+    g_strip = StripCache();
+}
+
+static const uint32_t *cached_strip(int n, int ni, cudaStream_t stream)
+{
+    std::lock_guard<std::mutex> lock(g_strip_mutex);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (g_strip.d && g_strip.n == n && g_strip.dev == dev) return g_strip.d;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (g_strip.d) { cudaFree(g_strip.d); g_strip = StripCache(); }
+    std::vector<uint32_t> h((size_t)ni);
+    for (int k = 0; k < ni; k++) h[k] = strip_index(k, n);
+    uint32_t *d = nullptr;
+    if (cudaMalloc(&d, (size_t)ni * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMemcpy(d, h.data(), (size_t)ni * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError();
+        if (d) cudaFree(d);
+        return nullptr;                                               // not fatal: closed form in the kernel
+    }
+    g_strip.n = n; g_strip.dev = dev; g_strip.d = d;
+    return d;
+}
+
 int launch_tessellate_uniform(const planet_gpu_params *p, int depth, int64_t first, int64_t nquads,
                               Quad *d_quads, uint32_t *d_indices, cudaStream_t stream)
 {
@@ -297,10 +340,11 @@ int launch_tessellate_uniform(const planet_gpu_params *p, int depth, int64_t fir
             return e ? std::max(1, std::min(8, atoi(e))) : 6;
         }();
         int idx_blocks = (int)std::min<int64_t>(nquads, (int64_t)sm_count_k1() * idx_per_sm);
+        const uint32_t *strip = cached_strip(n, ni, stream);
         if (vec4) k_tessellate_fused<4><<<quad_blocks + idx_blocks, 256, smem, stream>>>(
-                      depth, first, nquads, p->radius, d_quads, quad_blocks, n, nv, ni, d_indices);
+                      depth, first, nquads, p->radius, d_quads, quad_blocks, n, nv, ni, d_indices, strip);
         else      k_tessellate_fused<2><<<quad_blocks + idx_blocks, 256, smem, stream>>>(
-                      depth, first, nquads, p->radius, d_quads, quad_blocks, n, nv, ni, d_indices);
+                      depth, first, nquads, p->radius, d_quads, quad_blocks, n, nv, ni, d_indices, strip);
     }
     count_launch();
     return check_cuda(cudaGetLastError(), "tessellate launch");

@@ -28,6 +28,7 @@ int launch_select_lod(const planet_gpu_params *, const double *, int, Quad *, in
 uint32_t host_strip_index(int, int);
 uint64_t host_uniform_leaf_id(int64_t, int);
 void release_lod_scratch();
+void release_strip_cache();
 
 // ---- state ------------------------------------------------------------------------------
 static thread_local char t_error[512] = "";
@@ -212,6 +213,7 @@ void planet_gpu_shutdown(void)
     }
     g_stage = Staging();
     release_lod_scratch();
+    release_strip_cache();
     g_ready = false;
 }
 
