@@ -82,7 +82,11 @@ typedef struct planet_gpu_quad {
 /* ---- lifecycle ------------------------------------------------------------------- */
 int  planet_gpu_abi_version(void);
 void planet_gpu_default_params(planet_gpu_params *out);      /* the reference's defaults, EXACT mode */
-int  planet_gpu_init(int device);                            /* selects the device, uploads tables */
+/* Selects the device (must be Blackwell: the kernels are sm_100a only).  One device per process:
+ * the staging buffers of the host-pointer calls and the LOD scratch belong to it, matching the
+ * one-process-per-GPU model the multi-GPU path uses.  Calling any other entry point first
+ * adopts the caller's current CUDA device. */
+int  planet_gpu_init(int device);
 void planet_gpu_shutdown(void);
 const char *planet_gpu_last_error(void);
 /* name, SM count, boost clock (kHz) and FP32 lanes/SM of the active device: the
