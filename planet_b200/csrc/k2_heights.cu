@@ -102,6 +102,67 @@ k_heights_at_exact(const double *__restrict__ xyz, int64_t n, int depth, HeightC
     }
 }
 
+// ---- the reference's seam, one call at a time (main.cpp:107-111) -----------------------------
+// A synchronous GenerateHeightMap / GetHeightAt through the two function pointers is pure
+// latency: the quad / point travels as a kernel ARGUMENT (no H2D copy) and the kernel stores its
+// result straight into pinned host memory (no D2H copy), so a call is one launch + one sync.
+// A single map is 1 024 samples x 6..18 octaves: too little work to fill the chip one thread per
+// sample, and a serial octave loop is the whole latency.  So 8 lanes share a sample: lane `sub`
+// evaluates octaves sub, sub + 8, ... (the noise of an octave does not depend on the others) and
+// the group's lanes then accumulate them in the reference's order (main.cpp:699-704 / 716-731),
+// which keeps the float sum bit-identical to the sequential loop.
+__global__ void __launch_bounds__(256)
+k_height_map_seam_exact(Quad quad, int dim, HeightCfg cfg, float *__restrict__ host_out)
+{
+    __shared__ unsigned char s_perm[256];
+    __shared__ float s_grad[48];
+    stage_small_tables(s_perm, s_grad);
+    const int dim2 = dim * dim;
+    const double div = __ddiv_rn(1.0, (double)(dim - 3));            // main.cpp:134
+    const int octaves = cfg.kind == PLANET_NOISE_ZERO ? 0 : octaves_for(cfg.fixed_octaves, (int)quad_depth(quad.id), cfg.max_depth);
+    const int lane = threadIdx.x & 31, sub = lane & 7, first = lane & ~7;
+    const int group = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, ngroups = (gridDim.x * blockDim.x) >> 3;
+    for (int i0 = group - (lane >> 3); i0 < dim2; i0 += ngroups) {   // i0: the warp's first sample (warp-uniform trip count)
+        const int i = min(i0 + (lane >> 3), dim2 - 1);
+        const int y = i / dim, x = i - y * dim;
+        d3 p = exact::mul(exact::sample_point(quad, x, y, div), cfg.coord_scale);   // main.cpp:132-146, 828
+        if (cfg.has_seed) { p.x = __dadd_rn(p.x, cfg.seed[0]); p.y = __dadd_rn(p.y, cfg.seed[1]); p.z = __dadd_rn(p.z, cfg.seed[2]); }
+        float amplitude = 1.0f, weight = 1.0f, value = 0.0f;
+        double frequency = 1.0;
+        for (int k0 = 0; k0 < octaves; k0 += 8) {
+            double f = frequency;                                    // lacunarity^k by the reference's repeated product
+            for (int j = 0; j < sub; j++) f = __dmul_rn(f, cfg.lacunarity);
+            float n = 0.0f;
+            if (k0 + sub < octaves)
+                n = exact::noise3(s_perm, s_grad, __dmul_rn(p.x, f), __dmul_rn(p.y, f), __dmul_rn(p.z, f));
+            for (int j = 0; j < 8 && k0 + j < octaves; j++) {
+                const float nj = __shfl_sync(0xffffffffu, n, first + j);
+                if (cfg.kind == PLANET_NOISE_RIDGED) {
+                    float v = (nj < 0.0f) ? -nj : nj;
+                    v = __fsub_rn(1.0f, v);
+                    v = __fmul_rn(v, v);
+                    value = __fadd_rn(value, __fmul_rn(__fmul_rn(v, amplitude), weight));
+                    weight = v;
+                } else {
+                    value = __fadd_rn(value, __fmul_rn(nj, amplitude));
+                }
+                amplitude = __fmul_rn(amplitude, cfg.gain);
+                frequency = __dmul_rn(frequency, cfg.lacunarity);
+            }
+        }
+        if (sub == 0 && i0 + (lane >> 3) < dim2) host_out[i] = __fmul_rn(value, cfg.height_scale);   // main.cpp:831
+    }
+}
+
+__global__ void __launch_bounds__(32)
+k_height_at_seam_exact(double px, double py, double pz, int depth, HeightCfg cfg, float *__restrict__ host_out)
+{
+    __shared__ unsigned char s_perm[256];
+    __shared__ float s_grad[48];
+    stage_small_tables(s_perm, s_grad);
+    if (threadIdx.x == 0) host_out[0] = exact::height(s_perm, s_grad, cfg, d3{ px, py, pz }, depth);
+}
+
 // raw PerlinNoise3 (octaves == 0) / PerlinfBm / PerlinRidged on points, through the
 // reference-named device functions of planet_call_surface.cuh
 __global__ void __launch_bounds__(256)
@@ -869,6 +930,30 @@ int launch_height_maps_gathered(const planet_gpu_params *p, const Quad *d_quads,
     }
     count_launch();
     return check_cuda(cudaGetLastError(), "height map kernel launch");
+}
+
+// The two seam calls in EXACT arithmetic (what the reference's defaults select); `host_out` is
+// pinned host memory.  Returns PLANET_E_UNSUPPORTED when the params ask for FAST: the caller then
+// takes the batched path with a batch of one.
+int launch_height_map_seam(const planet_gpu_params *p, const Quad *h_quad, int dim, int max_depth,
+                           float *host_out, cudaStream_t stream)
+{
+    if (p->precision != PLANET_PRECISION_EXACT || dim > 2048) return PLANET_E_UNSUPPORTED;
+    HeightCfg cfg = make_cfg(p, max_depth);
+    const int grid = std::min((dim * dim * 8 + 255) / 256, sm_count() * 8);   // 8 lanes per sample
+    k_height_map_seam_exact<<<grid, 256, 0, stream>>>(*h_quad, dim, cfg, host_out);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "height map (seam) launch");
+}
+
+int launch_height_at_seam(const planet_gpu_params *p, const double *h_xyz, int depth, int max_depth,
+                          float *host_out, cudaStream_t stream)
+{
+    if (p->precision != PLANET_PRECISION_EXACT) return PLANET_E_UNSUPPORTED;
+    HeightCfg cfg = make_cfg(p, max_depth);
+    k_height_at_seam_exact<<<1, 32, 0, stream>>>(h_xyz[0], h_xyz[1], h_xyz[2], depth, cfg, host_out);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "height at (seam) launch");
 }
 
 int launch_heights_at(const planet_gpu_params *p, const double *d_xyz, int64_t n, int depth,

@@ -18,6 +18,8 @@ int launch_height_maps(const planet_gpu_params *, const Quad *, int64_t, int, in
 struct PeerOut { float *ptr[7]; int n; };
 int launch_height_maps_gathered(const planet_gpu_params *, const Quad *, int64_t, int, int, float *, const PeerOut &, cudaStream_t);
 int launch_heights_at(const planet_gpu_params *, const double *, int64_t, int, int, float *, cudaStream_t);
+int launch_height_map_seam(const planet_gpu_params *, const Quad *, int, int, float *, cudaStream_t);
+int launch_height_at_seam(const planet_gpu_params *, const double *, int, int, float *, cudaStream_t);
 int launch_noise(const double *, int64_t, int, double, float, int, int, float *, cudaStream_t);
 int launch_tessellate_uniform(const planet_gpu_params *, int, int64_t, int64_t, Quad *, uint32_t *, cudaStream_t);
 int launch_quads_from_ids(const planet_gpu_params *, const uint64_t *, int64_t, Quad *, cudaStream_t);
@@ -260,17 +262,23 @@ float planet_gpu_get_height_at(const double *p, int depth, int max_depth)
                  ? set_error(PLANET_E_INVALID, "max_depth == 0 divides by zero at main.cpp:827") : 0;
         if (!rc) rc = stage_stream();
         if (!rc) rc = grow(&g_stage.h_pinned, &g_stage.h_cap, 64, true);
-        if (!rc) rc = grow(&g_stage.d_in, &g_stage.d_in_cap, 64, false);
-        if (!rc) rc = grow(&g_stage.d_out, &g_stage.d_out_cap, 64, false);
         if (!rc) {
-            memcpy(g_stage.h_pinned, p, 24);
-            rc = check_cuda(cudaMemcpyAsync(g_stage.d_in, g_stage.h_pinned, 24, cudaMemcpyHostToDevice, g_stage.stream), "H2D point");
+            // fast lane: the point is a kernel argument, the height lands in pinned host memory
+            rc = launch_height_at_seam(prm, p, depth, max_depth, (float *)g_stage.h_pinned, g_stage.stream);
+            if (rc == PLANET_E_UNSUPPORTED) {                            // FAST params: batch of one
+                rc = grow(&g_stage.d_in, &g_stage.d_in_cap, 64, false);
+                if (!rc) rc = grow(&g_stage.d_out, &g_stage.d_out_cap, 64, false);
+                if (!rc) {
+                    memcpy((char *)g_stage.h_pinned + 32, p, 24);
+                    rc = check_cuda(cudaMemcpyAsync(g_stage.d_in, (char *)g_stage.h_pinned + 32, 24, cudaMemcpyHostToDevice, g_stage.stream), "H2D point");
+                }
+                if (!rc) rc = launch_heights_at(prm, (const double *)g_stage.d_in, 1, depth, max_depth,
+                                                (float *)g_stage.d_out, g_stage.stream);
+                if (!rc) rc = check_cuda(cudaMemcpyAsync(g_stage.h_pinned, g_stage.d_out, 4, cudaMemcpyDeviceToHost, g_stage.stream), "D2H height");
+            }
         }
-        if (!rc) rc = launch_heights_at(prm, (const double *)g_stage.d_in, 1, depth, max_depth,
-                                        (float *)g_stage.d_out, g_stage.stream);
-        if (!rc) rc = check_cuda(cudaMemcpyAsync((char *)g_stage.h_pinned + 32, g_stage.d_out, 4, cudaMemcpyDeviceToHost, g_stage.stream), "D2H height");
         if (!rc) rc = check_cuda(cudaStreamSynchronize(g_stage.stream), "sync");
-        if (!rc) memcpy(&result, (char *)g_stage.h_pinned + 32, 4);
+        if (!rc) memcpy(&result, g_stage.h_pinned, 4);
     }
     if (rc) fprintf(stderr, "[ERROR] planet_gpu_get_height_at: %s\n", t_error);
     return result;
@@ -359,7 +367,20 @@ void planet_gpu_generate_height_map(float *data, int dim, const void *quad, int 
     if (ensure_init()) {
         planet_gpu_params prm;
         { std::lock_guard<std::mutex> lock(g_mutex); prm = *legacy_params(); }
-        rc = planet_gpu_generate_height_maps_host(&prm, (const planet_gpu_quad *)quad, 1, dim, max_depth, data, nullptr);
+        rc = check_height_args(&prm, dim, max_depth);
+        if (!rc && (!data || !quad)) rc = set_error(PLANET_E_INVALID, "NULL buffer");
+        if (!rc) {
+            // fast lane: the quad is a kernel argument, the map lands in pinned host memory
+            std::lock_guard<std::mutex> lock(g_mutex);
+            const size_t bytes = (size_t)dim * dim * sizeof(float);
+            rc = stage_stream();
+            if (!rc) rc = grow(&g_stage.h_pinned, &g_stage.h_cap, bytes, true);
+            if (!rc) rc = launch_height_map_seam(&prm, (const Quad *)quad, dim, max_depth, (float *)g_stage.h_pinned, g_stage.stream);
+            if (!rc) rc = check_cuda(cudaStreamSynchronize(g_stage.stream), "sync");
+            if (!rc) memcpy(data, g_stage.h_pinned, bytes);
+        }
+        if (rc == PLANET_E_UNSUPPORTED)                                  // FAST params or a huge map: batch of one
+            rc = planet_gpu_generate_height_maps_host(&prm, (const planet_gpu_quad *)quad, 1, dim, max_depth, data, nullptr);
     }
     if (rc) {
         fprintf(stderr, "[ERROR] planet_gpu_generate_height_map: %s\n", t_error);
