@@ -1,5 +1,7 @@
 """BASELINE.json configs[3]: the full planet at ~1 B vertices (depth 8, patch 50 -> 52 x 52 maps,
 fBm 12 octaves) sharded by patch range over the ranks of one box.
+PLANET_DEPTH=7 PLANET_PATCH=30 PLANET_OCTAVES=8 gives configs[2] (100 M vertices) as a fixed total
+split over the ranks, i.e. its strong-scaling form.
 
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/c4_run.py
 
@@ -18,7 +20,7 @@ torch.cuda.set_device(local); pb.init(local)
 dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
-DEPTH, PATCH, OCT = 8, 50, 12
+DEPTH, PATCH, OCT = (int(os.environ.get(k, d)) for k, d in (("PLANET_DEPTH", 8), ("PLANET_PATCH", 50), ("PLANET_OCTAVES", 12)))
 DIM = PATCH + 2
 total_quads = 6 * 4 ** DEPTH
 lo, hi = shard_range(total_quads, rank, world)
@@ -51,7 +53,7 @@ if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
 finite = bool(torch.isfinite(heights).all()) and bool(torch.isfinite(nrm).all())
 if rank == 0:
     verts = total_quads * DIM * DIM
-    print(json.dumps({"config": "C4 full planet depth 8, patch 50 (52x52 maps), fBm 12 octaves", "n_gpus": world,
+    print(json.dumps({"config": f"full planet depth {DEPTH}, patch {PATCH} ({DIM}x{DIM} maps), fBm {OCT} octaves", "n_gpus": world,
                       "quads": total_quads, "vertices": verts, "ms_per_step_max_over_ranks": float(t[0]),
                       "gvert_s": verts / float(t[0]) / 1e6, "hbm_gib_per_gpu": float(t[1]),
                       "bytes_per_vertex_resident": 4 + 32 * nv / (DIM * DIM) + 4 * ni / (DIM * DIM), "finite": finite}))
