@@ -30,8 +30,8 @@
 //    octave-sample buy 16 fewer instructions than byte codes decoded by AND/PRMT/shift
 //    (tools/microbench3.cu).  Measured cost model of this kernel: an SM sub-partition spends one
 //    cycle per instruction plus one per shared-memory wavefront of its own loads.
-//  * 768-thread CTAs, one per SM (160 KB of tables), persistent; warps take 128-sample tiles
-//    round-robin; each thread owns 2 consecutive texels whose two independent dependency chains
+//  * 768-thread CTAs, one per SM (160 KB of tables), persistent; every warp owns a contiguous
+//    run of 128-sample tiles; each thread owns 2 consecutive texels whose two independent dependency chains
 //    interleave in the instruction stream.  Plain FP32 FMA: the packed f32x2 forms
 //    (FFMA2/FMUL2/FADD2) hold the issue port for two cycles (tools/microbench2.cu), so they save
 //    no issue time and would need register-pair moves here.  96 instructions per octave-sample.
@@ -590,25 +590,30 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
     const double div = 1.0 / (double)(dim - 3);
     const double s = cfg.coord_scale * FIX_ONE;
 
-    // warp tiles are dealt round-robin over all warps of the grid (neighbouring warps write
-    // neighbouring segments); (q_first, r_base) = divmod(tile start, dim2) is advanced
-    // incrementally so the only 64-bit divisions happen once, here
-    const int64_t wstride = (int64_t)gridDim.x * WARPS;
-    int64_t wt = (int64_t)blockIdx.x * WARPS + warp;
+    // Every warp of the grid owns one contiguous run of warp tiles, so consecutive tiles mostly
+    // stay inside one quad (8 tiles per 32 x 32 map) and its coefficients are built once;
+    // (q_first, r_base) = divmod(tile start, dim2) is advanced incrementally, so the only 64-bit
+    // divisions happen once, here
+    const int64_t nwarps = (int64_t)gridDim.x * WARPS;
+    const int64_t per_warp = (nwtiles + nwarps - 1) / nwarps;
+    int64_t wt = ((int64_t)blockIdx.x * WARPS + warp) * per_warp;
+    const int64_t wt_end = min(nwtiles, wt + per_warp);
     int64_t q_first = (wt * WTILE) / dim2;
     uint32_t r_base = (uint32_t)(wt * WTILE - q_first * dim2);
-    const int64_t step_q = (wstride * WTILE) / dim2;
-    const uint32_t step_r = (uint32_t)(wstride * WTILE - step_q * dim2);
+    int64_t q_built = -1;                                            // quad whose coefficients sit in tq[0]
 
-    for (; wt < nwtiles; wt += wstride) {
+    for (; wt < wt_end; wt++) {
         const int64_t base = wt * WTILE;
         const int n_here = (int)min((int64_t)WTILE, total - base);           // samples in this warp tile
         const uint32_t r_end = r_base + (uint32_t)n_here - 1;
         const int nq = (int)(small_maps ? div_magic(r_end, magic_dim2) : (uint32_t)(r_end >= dim2)) + 1;
 
-        // prologue: quad -> per-axis bilinear coefficients (main.cpp:130-146 regrouped)
+        // prologue: quad -> per-axis bilinear coefficients (main.cpp:130-146 regrouped); skipped when
+        // the tile lies in the one quad the previous tile left in tq[0]
+        const bool have = nq == 1 && q_first == q_built;                     // warp-uniform
+        q_built = nq == 1 ? q_first : -1;
         __syncwarp();
-        if (lane < nq * 3) {
+        if (!have && lane < nq * 3) {
             const int qi = lane / 3, axis = lane - qi * 3;
             const double *qp = reinterpret_cast<const double *>(quads + q_first + qi);
             double p0 = qp[axis], p1 = qp[3 + axis], p2 = qp[6 + axis], p3 = qp[9 + axis];
@@ -746,8 +751,9 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
             store(sub, value);
         }
 
-        q_first += step_q; r_base += step_r;
-        if (r_base >= dim2) { r_base -= dim2; q_first++; }
+        r_base += WTILE;                                                     // the next tile of this warp
+        if (small_maps) { const uint32_t dq = div_magic(r_base, magic_dim2); q_first += dq; r_base -= dq * dim2; }
+        else if (r_base >= dim2) { r_base -= dim2; q_first++; }
     }
 }
 
