@@ -333,8 +333,9 @@ def run_ours(args, rank, local_rank, world):
             "roofline": {"kernel": "k_height_maps_fast<768,32>", "bound": "fp32", "achieved": k2_tf, "peak": fp32_tf,
                          "unit": "TFLOP/s", "frac": k2_tf / fp32_tf,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
-                         # (profiles/r01j_ncu_summary_final.txt: 1.74 MB read + 15.65 MB written): the 67 MB of heights mostly stay in the 126 MB L2
-                         "traffic": 17391616,
+                         # (profiles/r01y_ncu_summary_final.txt: 1.74 MB read + 9.46 MB written): the 67 MB of
+                         # heights are still dirty in the 126 MB L2 when the kernel ends
+                         "traffic": 11205376,
                          "peak_source": "FFMA probe measured in this run", "nominal_peak": nominal_tf,
                          "frac_of_nominal": k2_tf / nominal_tf, "flop_per_vertex": FLOP_PER_VERTEX,
                          "vertices_per_s": VERTS_PER_GPU / (ms_k2 * 1e-3)},
