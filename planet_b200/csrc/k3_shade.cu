@@ -17,10 +17,11 @@
 //      per quad instead of 2 per vertex), together with q.p - p.p, xyscale (main.cpp:361)
 //      and the column-constant terms of the third interpolate (acos, tan, 1/sin); q is
 //      stored as deltas from p so the linear branch costs 6 FMAs.  Column data is kept
-//      in shared memory as struct-of-arrays so a warp reading 32 columns hits 32 banks;
-//   C. one warp owns one quad and walks its rows (n+2 vertices incl. the two skirt vertices;
-//      32 lanes for the reference's n = 30): lane = column, so height taps and column data
-//      are conflict-free and each float4 store instruction writes 512 contiguous bytes.
+//      in shared memory as 80-byte records read with four LDS.128 (the stride puts the 8
+//      records of a quarter-warp in 8 distinct bank groups);
+//   C. one warp owns one quad and walks its vertex slots 32 at a time (for the reference's
+//      n = 30 a step is one row incl. the two skirt vertices): height taps are consecutive
+//      words and each float4 store instruction writes 512 contiguous bytes.
 //      Warps never synchronise with each other, so A/B of one warp hide behind C of others.
 // Normalisations use rsqrt (MUFU) + multiplies instead of the shader's sqrt + divide; the
 // difference (<= 2 ulp) is far inside the 1e-4 rad parity bound.
