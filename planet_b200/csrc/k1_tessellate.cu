@@ -12,9 +12,10 @@
 // <= 27 levels of 5 normalisations) with the reference's exact fp64 operation order
 // (IEEE add/mul/div/sqrt, no FMA) -- corners come out bit-identical, and shared edges of
 // neighbouring quads stay bit-identical too because both sides compute Normalize(a+b).
-// The strip index buffer is produced in closed form per output slot (the reference's
-// loop has asymmetric cursor resets), one coalesced 4-byte store per
-// thread, rebased per quad so that all patches index one merged vertex buffer.
+// The strip index buffer has a closed form per output slot (the reference's loop has
+// asymmetric cursor resets); the strip of one patch is kept in device memory,
+// held in registers by the index-stream CTAs and written with 16-byte stores, rebased per
+// quad so that all patches index one merged vertex buffer.
 #include "planet_common.cuh"
 
 #include <algorithm>
@@ -158,10 +159,11 @@ __host__ __device__ inline uint32_t strip_index(int k, int n)
     return (k & 1) ? (uint32_t)(v1e + x) : (uint32_t)(v0e + 1 + x);
 }
 
-// merged index buffer: out[q*ni + k] = q*nv + strip[k].  The strip is staged once per CTA
-// in shared memory; a CTA then walks whole quads, each thread streaming VEC consecutive
-// indices per store (16 bytes when ni % 4 == 0, i.e. even patch_verts; else 8 bytes -- ni is
-// always even), so the index part is a pure coalesced HBM write with ~3 instructions per index.
+// merged index buffer: out[q*ni + k] = q*nv + strip[k].  Each thread keeps its slots of the
+// strip in registers (shared memory for patches too large for that); a CTA then walks whole
+// quads, each thread streaming VEC consecutive indices per store (16 bytes when ni % 4 == 0,
+// i.e. even patch_verts; else 8 bytes -- ni is always even), so the index part is a pure
+// coalesced HBM write: address arithmetic + stores.
 // K1 as ONE launch: the first `quad_blocks` CTAs walk QuadIDs to corners (latency-bound fp64
 // chains, few warps), all other CTAs stream the merged index buffer (bandwidth-bound).  The two
 // outputs are independent, so running them side by side hides the corner chains completely.
