@@ -92,6 +92,7 @@ class PortOracle:
             "orc_patch_vertices": (None, [i, vp]), "orc_patch_indices": (None, [i, vp]),
             "orc_max_lod": (i, [d, i]), "orc_max_skirt_size": (f, [d, i]),
             "orc_skirt_size_for_quad": (f, [f, u64]),
+            "orc_quad_uniforms": (None, [vp, vp, vp]),
             "orc_shade_patches": (None, [vp, l, vp, vp, i, f, vp, vp]),
             "orc_shade_patches_rect": (None, [vp, l, vp, vp, vp, vp, i, f, vp, vp]),
             "orc_perlin_tables": (None, [vp, vp]),
@@ -171,6 +172,15 @@ class PortOracle:
     def max_lod(self, radius=RADIUS, n=30): return self.L.orc_max_lod(radius, n)
     def max_skirt_size(self, radius=RADIUS, n=30): return self.L.orc_max_skirt_size(radius, n)
     def skirt_size_for_quad(self, max_skirt, qid): return self.L.orc_skirt_size_for_quad(max_skirt, int(qid))
+
+    def quad_uniforms(self, quads, cam_pos):
+        """P[4], N[4] of every quad's draw (main.cpp:666-672) as float32[n, 24]."""
+        quads = np.ascontiguousarray(quads, QUAD_DTYPE)
+        cam = np.ascontiguousarray(cam_pos, np.float64)
+        out = np.empty((len(quads), 24), np.float32)
+        for k in range(len(quads)):
+            self.L.orc_quad_uniforms(_p(quads[k:k + 1]), _p(cam), _p(out[k]))
+        return out
 
     def shade_patches(self, quads, cam_pos, heights, n=30, max_skirt=None, radius=RADIUS):
         quads = np.ascontiguousarray(quads, QUAD_DTYPE)

@@ -572,17 +572,30 @@ static void glsl_vertex(const glsl_V c[4], const float *H, int dim, int n,
     nrm4[0] = N.x; nrm4[1] = N.y; nrm4[2] = N.z; nrm4[3] = sqrtf(light);
 }
 
+/* the per-quad uniforms of a draw, main.cpp:666-672: P[j] = float(q.p[j] - cam), N[j] =
+ * float(Normalize(q.p[j])).  PINNED: tests compare them bit for bit with the values the reference
+ * passes to glUniform (captured by oracle/ref_oracle.cpp's recording GL). */
+void orc_quad_uniforms(const orc_quad *q, const double *cam_pos, float *PN24)
+{
+    orc_vec3d cam = { cam_pos[0], cam_pos[1], cam_pos[2] };
+    for (int j = 0; j < 4; j++) {
+        orc_vec3d rel = v_sub(q->p[j], cam);
+        orc_vec3d nd = v_normalize(q->p[j]);
+        PN24[3 * j] = (float)rel.x; PN24[3 * j + 1] = (float)rel.y; PN24[3 * j + 2] = (float)rel.z;
+        PN24[12 + 3 * j] = (float)nd.x; PN24[12 + 3 * j + 1] = (float)nd.y; PN24[12 + 3 * j + 2] = (float)nd.z;
+    }
+}
+
 static void shade_patch(const orc_quad *q, const double *cam_pos, const float *heights,
                         int n, float skirt_size, const float *rect, float *pos4, float *nrm4)
 {
     int dim = n + 2, nv = orc_patch_vertex_count(n);
     glsl_V c[4];
-    for (int j = 0; j < 4; j++) {                              /* main.cpp:666-672 */
-        orc_vec3d cam = { cam_pos[0], cam_pos[1], cam_pos[2] };
-        orc_vec3d rel = v_sub(q->p[j], cam);
-        orc_vec3d nd = v_normalize(q->p[j]);
-        c[j].p.x = (float)rel.x; c[j].p.y = (float)rel.y; c[j].p.z = (float)rel.z;
-        c[j].n.x = (float)nd.x;  c[j].n.y = (float)nd.y;  c[j].n.z = (float)nd.z;
+    float PN[24];
+    orc_quad_uniforms(q, cam_pos, PN);
+    for (int j = 0; j < 4; j++) {
+        c[j].p.x = PN[3 * j]; c[j].p.y = PN[3 * j + 1]; c[j].p.z = PN[3 * j + 2];
+        c[j].n.x = PN[12 + 3 * j]; c[j].n.y = PN[12 + 3 * j + 1]; c[j].n.z = PN[12 + 3 * j + 2];
     }
     float *uv = (float *)malloc(sizeof(float) * 3 * nv);
     int *tex = (int *)malloc(sizeof(int) * 2 * nv);

@@ -18,7 +18,11 @@
  *            reference does this in a GLSL 1.40 vertex/fragment shader
  *            (main.cpp:282-382); there is no CPU implementation to execute and
  *            no GL driver here.  The restatement follows the shader text line
- *            by line in fp32 -- "parity unpinned" for that part.
+ *            by line in fp32 -- "parity unpinned" for that part.  Everything
+ *            the shader is FED is pinned: the vertex attributes (patch vertex
+ *            buffer), the per-quad uniforms P/N/SkirtSize (orc_quad_uniforms,
+ *            orc_skirt_size_for_quad) and the texture rects, each compared bit
+ *            for bit with what the reference hands to GL.
  */
 #ifndef PLANET_ORACLE_H
 #define PLANET_ORACLE_H
@@ -97,6 +101,9 @@ float orc_skirt_size_for_quad(float max_skirt, uint64_t id);   /* main.cpp:674-6
  *   pos4  = (v.p + v.n*height, height)   camera-relative position, w = height
  *   nrm4  = (Normal, sqrt(0.001 + max(0, dot(Normal, l))))  w = Lambert colour
  * `heights` is the quad's own dim x dim map, dim == n + 2. */
+/* per-quad draw uniforms P[4], N[4] (main.cpp:666-672) as 24 floats -- pinned against the
+ * reference's captured glUniform values */
+void orc_quad_uniforms(const orc_quad *q, const double *cam_pos, float *PN24);
 void orc_shade_patch(const orc_quad *q, const double *cam_pos, const float *heights,
                      int n, float skirt_size, float *pos4, float *nrm4);
 void orc_shade_patches(const orc_quad *quads, long nquads, const double *cam_pos,

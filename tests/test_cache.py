@@ -37,7 +37,7 @@ def reference_frames(ref):
                 owner[t] = int(q["id"])
         frames.append(dict(cam=cam, quads=quads, owners=np.array([owner[int(t)] for t in tex], np.uint64),
                            corners=draws[:, 25:29].copy(), pixel=draws[:, 29:31].copy(), generated=len(maps),
-                           maps=maps, tex=tex))
+                           maps=maps, tex=tex, pn=draws[:, 0:24].copy(), skirt=draws[:, 24].copy()))
     return frames
 
 
@@ -72,6 +72,18 @@ def test_plan_frame_makes_the_reference_decisions(frames):
         assert ((rects["flags"] == pb.TEXRECT_PARENT) == want_parent).all(), k
     assert cache.count == 1024
     cache.close()
+
+
+def test_draw_uniforms_of_the_glsl_stage_are_pinned(frames, port):
+    """The GLSL stage itself cannot be executed here, but everything it is fed can be pinned: the
+    per-quad uniforms P[4], N[4] and SkirtSize of the oracle (and of K3, which computes them the
+    same way) equal, bit for bit, what the reference passed to glUniform on a 30-frame flight."""
+    max_skirt = port.max_skirt_size()
+    for k, f in enumerate(frames):
+        got = port.quad_uniforms(f["quads"], f["cam"])
+        assert got.tobytes() == f["pn"].tobytes(), k
+        skirt = np.array([port.skirt_size_for_quad(max_skirt, q["id"]) for q in f["quads"]], np.float32)
+        assert skirt.tobytes() == f["skirt"].tobytes(), k
 
 
 def test_pool_exhaustion_is_an_error_not_a_corruption(frames):
