@@ -252,6 +252,7 @@ class RefOracle:
             "ref_captured_height_map_count": (l, []),
             "ref_captured_height_map": (i, [l, vp, vp, vp]),
             "ref_captured_draw_count": (l, []), "ref_captured_draw": (i, [l, vp]),
+            "ref_captured_shader_count": (l, []), "ref_captured_shader_source": (l, [l, vp, l]),
             "ref_captured_buffer_count": (l, []), "ref_captured_buffer": (l, [l, vp, l]),
         }
         for name, (res, args) in sig.items():
@@ -363,6 +364,16 @@ class RefOracle:
         """The reference's real main() for one headless frame (its local `Perlin` functor)."""
         rc = self.L.ref_run_reference_main(scratch_dir.encode())
         return rc, self.captured_height_maps(), self.captured_draws()
+
+    def captured_shaders(self):
+        """The GLSL texts InitPlanet handed to glShaderSource (vertex stage, fragment stage)."""
+        out = []
+        for k in range(self.L.ref_captured_shader_count()):
+            n = self.L.ref_captured_shader_source(k, None, 0)
+            buf = C.create_string_buffer(n + 1)
+            self.L.ref_captured_shader_source(k, buf, n + 1)
+            out.append(buf.value.decode())
+        return out
 
     def captured_height_maps(self):
         n = self.L.ref_captured_height_map_count()

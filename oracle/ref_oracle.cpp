@@ -54,6 +54,7 @@ static std::vector<HeightMap> height_maps;      /* index = texture id order */
 static std::vector<GLuint> height_map_ids;
 static std::vector<DrawRecord> draws;
 static std::vector<std::string> uniform_names;  /* location = index */
+static std::vector<std::string> shader_sources; /* one entry per glShaderSource call */
 static float uni_P[12], uni_N[12], uni_skirt, uni_corners[4], uni_pixel[2];
 static GLuint bound_texture = 0;
 static bool recording = true;
@@ -122,7 +123,15 @@ GLint glGetUniformLocation(GLuint, const GLchar *name)
 }
 void glLinkProgram(GLuint) {}
 void glPolygonMode(GLenum, GLenum) {}
-void glShaderSource(GLuint, GLsizei, const GLchar *const *, const GLint *) {}
+/* the shader text the reference hands to the driver (render.cpp:111): kept so that the tests can
+ * state exactly which text the CPU restatement of the GLSL stage was written against */
+void glShaderSource(GLuint, GLsizei count, const GLchar *const *strings, const GLint *lengths)
+{
+    std::string text;
+    for (GLsizei i = 0; i < count; i++)
+        text += lengths ? std::string(strings[i], (size_t)lengths[i]) : std::string(strings[i]);
+    fakegl::shader_sources.push_back(text);
+}
 void glTexImage2D(GLenum, GLint, GLint, GLsizei w, GLsizei h, GLint, GLenum, GLenum, const void *data)
 {
     if (!fakegl::recording) return;
@@ -411,6 +420,20 @@ int ref_captured_height_map(long i, float *out, int *w, int *h)
     return 1;
 }
 long ref_captured_draw_count() { return (long)fakegl::draws.size(); }
+/* shader k as handed to glShaderSource by InitPlanet (0 = vertex stage, 1 = fragment stage);
+ * returns its length, copies at most cap-1 bytes */
+long ref_captured_shader_count() { return (long)fakegl::shader_sources.size(); }
+long ref_captured_shader_source(long k, char *buf, long cap)
+{
+    if (k < 0 || k >= (long)fakegl::shader_sources.size()) return -1;
+    const std::string &t = fakegl::shader_sources[(size_t)k];
+    if (buf && cap > 0) {
+        long n = std::min<long>((long)t.size(), cap - 1);
+        memcpy(buf, t.data(), (size_t)n);
+        buf[n] = 0;
+    }
+    return (long)t.size();
+}
 /* 32 floats per draw: P[12] N[12] skirt corners[4] pixel_size[2] count */
 int ref_captured_draw(long i, float *out32)
 {

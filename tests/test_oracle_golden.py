@@ -161,3 +161,35 @@ def test_shade_restatement_sanity(port, golden):
     # skirt vertices sit skirt_size lower than the edge vertex under them
     sk = port.skirt_size_for_quad(port.max_skirt_size(), quads["id"][2])
     assert np.isclose(pos[2, 30, 3], pos[2, 31, 3] - sk)
+
+
+def test_glsl_text_the_restatement_follows(ref):
+    """The shader cannot be executed here, so the restatement (oracle/planet_oracle.c: glsl_*) is a
+    transcription.  This states WHICH text it transcribes: the strings the reference hands to
+    glShaderSource (render.cpp:111), captured by the recording GL, hashed, and checked for the lines
+    whose arithmetic the restatement and K3 reproduce.  If the reference's shader changes, this fails."""
+    from oracle.bindings import fnv1a32
+    ref.render_frame(np.array([0.0, 0.0, -6371010.0]))       # InitPlanet compiles the shader
+    vs, fs = ref.captured_shaders()
+    assert (fnv1a32(vs.encode()), fnv1a32(fs.encode())) == (0x06e4320c, 0xd545d6af)
+    assert "#define VERTEX_SHADER 1" in vs and "#define FRAGMENT_SHADER 1" in fs
+    for line in ("if (1.0 - dot(v0.n, v1.n) < 0.001)",
+                 "vec3 n = normalize(mix(v0.n, v1.n, t));",
+                 "float theta2 = acos(dot(v0.n, v1.n));",
+                 "vec3 n = normalize(sin(k*theta2)*v0.n + sin(t*theta2)*v1.n);",
+                 "float gamma = theta - theta2*t;",
+                 "float x = 1.0 - tan(gamma)/tan_theta;",
+                 "float y = 1.0/sin(theta) - 1.0/(cos(gamma)*tan_theta);",
+                 "vec3 p = v0.p + x*v + y*n*length(v);",
+                 "return normalize(vec3(x0 - x1, 2.0*xyscale, y0 - y1));",
+                 "vec2 uv = mix(HeightMap_corners[0], HeightMap_corners[1], UV.xy);",
+                 "float height = sample_height(uv) - SkirtSize*UV.z;",
+                 "vec3 normal = compute_normal(uv, length(q.p - p.p) / 29.0);",
+                 "vec3 t = normalize(cross(n, q.p - p.p));",
+                 "vec3 bi = normalize(cross(t, n));",
+                 "Normal = normalize(mat3(t, n, bi) * normal);",
+                 "gl_Position = Projection * View * vec4(v.p + v.n*height, 1.0);",
+                 "vec3 l = normalize(vec3(0.0, 1.0, -1.0));",
+                 "float light = 0.001 + max(0.0, dot(n, l));",
+                 "FragColor = vec4(vec3(sqrt(light)), 1.0);"):
+        assert line in vs, line
