@@ -167,6 +167,8 @@ __host__ __device__ inline uint32_t strip_index(int k, int n)
 // K1 as ONE launch: the first `quad_blocks` CTAs walk QuadIDs to corners (latency-bound fp64
 // chains, few warps), all other CTAs stream the merged index buffer (bandwidth-bound).  The two
 // outputs are independent, so running them side by side hides the corner chains completely.
+// (forcing more resident CTAs with a register cap spills the fp64 corner chains and makes them the
+// long pole: 31 -> 41 us at a 40-register cap)
 template <int VEC>
 __global__ void __launch_bounds__(256)
 k_tessellate_fused(int depth, int64_t first, int64_t nquads, double radius, Quad *__restrict__ quads,
