@@ -315,6 +315,33 @@ def test_reference_shaped_calls_from_eight_host_threads(gpu, golden):
         assert want_h.setdefault(k, h) == h and np.isfinite(h)
 
 
+def test_seam_calls_fall_back_to_the_batched_path_when_the_fast_lane_does_not_apply(gpu, golden):
+    """FAST params, a map too large for the fast lane, and the ZERO functor through the two
+    reference-shaped calls: same results as the batched device API."""
+    import torch
+    quads = quads_from_bytes(golden["frame_quads"])
+    pt = np.array(quads[5]["p"][2])
+    try:
+        fast = gpu.default_params(precision=gpu.FAST)
+        gpu.set_params(fast)
+        got = gpu.generate_height_map(quads[40], 32, 18)
+        want = to_np(gpu.generate_height_maps(gpu.quads_to_device(quads[40:41]), 32, 18, fast))[0]
+        assert got.tobytes() == want.tobytes()
+        h = gpu.get_height_at(pt, 0, 1)
+        want_h = to_np(gpu.heights_at(dev_points(gpu, pt[None, :]), 0, 1, fast))[0]
+        assert np.float32(h).tobytes() == np.float32(want_h).tobytes()
+        exact = gpu.default_params()
+        gpu.set_params(exact)
+        big = gpu.generate_height_map(quads[3], 2304, 18)          # > 2048: batch of one through the host path
+        want_big = to_np(gpu.generate_height_maps(gpu.quads_to_device(quads[3:4]), 2304, 18, exact))[0]
+        assert big.tobytes() == want_big.tobytes()
+        gpu.set_params(gpu.default_params(noise_kind=gpu.ZERO))
+        assert not gpu.generate_height_map(quads[0], 32, 18).any()
+        assert gpu.get_height_at(pt, 0, 1) == 0.0
+    finally:
+        gpu.set_params(gpu.default_params())
+
+
 def test_host_batch_path_equals_device_path(gpu, golden):
     quads = quads_from_bytes(golden["frame_quads"])
     p = gpu.default_params(precision=gpu.FAST)
