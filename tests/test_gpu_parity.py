@@ -342,6 +342,23 @@ def test_seam_calls_fall_back_to_the_batched_path_when_the_fast_lane_does_not_ap
         gpu.set_params(gpu.default_params())
 
 
+def test_shutdown_releases_and_the_library_comes_back(gpu, golden):
+    """planet_gpu_shutdown frees the staging buffers, the LOD scratch and the cached strip; the next
+    call re-initialises lazily and every path that owned one of them still gives the same bytes."""
+    quads = quads_from_bytes(golden["frame_quads"])
+    gpu.set_params(gpu.default_params())
+    before = gpu.generate_height_map(quads[7], 32, 18)
+    _, idx_before = gpu.tessellate_uniform(2, first=0, nquads=5, with_indices=True)
+    lod_before = gpu.quads_to_host(gpu.select_lod((0.0, 0.0, -6371010.0), 18, gpu.default_params()))
+    gpu.lib().planet_gpu_shutdown()
+    gpu.set_params(gpu.default_params())
+    assert gpu.generate_height_map(quads[7], 32, 18).tobytes() == before.tobytes()
+    _, idx_after = gpu.tessellate_uniform(2, first=0, nquads=5, with_indices=True)
+    assert to_np(idx_after).tobytes() == to_np(idx_before).tobytes()
+    lod_after = gpu.quads_to_host(gpu.select_lod((0.0, 0.0, -6371010.0), 18, gpu.default_params()))
+    assert lod_after.tobytes() == lod_before.tobytes()
+
+
 def test_host_batch_path_equals_device_path(gpu, golden):
     quads = quads_from_bytes(golden["frame_quads"])
     p = gpu.default_params(precision=gpu.FAST)
