@@ -359,6 +359,26 @@ def test_shutdown_releases_and_the_library_comes_back(gpu, golden):
     assert lod_after.tobytes() == lod_before.tobytes()
 
 
+def test_large_maps_dim_1024_and_4096(gpu, golden):
+    """C5-sized single patches: the reference's own dim-1024 probe (first leaf of the
+    default frame, default ridged functor, FNV-1a 0x57fc9fba) through both EXACT kernels, and FAST
+    against EXACT at 1024^2 and 4096^2."""
+    from oracle.bindings import fnv1a32
+    quads = quads_from_bytes(golden["frame_quads"])
+    dq = gpu.quads_to_device(quads[:2])
+    exact, fast = gpu.default_params(), gpu.default_params(precision=gpu.FAST)
+    one = to_np(gpu.generate_height_maps(dq[:1], 1024, 18, exact))            # 2^20 samples: small-batch kernel
+    assert fnv1a32(one) == int(golden["ridged_leaf0_dim1024_fnv"])
+    two = to_np(gpu.generate_height_maps(dq, 1024, 18, exact))                # 2^21 samples: table kernel
+    assert two[0].tobytes() == one[0].tobytes()
+    tol = REL_TOL * 8848.0 * amp_sum(0.55, 6)
+    f1 = to_np(gpu.generate_height_maps(dq, 1024, 18, fast))
+    assert np.abs(f1.astype(np.float64) - two).max() <= tol
+    e4 = gpu.generate_height_maps(dq[:1], 4096, 18, exact)
+    f4 = gpu.generate_height_maps(dq[:1], 4096, 18, fast)
+    assert bool((e4.double() - f4.double()).abs().max() <= tol)
+
+
 def test_host_batch_path_equals_device_path(gpu, golden):
     quads = quads_from_bytes(golden["frame_quads"])
     p = gpu.default_params(precision=gpu.FAST)
