@@ -379,6 +379,36 @@ def test_large_maps_dim_1024_and_4096(gpu, golden):
     assert bool((e4.double() - f4.double()).abs().max() <= tol)
 
 
+def test_batched_api_from_four_threads_on_four_streams(gpu):
+    """The batched entry points are stream-ordered and re-entrant: four host threads, each on its
+    own CUDA stream, run K1 + K2 + K3 on different quad ranges and get the single-threaded bytes."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    p = gpu.fbm_params(octaves=8, gain=0.5, precision=gpu.FAST)
+    cam = (0.0, 0.0, -6371010.0)
+
+    def run(k, stream=None):
+        ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream())
+        with ctx:
+            quads, idx = gpu.tessellate_uniform(6, first=1000 * k, nquads=700 + 100 * k, params=p, with_indices=True, stream=stream)
+            maps = gpu.generate_height_maps(quads, 32, 18, p, stream=stream)
+            pos, nrm = gpu.shade(quads, maps, cam, p, stream=stream)
+            if stream is not None:
+                stream.synchronize()
+            else:
+                torch.cuda.synchronize()
+            return [t.cpu() for t in (quads, idx, maps, pos, nrm)]
+
+    want = [run(k) for k in range(4)]
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    for _ in range(3):
+        with ThreadPoolExecutor(max_workers=4) as pool:
+            got = list(pool.map(lambda k: run(k, streams[k]), range(4)))
+        for g, w in zip(got, want):
+            for a, b in zip(g, w):
+                assert torch.equal(a, b)
+
+
 def test_host_batch_path_equals_device_path(gpu, golden):
     quads = quads_from_bytes(golden["frame_quads"])
     p = gpu.default_params(precision=gpu.FAST)
