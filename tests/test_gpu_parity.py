@@ -409,6 +409,50 @@ def test_batched_api_from_four_threads_on_four_streams(gpu):
                 assert torch.equal(a, b)
 
 
+def test_the_step_can_be_captured_in_a_cuda_graph(gpu):
+    """K1 + K2 + K3 make no host synchronisation and no allocation of their own, so a frame-sized
+    step captures into a CUDA graph (the way to take the launch latency out of small frames) and
+    replays to the same bytes -- also when K1 meets a patch size whose strip it has not cached yet
+    (it then evaluates the closed form in the kernel instead of uploading during capture)."""
+    import torch
+    cam = (0.0, 0.0, -6371010.0)
+    for patch in (30, 22):                                         # 22: strip not cached before the capture
+        p = gpu.fbm_params(octaves=8, gain=0.5, precision=gpu.FAST, patch_verts=patch)
+        dim, nq = patch + 2, 117
+        nv, ni = gpu.patch_vertex_count(patch), gpu.patch_index_count(patch)
+        quads = torch.empty((nq, 13), dtype=torch.int64, device="cuda")
+        idx = torch.empty(nq * ni, dtype=torch.int32, device="cuda")
+        maps = torch.empty((nq, dim, dim), dtype=torch.float32, device="cuda")
+        pos = torch.empty((nq, nv, 4), dtype=torch.float32, device="cuda")
+        nrm = torch.empty_like(pos)
+        L, C = gpu.lib(), gpu.C
+
+        def step(stream):
+            sp = C.c_void_p(stream.cuda_stream)
+            gpu._check(L.planet_gpu_tessellate_uniform(C.byref(p), 5, 300, nq, quads.data_ptr(), idx.data_ptr(), sp))
+            gpu._check(L.planet_gpu_generate_height_maps(C.byref(p), quads.data_ptr(), nq, dim, 18, maps.data_ptr(), sp))
+            camv = (C.c_double * 3)(*cam)
+            gpu._check(L.planet_gpu_shade(C.byref(p), quads.data_ptr(), nq, camv, maps.data_ptr(), -1.0,
+                                          pos.data_ptr(), nrm.data_ptr(), sp))
+
+        if patch == 30:
+            step(torch.cuda.current_stream())                      # warm: function attributes, strip cache
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step(torch.cuda.current_stream())
+        for t in (quads, idx, maps, pos, nrm):
+            t.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        got = [t.clone() for t in (quads, idx, maps, pos, nrm)]
+        step(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        for a, b in zip(got, (quads, idx, maps, pos, nrm)):
+            assert torch.equal(a, b)
+        assert bool(maps.abs().max() > 0)
+
+
 def test_host_batch_path_equals_device_path(gpu, golden):
     quads = quads_from_bytes(golden["frame_quads"])
     p = gpu.default_params(precision=gpu.FAST)
