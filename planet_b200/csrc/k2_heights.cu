@@ -185,6 +185,9 @@ k_noise_exact(const double *__restrict__ xyz, int64_t n, int kind, double lacuna
 // =====================================================================================
 namespace fast {
 
+#ifndef PLANET_K2_ALIGN
+#define PLANET_K2_ALIGN 1
+#endif
 #ifndef PLANET_K2_UNROLL
 #define PLANET_K2_UNROLL 1
 #endif
@@ -226,8 +229,20 @@ struct TileQuad { AxisCoef ax[3]; int octaves; int wide; };
 template <int REPL> constexpr int smem_bytes(int nthreads)
 {
     // tables + per-warp quad scratch (never less than the 2 KB the table build stages through)
-    return Layout<REPL>::TABLES + ((nthreads / 32) * (128 / 16 + 2) * (int)sizeof(TileQuad) > 2048
-                                       ? (nthreads / 32) * (128 / 16 + 2) * (int)sizeof(TileQuad) : 2048);
+    // + up to one P1 of slack in front: the tables start on a multiple of P1's size (tables_at)
+    return (PLANET_K2_ALIGN ? Layout<REPL>::P1_BYTES : 0) + Layout<REPL>::TABLES +
+           ((nthreads / 32) * (128 / 16 + 2) * (int)sizeof(TileQuad) > 2048
+                ? (nthreads / 32) * (128 / 16 + 2) * (int)sizeof(TileQuad) : 2048);
+}
+// Start of the tables inside the dynamic shared array: the first address whose shared-window
+// address is a multiple of P1's size.  A level-1 address is then (absolute P1 address of the
+// lane's copy) | (cell offset) -- the same LOP3 that merges the lane offset -- and the load
+// needs no base register added (one instruction per octave-sample in an issue-bound loop).
+template <int REPL> __device__ __forceinline__ unsigned char *tables_at(unsigned char *smem)
+{
+    if (!PLANET_K2_ALIGN) return smem;
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem);
+    return smem + ((0u - base) & (uint32_t)(Layout<REPL>::P1_BYTES - 1));
 }
 constexpr int SMEM_BYTES = smem_bytes<32>(768);
 
@@ -245,11 +260,21 @@ __device__ __forceinline__ uint4 lds_v4(const unsigned char *base, uint32_t off)
 // byte offsets of the lane's own copies inside a P1/P2 row and a T3 row.  Keeping the base uniform and the
 // lane part a 32-bit offset lets every lookup be LDS [R + UR + imm]: the lane offset is OR-ed
 // into the cell offset once per axis instead of being added to every address.
-struct LaneTab { const unsigned char *base; uint32_t lp, l3; };
-template <int REPL> __device__ __forceinline__ LaneTab lane_tab(const unsigned char *smem, int lane)
+struct LaneTab { const unsigned char *base; uint32_t lp, l3, l1abs; };
+template <int REPL> __device__ __forceinline__ LaneTab lane_tab(const unsigned char *tabs, int lane, uint32_t zero = 0)
 {
     using L = Layout<REPL>;
-    return { smem, (uint32_t)(lane % L::P_COPIES) * 8u, (uint32_t)(lane % L::T3_COPIES) * 16u };
+    const uint32_t lp = (uint32_t)(lane % L::P_COPIES) * 8u;
+    // `zero` is a run-time 0 the compiler cannot see through (one_bits ^ ONE_BITS): without it ptxas
+    // does not keep base | lp in a register but re-derives it with a second LOP3 at every use
+    return { tabs, lp, (uint32_t)(lane % L::T3_COPIES) * 16u, ((uint32_t)__cvta_generic_to_shared(tabs) | lp) ^ zero };
+}
+// level-1 read from an absolute shared-window address (tables_at)
+__device__ __forceinline__ uint2 lds_abs_v2(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
 }
 
 // A gradient vector of perlin.h:30-36 as three byte codes, one per component, each the TOP
@@ -303,6 +328,12 @@ __device__ __forceinline__ float corner(uint32_t gxw, uint32_t gyw, float X, flo
     return fmaf(__uint_as_float(gxw << 30), Z, fmaf(__uint_as_float(gyw), Y, __uint_as_float(gxw) * X));
 }
 
+// the same dot minus `a`, as one chain: (gx*X - a) + gy*Y + gz*Z
+__device__ __forceinline__ float corner_minus(uint32_t gxw, uint32_t gyw, float X, float Y, float Z, float a)
+{
+    return fmaf(__uint_as_float(gxw << 30), Z, fmaf(__uint_as_float(gyw), Y, fmaf(__uint_as_float(gxw), X, -a)));
+}
+
 __device__ __forceinline__ float fade1(float t)       // perlin.h:62 in fp32 + FMA
 {
     return (t * t * t) * fmaf(fmaf(t, 6.0f, -15.0f), t, 10.0f);
@@ -338,11 +369,11 @@ __device__ __forceinline__ Hashed hash_octave(const LaneTab &tab, const Fixed3 &
     h.my = splice_mantissa(wy, one_bits);
     h.mz = splice_mantissa(wz, one_bits);
     // (cell & 255) * row size, with the lane's copy offset OR-ed into the (zero) low bits
-    const uint32_t cx = ((wx >> (23 - L::LOGP)) & (255u << L::LOGP)) | tab.lp;
+    const uint32_t cx = ((wx >> (23 - L::LOGP)) & (255u << L::LOGP)) | (PLANET_K2_ALIGN ? tab.l1abs : tab.lp);   // absolute P1 address
     const uint32_t cy = ((wy >> (23 - L::LOGP)) & (255u << L::LOGP)) | tab.lp;
     const uint32_t cz = ((wz >> (23 - L::LOG3)) & (255u << L::LOG3)) | tab.l3;
     const unsigned char *t = tab.base;
-    const uint2 a = lds_v2(t, cx);                                  // R(ix), R(ix+1)
+    const uint2 a = PLANET_K2_ALIGN ? lds_abs_v2(cx) : lds_v2(t, cx);   // R(ix), R(ix+1)
     const uint2 b0 = lds_v2(t, a.x + cy + L::P2_AT);                // R(R(ix)+iy), R(R(ix)+iy+1)
     const uint2 b1 = lds_v2(t, a.y + cy + L::P2_AT);                // the same for ix+1
     h.e00 = lds_v4(t, b0.x + cz + L::T3_AT);                        // R(R(R(ix)+iy)+iz), ..+iz+1
@@ -352,25 +383,31 @@ __device__ __forceinline__ Hashed hash_octave(const LaneTab &tab, const Fixed3 &
     return h;
 }
 
-// 2 * PerlinNoise3 of octave k for one sample (perlin.h:50-88)
-template <int REPL>
-__device__ __forceinline__ float noise_octave(const LaneTab &tab, const Fixed3 &p, int k, uint32_t one_bits)
+// 2 * PerlinNoise3 from the hashed gradients and fractions of one sample (perlin.h:50-88).
+// The x+1 corner of each pair is formed as (its dot) - (the x corner's dot) in one FMA chain
+// seeded with the negated first dot, so the lerp along x is a single FMA: 7 instructions per
+// corner pair instead of 8.  (Also folding x - 1 into the chain start, gx*x - gx, and lerping
+// with 1 - u removes two more instructions per iteration and no time: measured, not kept.)
+__device__ __forceinline__ float noise_from(const Hashed &h)
 {
-    const Hashed h = hash_octave<REPL>(tab, p, k, one_bits);
     const float x0 = h.mx - 1.0f, x1 = h.mx - 2.0f;                 // fraction, fraction - 1 (exact)
     const float y0 = h.my - 1.0f, y1 = h.my - 2.0f;
     const float z0 = h.mz - 1.0f, z1 = h.mz - 2.0f;
-    const float g0 = corner(h.e00.x, h.e00.y, x0, y0, z0);          // perlin.h:68-75
-    const float g1 = corner(h.e10.x, h.e10.y, x1, y0, z0);
-    const float g2 = corner(h.e01.x, h.e01.y, x0, y1, z0);
-    const float g3 = corner(h.e11.x, h.e11.y, x1, y1, z0);
-    const float g4 = corner(h.e00.z, h.e00.w, x0, y0, z1);
-    const float g5 = corner(h.e10.z, h.e10.w, x1, y0, z1);
-    const float g6 = corner(h.e01.z, h.e01.w, x0, y1, z1);
-    const float g7 = corner(h.e11.z, h.e11.w, x1, y1, z1);
     const float u = fade1(x0), v = fade1(y0), w = fade1(z0);
-    const float l0 = lerp1(g0, g1, u), l1 = lerp1(g2, g3, u), l2 = lerp1(g4, g5, u), l3 = lerp1(g6, g7, u);
+    const float g0 = corner(h.e00.x, h.e00.y, x0, y0, z0);          // perlin.h:68-75
+    const float l0 = fmaf(corner_minus(h.e10.x, h.e10.y, x1, y0, z0, g0), u, g0);
+    const float g2 = corner(h.e01.x, h.e01.y, x0, y1, z0);
+    const float l1 = fmaf(corner_minus(h.e11.x, h.e11.y, x1, y1, z0, g2), u, g2);
+    const float g4 = corner(h.e00.z, h.e00.w, x0, y0, z1);
+    const float l2 = fmaf(corner_minus(h.e10.z, h.e10.w, x1, y0, z1, g4), u, g4);
+    const float g6 = corner(h.e01.z, h.e01.w, x0, y1, z1);
+    const float l3 = fmaf(corner_minus(h.e11.z, h.e11.w, x1, y1, z1, g6), u, g6);
     return lerp1(lerp1(l0, l1, v), lerp1(l2, l3, v), w);            // perlin.h:77-86
+}
+template <int REPL>
+__device__ __forceinline__ float noise_octave(const LaneTab &tab, const Fixed3 &p, int k, uint32_t one_bits)
+{
+    return noise_from(hash_octave<REPL>(tab, p, k, one_bits));
 }
 
 // fractal sum over octaves for the thread's two samples (main.cpp:689-734 with FMA); the two
@@ -387,6 +424,7 @@ __device__ __forceinline__ void fractal_loop(const LaneTab &tab, const Fixed3 (&
         float weight[N];
 #pragma unroll
         for (int s = 0; s < N; s++) weight[s] = 1.0f;
+#pragma unroll K2_UNROLL
         for (int k = 0; k < omax; k++) {
 #pragma unroll
             for (int s = 0; s < N; s++) {
@@ -508,8 +546,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 k_height_maps_exact_tab(const Quad *__restrict__ quads, int64_t total, int dim, HeightCfg cfg,
                         float *__restrict__ out, uint64_t magic_dim, PeerOut peers)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     using L = Layout<32>;
+    unsigned char *smem = tables_at<32>(smem_raw);
     build_tables<32>(smem);
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -572,8 +611,9 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
                    float *__restrict__ out, int64_t nwtiles, int out_aligned8,
                    uint64_t magic_dim, uint64_t magic_dim2, uint32_t one_bits, PeerOut peers)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     using L = Layout<REPL>;
+    unsigned char *smem = tables_at<REPL>(smem_raw);
     // the peer pointers wait in shared memory until the stores: held in registers across the
     // octave loop they cost it 14 rematerialised address adds
     __shared__ float *s_peer[7];
@@ -584,7 +624,7 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int WARPS = NTHREADS / 32;
     TileQuad *tq = reinterpret_cast<TileQuad *>(smem + L::TABLES) + warp * MAX_WTILE_QUADS;
-    const LaneTab tab = lane_tab<REPL>(smem, lane);
+    const LaneTab tab = lane_tab<REPL>(smem, lane, one_bits ^ ONE_BITS);
     const uint32_t dim2 = (uint32_t)dim * (uint32_t)dim;
     const bool small_maps = dim2 < (uint32_t)WTILE;          // a warp tile may then span > 2 quads
     const double div = 1.0 / (double)(dim - 3);
@@ -765,11 +805,12 @@ k_points_fast(const double *__restrict__ xyz, int64_t n, int kind, float gain, i
               double coord_scale, double sx, double sy, double sz, float height_scale,
               float *__restrict__ out, int64_t ntiles, uint32_t one_bits)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char *smem = tables_at<REPL>(smem_raw);
     build_tables<REPL>(smem);
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const LaneTab tab = lane_tab<REPL>(smem, lane);
+    const LaneTab tab = lane_tab<REPL>(smem, lane, one_bits ^ ONE_BITS);
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         // samples of one thread are strided by THREADS so the 24-byte point loads and the
@@ -939,7 +980,7 @@ int launch_height_maps_gathered(const planet_gpu_params *p, const Quad *d_quads,
         const uint64_t m1 = ((1ull << 40) + dim - 1) / dim;
         int grid = (int)std::min<int64_t>((total + NT - 1) / NT, sm_count());
         auto kern = peers.n > 0 ? fast::k_height_maps_exact_tab<NT, true> : fast::k_height_maps_exact_tab<NT, false>;
-        kern<<<grid, NT, fast::Layout<32>::TABLES + 2048, stream>>>(d_quads, total, dim, cfg, d_out, m1, peers);
+        kern<<<grid, NT, fast::smem_bytes<32>(0), stream>>>(d_quads, total, dim, cfg, d_out, m1, peers);
     } else {
         int64_t blocks = (total + 255) / 256;
         int grid = (int)std::min<int64_t>(blocks, (int64_t)sm_count() * 8);
