@@ -28,6 +28,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: with NCCL_DEBUG=VERSION/WARN in the environment NCCL prints
+# its version banner to stdout unless its log is pointed elsewhere
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 DEPTH, DIM, PATCH, OCTAVES, GAIN, MAX_LOD = 7, 32, 30, 8, 0.5, 18
 QUADS_PER_FACE = 4 ** DEPTH                      # 16 384

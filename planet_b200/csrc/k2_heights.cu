@@ -605,7 +605,9 @@ constexpr int MAX_WTILE_QUADS = WTILE / 16 + 2;          // dim >= 4
 
 // GATHER is a template flag, not a run-time test of peers.n: with the peer pointers live in the
 // plain kernel the octave loop grew by 14 address adds (register pressure), 6 % of the run time.
-template <int NTHREADS, int REPL, bool GATHER>
+// KIND is the noise kind as a template parameter (fBm or ridged; ZERO runs as fBm with no octaves):
+// the per-sub-tile dispatch on it was 3 % of the kernel's time in branches and reconvergence.
+template <int NTHREADS, int REPL, bool GATHER, int KIND>
 __global__ void __launch_bounds__(NTHREADS, REPL == 32 ? 1 : 2)
 k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, HeightCfg cfg,
                    float *__restrict__ out, int64_t nwtiles, int out_aligned8,
@@ -671,7 +673,7 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
             unsigned wide = __ballot_sync(__activemask(), span > 0.4 * FIX_WRAP);
             if (axis == 0) {
                 uint64_t id = reinterpret_cast<const uint64_t *>(qp)[12];
-                tq[qi].octaves = octaves_for(cfg.fixed_octaves, (int)quad_depth(id), cfg.max_depth);
+                tq[qi].octaves = cfg.kind == PLANET_NOISE_ZERO ? 0 : octaves_for(cfg.fixed_octaves, (int)quad_depth(id), cfg.max_depth);
                 tq[qi].wide = (wide >> lane) & 7u;                           // any of this quad's 3 axes
             }
         }
@@ -787,7 +789,9 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
             int oct[S];
             float value[S] = { 0.0f, 0.0f };
             positions(sub, p, oct);
-            if (cfg.kind != PLANET_NOISE_ZERO) fractal<REPL, S>(tab, p, oct, cfg.kind, cfg.gain, one_bits, value);
+            // regular tiles: both texels in one quad, so one octave count and no per-sample guard
+            if (regular) fractal_loop<REPL, S, false>(tab, p, oct, oct[0], KIND, cfg.gain, one_bits, value);
+            else fractal<REPL, S>(tab, p, oct, KIND, cfg.gain, one_bits, value);
             store(sub, value);
         }
 
@@ -889,18 +893,23 @@ static int64_t k2_small_max()
     return v;
 }
 
+// the twelve instantiations of the height-map kernel: (threads, table layout) x gather x kind
+template <int NT, int REPL> static const void *fast_kernel(bool gather, bool ridged)
+{
+    constexpr int F = PLANET_NOISE_FBM, R = PLANET_NOISE_RIDGED;
+    if (gather) return ridged ? (const void *)fast::k_height_maps_fast<NT, REPL, true, R> : (const void *)fast::k_height_maps_fast<NT, REPL, true, F>;
+    return ridged ? (const void *)fast::k_height_maps_fast<NT, REPL, false, R> : (const void *)fast::k_height_maps_fast<NT, REPL, false, F>;
+}
+
 static int prepare_fast()
 {
     const int dev = current_device();
     if (!g_fast_attr_set[dev]) {
-        PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_fast<512, 32, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
-        PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_fast<768, 32, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
-        PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_fast<512, 32, true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
-        PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_fast<768, 32, true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
+        for (int g = 0; g < 2; g++)
+            for (int r = 0; r < 2; r++) {
+                PLANET_CUDA(cudaFuncSetAttribute(fast_kernel<512, 32>(g, r), cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
+                PLANET_CUDA(cudaFuncSetAttribute(fast_kernel<768, 32>(g, r), cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
+            }
         PLANET_CUDA(cudaFuncSetAttribute(fast::k_points_fast<32>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, fast::SMEM_BYTES));
         PLANET_CUDA(cudaFuncSetAttribute(fast::k_height_maps_exact_tab<1024, false>,
@@ -958,20 +967,24 @@ int launch_height_maps_gathered(const planet_gpu_params *p, const Quad *d_quads,
         const uint64_t m1 = (one40 + dim - 1) / dim, m2 = (one40 + (uint64_t)dim * dim - 1) / ((uint64_t)dim * dim);
         int al = (reinterpret_cast<uintptr_t>(d_out) & 7) == 0;
         for (int r = 0; r < peers.n; r++) al = al && (reinterpret_cast<uintptr_t>(peers.ptr[r]) & 7) == 0;
-        const bool gather = peers.n > 0;
+        const bool gather = peers.n > 0, ridged = cfg.kind == PLANET_NOISE_RIDGED;
+        uint32_t one_bits = fast::ONE_BITS;
+        PeerOut peers_arg = peers;
+        void *args[] = { (void *)&d_quads, &total, &dim, &cfg, (void *)&d_out, &nwtiles, &al, (void *)&m1, (void *)&m2, &one_bits, &peers_arg };
+        auto launch_fast = [&](const void *kern, int grid, int threads, size_t smem, cudaStream_t st) -> int {
+            return check_cuda(cudaLaunchKernel(kern, dim3(grid), dim3(threads), args, smem, st), "height map kernel launch");
+        };
         if (total <= k2_small_max()) {
             // latency path: compact tables (6 KB), 256-thread CTAs spread over the whole chip
             int grid = (int)std::min<int64_t>((nwtiles + 7) / 8, (int64_t)sm_count() * 8);
-            auto kern = gather ? fast::k_height_maps_fast<256, 1, true> : fast::k_height_maps_fast<256, 1, false>;
-            kern<<<grid, 256, fast::smem_bytes<1>(256), stream>>>(d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2, fast::ONE_BITS, peers);
+            rc = launch_fast(fast_kernel<256, 1>(gather, ridged), grid, 256, fast::smem_bytes<1>(256), stream);
         } else {
             const int nt = k2_threads();
             int grid = (int)std::min<int64_t>((nwtiles + nt / 32 - 1) / (nt / 32), sm_count());
             const size_t sm = fast::smem_bytes<32>(nt);
-            auto kern = nt == 512 ? (gather ? fast::k_height_maps_fast<512, 32, true> : fast::k_height_maps_fast<512, 32, false>)
-                                  : (gather ? fast::k_height_maps_fast<768, 32, true> : fast::k_height_maps_fast<768, 32, false>);
-            kern<<<grid, nt, sm, stream>>>(d_quads, total, dim, cfg, d_out, nwtiles, al, m1, m2, fast::ONE_BITS, peers);
+            rc = launch_fast(nt == 512 ? fast_kernel<512, 32>(gather, ridged) : fast_kernel<768, 32>(gather, ridged), grid, nt, sm, stream);
         }
+        if (rc) return rc;
     } else if (total > k2_small_max() && dim <= 8192) {
         // EXACT arithmetic, large batch: same roundings on the replicated tables (1 CTA per SM)
         int rc = prepare_fast();
