@@ -644,7 +644,34 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
     uint32_t r_base = (uint32_t)(wt * WTILE - q_first * dim2);
     int64_t q_built = -1;                                            // quad whose coefficients sit in tq[0]
 
-    for (; wt < wt_end; wt++) {
+    // the lane's two texels of a sub-tile of a REGULAR tile (below): one quad, same row
+    auto positions_regular = [&](uint32_t r, Fixed3 *p) {
+        const uint32_t yy = div_magic(r, magic_dim), xx = r - yy * (uint32_t)dim;   // xx even: xx + 1 is on the same row
+        const TileQuad &c = tq[0];
+        const double xd = (double)((int)xx - 1), yd = (double)((int)yy - 1);
+        double P0[3], P1[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const double step = fma(c.ax[a].d, yd, c.ax[a].b);
+            P0[a] = fma(yd, c.ax[a].c, fma(step, xd, c.ax[a].a));
+            P1[a] = P0[a] + step;
+        }
+        to_fixed(P0[0], p[0].xlo, p[0].xhi); to_fixed(P0[1], p[0].ylo, p[0].yhi); to_fixed(P0[2], p[0].zlo, p[0].zhi);
+        to_fixed(P1[0], p[1].xlo, p[1].xhi); to_fixed(P1[1], p[1].ylo, p[1].yhi); to_fixed(P1[2], p[1].zlo, p[1].zhi);
+    };
+    // plain (write-back, evict-normal) store: the maps are K3's input and a C2 batch (67 MB)
+    // fits the 126 MB L2; a streaming store made K3 re-read them from HBM (K3 0.117 -> 0.100 ms)
+    auto store_pair = [&](int64_t o, const float *value) {
+        const float2 h2 = make_float2(value[0] * cfg.height_scale, value[1] * cfg.height_scale);
+        *reinterpret_cast<float2 *>(out + o) = h2;
+        if constexpr (GATHER) {
+#pragma unroll
+            for (int r = 0; r < 7; r++)                              // NVLink peer stores (fused gather)
+                if (r < peers.n) __stcs(reinterpret_cast<float2 *>(((float *volatile *)s_peer)[r] + o), h2);
+        }
+    };
+
+    while (wt < wt_end) {
         const int64_t base = wt * WTILE;
         const int n_here = (int)min((int64_t)WTILE, total - base);           // samples in this warp tile
         const uint32_t r_end = r_base + (uint32_t)n_here - 1;
@@ -681,91 +708,83 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
 
         // Regular tiles -- a full tile inside one quad of even dim, not wide, 8-byte aligned output:
         // every tile of the 32 x 32 maps of the reference -- skip the ragged-edge bookkeeping
-        // (second texel on another row / quad, per-sample range reduction, partial tiles).
+        // (second texel on another row / quad, per-sample range reduction, partial tiles), and so
+        // do the full tiles that follow in the same quad: the whole run is walked here with no
+        // per-tile setup at all (15 % of the kernel's time was outside the octave loops).
         const bool regular = out_aligned8 && n_here == WTILE && nq == 1 && !(dim & 1) && tq[0].wide == 0;
+        if (regular) {
+            const int run = (int)min(wt_end - wt, (int64_t)((dim2 - r_base) / (uint32_t)WTILE));   // >= 1
+            const int octaves = tq[0].octaves;
+            uint32_t r = r_base + (uint32_t)(lane * S);
+            int64_t o = base + lane * S;                                     // even
+#pragma unroll 1
+            for (int t = 0; t < run * SUB; t++, r += 32 * S, o += 32 * S) {
+                Fixed3 p[S];
+                const int oct[S] = { octaves, octaves };
+                float value[S];
+                positions_regular(r, p);
+                fractal_loop<REPL, S, false>(tab, p, oct, octaves, KIND, cfg.gain, one_bits, value);
+                store_pair(o, value);
+            }
+            wt += run;
+            r_base += (uint32_t)run * WTILE;
+            if (r_base >= dim2) { r_base -= dim2; q_first++; }               // the run ended with the quad
+            continue;
+        }
 
         // the lane's two texels of sub-tile `sub`: fixed-point positions and octave counts
         auto positions = [&](int sub, Fixed3 *p, int *oct) {
             const int i0 = sub * (32 * S) + lane * S;                        // first sample of this lane
-            if (regular) {
-                const uint32_t r = r_base + (uint32_t)i0;
-                const uint32_t yy = div_magic(r, magic_dim), xx = r - yy * (uint32_t)dim;   // xx even: xx + 1 is on the same row
-                const TileQuad &c = tq[0];
-                const double xd = (double)((int)xx - 1), yd = (double)((int)yy - 1);
-                double P0[3], P1[3];
-#pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    const double step = fma(c.ax[a].d, yd, c.ax[a].b);
-                    P0[a] = fma(yd, c.ax[a].c, fma(step, xd, c.ax[a].a));
-                    P1[a] = P0[a] + step;
-                }
-                oct[0] = oct[1] = c.octaves;
-                to_fixed(P0[0], p[0].xlo, p[0].xhi); to_fixed(P0[1], p[0].ylo, p[0].yhi); to_fixed(P0[2], p[0].zlo, p[0].zhi);
-                to_fixed(P1[0], p[1].xlo, p[1].xhi); to_fixed(P1[1], p[1].ylo, p[1].yhi); to_fixed(P1[2], p[1].zlo, p[1].zhi);
-            } else {
-                // texel (q, y, x) of the lane's first sample; the second one follows by increment
-                uint32_t r = r_base + (uint32_t)min(i0, n_here - 1);
-                uint32_t q[S], y[S], x[S];
-                q[0] = small_maps ? div_magic(r, magic_dim2) : (uint32_t)(r >= dim2);
-                r -= q[0] * dim2;
-                y[0] = div_magic(r, magic_dim);
-                x[0] = r - y[0] * (uint32_t)dim;
-                q[1] = q[0]; y[1] = y[0]; x[1] = x[0];
-                if (i0 + 1 < n_here) {
-                    if (++x[1] == (uint32_t)dim) { x[1] = 0; if (++y[1] == (uint32_t)dim) { y[1] = 0; ++q[1]; } }
-                }
-                {
-                    // sample 0: P = A + B x + y (C + D x) per axis (coefficients pre-scaled by 2^55)
-                    const TileQuad &c = tq[q[0]];
-                    const double xd = (double)((int)x[0] - 1), yd = (double)((int)y[0] - 1);
-                    double P0[3], P1[3], step[3];
-#pragma unroll
-                    for (int a = 0; a < 3; a++) {
-                        step[a] = fma(c.ax[a].d, yd, c.ax[a].b);                 // dP/dx along this row
-                        P0[a] = fma(yd, c.ax[a].c, fma(step[a], xd, c.ax[a].a));
-                        P1[a] = P0[a] + step[a];                                 // the neighbour texel, same row
-                    }
-                    int wide = c.wide;
-                    oct[0] = oct[1] = c.octaves;
-                    // warp-uniform slow paths: the second texel starts a new row / quad (odd dim), or a
-                    // quad too wide for the per-quad reduction (then every sample is reduced on its own)
-                    if (__any_sync(0xffffffffu, (q[1] != q[0]) | (y[1] != y[0]))) {
-                        if (q[1] != q[0] || y[1] != y[0]) {
-                            const TileQuad &c1 = tq[q[1]];
-                            const double xd1 = (double)((int)x[1] - 1), yd1 = (double)((int)y[1] - 1);
-#pragma unroll
-                            for (int a = 0; a < 3; a++)
-                                P1[a] = fma(yd1, fma(c1.ax[a].d, xd1, c1.ax[a].c), fma(c1.ax[a].b, xd1, c1.ax[a].a));
-                            wide |= c1.wide;
-                            oct[1] = c1.octaves;
-                        }
-                    }
-                    if (__any_sync(0xffffffffu, wide)) {
-                        if (wide) {
-#pragma unroll
-                            for (int a = 0; a < 3; a++) { P0[a] = wrap_period(P0[a]); P1[a] = wrap_period(P1[a]); }
-                        }
-                    }
-                    to_fixed(P0[0], p[0].xlo, p[0].xhi); to_fixed(P0[1], p[0].ylo, p[0].yhi); to_fixed(P0[2], p[0].zlo, p[0].zhi);
-                    to_fixed(P1[0], p[1].xlo, p[1].xhi); to_fixed(P1[1], p[1].ylo, p[1].yhi); to_fixed(P1[2], p[1].zlo, p[1].zhi);
-                }
-
+            // texel (q, y, x) of the lane's first sample; the second one follows by increment
+            uint32_t r = r_base + (uint32_t)min(i0, n_here - 1);
+            uint32_t q[S], y[S], x[S];
+            q[0] = small_maps ? div_magic(r, magic_dim2) : (uint32_t)(r >= dim2);
+            r -= q[0] * dim2;
+            y[0] = div_magic(r, magic_dim);
+            x[0] = r - y[0] * (uint32_t)dim;
+            q[1] = q[0]; y[1] = y[0]; x[1] = x[0];
+            if (i0 + 1 < n_here) {
+                if (++x[1] == (uint32_t)dim) { x[1] = 0; if (++y[1] == (uint32_t)dim) { y[1] = 0; ++q[1]; } }
             }
-
+            // sample 0: P = A + B x + y (C + D x) per axis (coefficients pre-scaled by 2^55)
+            const TileQuad &c = tq[q[0]];
+            const double xd = (double)((int)x[0] - 1), yd = (double)((int)y[0] - 1);
+            double P0[3], P1[3], step[3];
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                step[a] = fma(c.ax[a].d, yd, c.ax[a].b);                     // dP/dx along this row
+                P0[a] = fma(yd, c.ax[a].c, fma(step[a], xd, c.ax[a].a));
+                P1[a] = P0[a] + step[a];                                     // the neighbour texel, same row
+            }
+            int wide = c.wide;
+            oct[0] = oct[1] = c.octaves;
+            // warp-uniform slow paths: the second texel starts a new row / quad (odd dim), or a
+            // quad too wide for the per-quad reduction (then every sample is reduced on its own)
+            if (__any_sync(0xffffffffu, (q[1] != q[0]) | (y[1] != y[0]))) {
+                if (q[1] != q[0] || y[1] != y[0]) {
+                    const TileQuad &c1 = tq[q[1]];
+                    const double xd1 = (double)((int)x[1] - 1), yd1 = (double)((int)y[1] - 1);
+#pragma unroll
+                    for (int a = 0; a < 3; a++)
+                        P1[a] = fma(yd1, fma(c1.ax[a].d, xd1, c1.ax[a].c), fma(c1.ax[a].b, xd1, c1.ax[a].a));
+                    wide |= c1.wide;
+                    oct[1] = c1.octaves;
+                }
+            }
+            if (__any_sync(0xffffffffu, wide)) {
+                if (wide) {
+#pragma unroll
+                    for (int a = 0; a < 3; a++) { P0[a] = wrap_period(P0[a]); P1[a] = wrap_period(P1[a]); }
+                }
+            }
+            to_fixed(P0[0], p[0].xlo, p[0].xhi); to_fixed(P0[1], p[0].ylo, p[0].yhi); to_fixed(P0[2], p[0].zlo, p[0].zhi);
+            to_fixed(P1[0], p[1].xlo, p[1].xhi); to_fixed(P1[1], p[1].ylo, p[1].yhi); to_fixed(P1[2], p[1].zlo, p[1].zhi);
         };
         auto store = [&](int sub, const float *value) {
             const int i0 = sub * (32 * S) + lane * S;
             const int64_t o = base + i0;                                     // even
-            if (regular || (out_aligned8 && i0 + 1 < n_here)) {
-                const float2 h2 = make_float2(value[0] * cfg.height_scale, value[1] * cfg.height_scale);
-                // plain (write-back, evict-normal) store: the maps are K3's input and a C2 batch (67 MB)
-                // fits the 126 MB L2; a streaming store made K3 re-read them from HBM (K3 0.117 -> 0.100 ms)
-                *reinterpret_cast<float2 *>(out + o) = h2;
-                if constexpr (GATHER) {
-#pragma unroll
-                    for (int r = 0; r < 7; r++)                              // NVLink peer stores (fused gather)
-                        if (r < peers.n) __stcs(reinterpret_cast<float2 *>(((float *volatile *)s_peer)[r] + o), h2);
-                }
+            if (out_aligned8 && i0 + 1 < n_here) {
+                store_pair(o, value);
             } else {
 #pragma unroll
                 for (int sidx = 0; sidx < S; sidx++)
@@ -789,12 +808,11 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
             int oct[S];
             float value[S] = { 0.0f, 0.0f };
             positions(sub, p, oct);
-            // regular tiles: both texels in one quad, so one octave count and no per-sample guard
-            if (regular) fractal_loop<REPL, S, false>(tab, p, oct, oct[0], KIND, cfg.gain, one_bits, value);
-            else fractal<REPL, S>(tab, p, oct, KIND, cfg.gain, one_bits, value);
+            fractal<REPL, S>(tab, p, oct, KIND, cfg.gain, one_bits, value);
             store(sub, value);
         }
 
+        wt++;
         r_base += WTILE;                                                     // the next tile of this warp
         if (small_maps) { const uint32_t dq = div_magic(r_base, magic_dim2); q_first += dq; r_base -= dq * dim2; }
         else if (r_base >= dim2) { r_base -= dim2; q_first++; }
