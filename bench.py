@@ -342,12 +342,12 @@ def run_ours(args, rank, local_rank, world):
                    "k2_heights_exact_mode": ms_k2_exact},
             "parity": {"fast_vs_exact_max_abs_m": fast_err, "tolerance_m": fast_tol,
                        "exact_mode_bytes_equal_reference_cpu": same_bytes},
-            "roofline": {"kernel": "k_height_maps_fast<768,32>", "bound": "fp32", "achieved": k2_tf, "peak": fp32_tf,
+            "roofline": {"kernel": "k_height_maps_fast<768,32,gather=0,kind=fBm>", "bound": "fp32", "achieved": k2_tf, "peak": fp32_tf,
                          "unit": "TFLOP/s", "frac": k2_tf / fp32_tf,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
-                         # (profiles/r01y_ncu_summary_final.txt: 1.74 MB read + 9.46 MB written): the 67 MB of
+                         # (profiles/r01zc_ncu_summary_k2.txt: 1.74 MB read + 9.52 MB written): the 67 MB of
                          # heights are still dirty in the 126 MB L2 when the kernel ends
-                         "traffic": 11205376,
+                         "traffic": 11262208,
                          "peak_source": "FFMA probe measured in this run", "nominal_peak": nominal_tf,
                          "frac_of_nominal": k2_tf / nominal_tf, "flop_per_vertex": FLOP_PER_VERTEX,
                          "vertices_per_s": VERTS_PER_GPU / (ms_k2 * 1e-3)},

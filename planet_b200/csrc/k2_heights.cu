@@ -29,12 +29,16 @@
 //    half / quarter warp at a time, hence 16 / 8 copies per row.  22 shared-memory wavefronts per
 //    octave-sample buy 16 fewer instructions than byte codes decoded by AND/PRMT/shift
 //    (tools/microbench3.cu).  Measured cost model of this kernel: an SM sub-partition spends one
-//    cycle per instruction plus one per shared-memory wavefront of its own loads.
+//    cycle per 32-bit register a warp instruction writes -- one per ordinary instruction, one per
+//    word a load returns (tools/microbench5.cu): a load costs what the arithmetic that could
+//    replace it would cost, and only fewer results make the loop faster.
 //  * 768-thread CTAs, one per SM (160 KB of tables), persistent; every warp owns a contiguous
 //    run of 128-sample tiles; each thread owns 2 consecutive texels whose two independent dependency chains
 //    interleave in the instruction stream.  Plain FP32 FMA: the packed f32x2 forms
 //    (FFMA2/FMUL2/FADD2) hold the issue port for two cycles (tools/microbench2.cu), so they save
-//    no issue time and would need register-pair moves here.  96 instructions per octave-sample.
+//    no issue time and would need register-pair moves here.  91 instructions per octave-sample.
+//  * Tiles that lie inside one quad (every tile of a 32 x 32 map) are walked as runs with no
+//    per-tile setup; the noise kind is a template parameter.
 //  * Per-tile prologue: one thread per touched quad turns the 104-byte Quad into the
 //    bilinear form P = A + B x + y (C + D x) per axis in doubles pre-scaled by 2^55
 //    (same sample points as main.cpp:132-146 up to 1 ulp of double), so a sample's

@@ -104,11 +104,13 @@ def test_vector_call_surface_on_the_host(tmp_path):
 
 
 def test_k2_octave_loop_has_not_grown():
-    """K2 is issue-bound, so its run time tracks the instruction count of the octave loop.  The
-    count is read from the built library with cuobjdump (no GPU): 192 instructions per two samples
-    for fBm, 201 for ridged, 198 / 206 for the two mixed-octave-count variants when this bound was
-    set.  A change that adds registers to the kernel (e.g. live pointers across the loop) or
-    defeats the uniform-base addressing of the table reads shows up here first."""
+    """K2 is bound by the registers its octave loop writes, so its run time tracks the instruction
+    count of that loop.  The count is read from the built library with cuobjdump (no GPU): 182
+    instructions per two samples for fBm, 191 for ridged, 188 / 199 for the mixed-octave-count
+    variants of the ragged-tile path when this bound was set (first float-table version: 192 /
+    201 / 198 / 206).  A change that adds registers to the kernel (e.g. live pointers across the
+    loop) or defeats the absolute / uniform-base addressing of the table reads shows up here
+    first."""
     import shutil
     import sys
     if shutil.which("cuobjdump") is None:
@@ -116,8 +118,10 @@ def test_k2_octave_loop_has_not_grown():
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     from sass_loops import octave_loops
     found = octave_loops()
-    assert len(found) == 2, sorted(found)                    # plain and fused-gather instantiations
+    assert len(found) == 4, sorted(found)                    # (plain, fused gather) x (fBm, ridged)
     for name, loops in found.items():
-        counts = sorted(n for n, _ in loops)
-        assert len(counts) == 4, (name, counts)
-        assert counts[0] <= 194 and counts[-1] <= 209, (name, counts)
+        fbm = "ELi1EEEv" in name                             # KIND = PLANET_NOISE_FBM
+        octave = sorted(n for n, _ in loops if n < 215)      # the run-of-tiles loop also lands in the window
+        assert len(octave) >= 3, (name, octave)
+        assert octave[0] <= (184 if fbm else 193), (name, octave)
+        assert octave[-1] <= (190 if fbm else 201), (name, octave)
