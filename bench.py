@@ -28,9 +28,15 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: with NCCL_DEBUG=VERSION/WARN in the environment NCCL prints
-# its version banner to stdout unless its log is pointed elsewhere
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line.  Libraries write there too (with NCCL_DEBUG=VERSION in the
+# environment NCCL prints its banner to stdout whatever NCCL_DEBUG_FILE says), so file descriptor 1
+# is pointed at stderr for the whole run and the JSON line goes to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 DEPTH, DIM, PATCH, OCTAVES, GAIN, MAX_LOD = 7, 32, 30, 8, 0.5, 18
 QUADS_PER_FACE = 4 ** DEPTH                      # 16 384
@@ -138,7 +144,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": "vertices/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "vertices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args, rank, local_rank, world):
@@ -384,7 +390,7 @@ def run_ours(args, rank, local_rank, world):
                           "while the kernel computes (planet_gpu_generate_height_maps_gathered) + one barrier",
                 "bytes_per_gpu": nq * DIM * DIM * 4, "identical_to_nccl_all_gather": gather_bad == 0.0,
                 "nccl": nccl_gather}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
