@@ -677,6 +677,24 @@ def test_k2_writes_exactly_its_output(gpu, port, dim, nq, octaves, offset, small
     assert np.abs(got.astype(np.float64) - want).max() <= REL_TOL * 8848.0 * amp_sum(0.5, octaves)
 
 
+@pytest.mark.parametrize("kind", ["fbm", "ridged"])
+@pytest.mark.parametrize("nq", [700, 2100])                                     # compact- and replicated-table kernels
+def test_k2_tile_paths_agree_bit_for_bit(gpu, kind, nq):
+    """A height is a function of (quad, x, y) only.  With an 8-byte aligned output every tile of a
+    32 x 32 map takes the run-of-regular-tiles path of K2; with the output one float off it, every
+    tile takes the ragged path (scalar stores, per-sample guards).  Same bits either way."""
+    import torch
+    p = gpu.fbm_params(8, 0.5, gpu.FAST) if kind == "fbm" else gpu.default_params(precision=gpu.FAST)
+    quads = gpu.tessellate_uniform(6, first=5, nquads=nq, params=p)
+    aligned = gpu.generate_height_maps(quads, 32, 18, p)
+    big, win = _window(torch, nq * 1024, torch.float32, pad=4100, offset_elems=1)
+    assert win.data_ptr() % 8 == 4
+    gpu.generate_height_maps(quads, 32, 18, p, out=win.view(nq, 32, 32))
+    torch.cuda.synchronize()
+    assert torch.equal(win.view(nq, 32, 32), aligned)
+    assert _intact(big, 4101, nq * 1024)
+
+
 @pytest.mark.parametrize("n,nq", [(30, 5), (5, 3), (31, 17), (50, 9), (12, 1)])
 def test_k1_k3_write_exactly_their_outputs(gpu, n, nq):
     import torch
