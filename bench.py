@@ -31,12 +31,19 @@ sys.path.insert(0, ROOT)
 # stdout carries exactly one JSON line.  Libraries write there too (with NCCL_DEBUG=VERSION in the
 # environment NCCL prints its banner to stdout whatever NCCL_DEBUG_FILE says), so file descriptor 1
 # is pointed at stderr for the whole run and the JSON line goes to the saved descriptor.
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
 
 
 def emit(line):
-    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    os.write(1 if _REAL_STDOUT is None else _REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 DEPTH, DIM, PATCH, OCTAVES, GAIN, MAX_LOD = 7, 32, 30, 8, 0.5, 18
 QUADS_PER_FACE = 4 ** DEPTH                      # 16 384
@@ -402,6 +409,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
