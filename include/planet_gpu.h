@@ -156,7 +156,7 @@ float planet_gpu_max_skirt_size(double radius, int patch_verts);   /* main.cpp:5
  * cam_pos (HOST pointer, 3 doubles), in the same order, with bit-identical corners and ids.
  * Split decisions evaluate GetHeightAt(p, 0, 1) in EXACT arithmetic whatever p->precision says.
  * d_quads (DEVICE) must hold `capacity` quads; *count (HOST) receives the number of leaves.
- * Synchronises `stream` once per quadtree level. */
+ * One cooperative launch walks all levels; `stream` is synchronised once, to read the leaf count. */
 int planet_gpu_select_lod(const planet_gpu_params *p, const double *cam_pos, int max_lod,
                           planet_gpu_quad *d_quads, int64_t capacity, int64_t *count, void *stream);
 
