@@ -358,9 +358,9 @@ def run_ours(args, rank, local_rank, world):
             "roofline": {"kernel": "k_height_maps_fast<768,32,gather=0,kind=fBm>", "bound": "fp32", "achieved": k2_tf, "peak": fp32_tf,
                          "unit": "TFLOP/s", "frac": k2_tf / fp32_tf,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
-                         # (profiles/r01zc_ncu_summary_k2.txt: 1.74 MB read + 9.52 MB written): the 67 MB of
+                         # (profiles/r01zf_ncu_summary_final.txt: 1.74 MB read + 12.81 MB written): the 67 MB of
                          # heights are still dirty in the 126 MB L2 when the kernel ends
-                         "traffic": 11262208,
+                         "traffic": 14550016,
                          "peak_source": "FFMA probe measured in this run", "nominal_peak": nominal_tf,
                          "frac_of_nominal": k2_tf / nominal_tf, "flop_per_vertex": FLOP_PER_VERTEX,
                          "vertices_per_s": VERTS_PER_GPU / (ms_k2 * 1e-3)},
