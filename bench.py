@@ -3,21 +3,27 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-A *step* is one pass of the hot path over one batch of synthetic quads, per GPU:
-    K1 tessellate  : 16 384 leaf quads of one cube-sphere face at depth 7 + merged strip indices
-    K2 heights     : 16 384 x 32^2 = 16 777 216 height samples, fBm 8 octaves (FAST arithmetic)
-    K3 shade       : 16 384 x 1 020 displaced positions + normals + Lambert term
-(BASELINE.json configs[1]; with N GPUs rank r takes face r -- configs[2] sharded by face --
-and faces 6, 7 reuse faces 0, 1 with a seed offset so every GPU always has one face of work:
-weak scaling, no data-path collective.  The NCCL gather of finished patches is timed separately
-and reported as `with_gather`.)
+A *step* is one pass of the hot path over one batch of synthetic quads:
+    K1 tessellate  : leaf quads of the uniform depth-7 tree + merged strip indices
+    K2 heights     : 32^2 height samples per quad, fBm 8 octaves (FAST arithmetic)
+    K3 shade       : 1 020 displaced positions + normals + Lambert term per quad
+    K4 gather      : (N > 1) every rank's finished height maps in one buffer on every rank
+
+N = 1 runs BASELINE.json configs[1] (C2): one cube-sphere face, 16 384 quads, 16.8 M vertices.
+N > 1 runs configs[2] (C3): the full planet, 6 faces = 98 304 quads = 100.7 M vertices as a FIXED
+total, rank r taking the patch range shard_range(98 304, r, N) -- strong scaling --
+and the timed step INCLUDES K4, fused into K2 (planet_gpu_gather_height_maps: finished tiles leave
+the SM as bulk copies to every peer over NVLink while the kernel computes; arrival is signalled
+GPU to GPU, no host barrier inside a step).  Compute without the gather and the plain NCCL
+collective are extra keys.
 
 `value` counts height-map vertices (32^2 per quad, border included -- SURVEY.md 8d) per second
 with inputs resident in HBM; `e2e` is the same metric through the reference-facing host-buffer
 call (quads in pinned host memory, height maps back to pinned host memory).  `--impl reference`
-times the reference's own CPU implementation (oracle/_ref, else the C port) on the host cores.
+times the reference's own CPU implementation (oracle/_ref) on the host cores.
 """
 import argparse
+import glob
 import json
 import os
 import sys
@@ -45,14 +51,37 @@ def claim_stdout():
 def emit(line):
     os.write(1 if _REAL_STDOUT is None else _REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
+
 DEPTH, DIM, PATCH, OCTAVES, GAIN, MAX_LOD = 7, 32, 30, 8, 0.5, 18
 QUADS_PER_FACE = 4 ** DEPTH                      # 16 384
-VERTS_PER_GPU = QUADS_PER_FACE * DIM * DIM       # 16 777 216
 # algorithmic flop per height sample = octaves*95 + 27
 FLOP_PER_VERTEX = OCTAVES * 95 + 27              # 787
 METRIC = "displaced+shaded vertices/sec"
-WORKLOAD = ("C2 per GPU: one cube-sphere face at depth 7 = 16384 quads x 32^2 = 16.78M vertices, "
-            "fBm 8 octaves gain 0.5, patch 30 verts; N GPUs = N faces (C3 sharded by face)")
+
+
+def total_quads(world):
+    """C2 (one face) on one GPU, C3 (the planet) as a fixed total on several."""
+    return QUADS_PER_FACE if world == 1 else 6 * QUADS_PER_FACE
+
+
+def shard_range(n_units, rank, world):                              # == planet_b200.sharding.shard_range
+    base, extra = divmod(n_units, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def make_config(world):
+    """The workload, identically worded by both arms (--impl ours / reference)."""
+    nq = total_quads(world)
+    if world == 1:
+        workload = ("C2 (BASELINE.json configs[1]): one cube-sphere face at depth 7 = 16384 quads x 32^2 = 16.78M vertices, "
+                    "fBm 8 octaves gain 0.5, patch 30 verts, 1 GPU")
+    else:
+        workload = (f"C3 (BASELINE.json configs[2]): full planet, 6 faces at depth 7 = 98304 quads x 32^2 = 100.66M vertices "
+                    f"as a fixed total, fBm 8 octaves gain 0.5, patch 30 verts, split by patch range over {world} GPUs, "
+                    f"finished height maps gathered on every GPU")
+    return {"workload": workload, "depth": DEPTH, "dim": DIM, "octaves": OCTAVES, "gain": GAIN, "faces": nq // QUADS_PER_FACE,
+            "quads": nq, "vertices": nq * DIM * DIM, "gpus": world}
 
 
 def measured_peaks():
@@ -61,6 +90,17 @@ def measured_peaks():
         d = json.load(open(path))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one K2 launch from the newest committed ncu
+    capture (profiles/*k2_dram_traffic.json, written by tools/ncu_summary.py from an `ncu --set full`
+    run of this same command); None when no capture is committed."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*k2_dram_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    return int(d["dram_bytes_read"] + d["dram_bytes_write"]), os.path.relpath(files[-1], ROOT)
 
 
 class ClockSampler(threading.Thread):
@@ -110,45 +150,58 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_reference_run(nquads, threads, repeats=1):
+def reference_quads(world, nquads=None):
+    """The workload's quads from the CPU checker (face-major emission order, main.cpp:604-624)."""
+    from oracle.bindings import PortOracle
+    port = PortOracle()
+    faces = total_quads(world) // QUADS_PER_FACE
+    quads = np.concatenate([port.uniform_quads(f, DEPTH) for f in range(faces)])
+    return quads if nquads is None else quads[:nquads]
+
+
+def cpu_reference_run(orc, quads, threads, repeats=1):
     """The reference's CPU path (GenerateHeightMap over quads) on the host cores; returns
-    (vertices/s, kind, seconds).  This is the one place bench.py executes oracle/."""
-    from oracle.bindings import FBM, best_oracle, height_params, PortOracle
-    orc = best_oracle()
-    quads = PortOracle().uniform_quads(0, DEPTH)[:nquads]
+    (vertices/s, seconds, maps).  This is the one place bench.py executes oracle/."""
+    from oracle.bindings import FBM, height_params
     hp = height_params(kind=FBM, gain=GAIN, fixed_octaves=OCTAVES)
-    best = None
+    best, maps = None, None
     for _ in range(repeats):
         t0 = time.perf_counter()
         maps = orc.generate_height_maps(quads, DIM, MAX_LOD, hp, nthreads=threads)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     assert np.isfinite(maps).all()
-    cpu_reference_run.last_maps = maps
-    return nquads * DIM * DIM / best, orc.kind, best
+    return len(quads) * DIM * DIM / best, best, maps
 
 
 def run_reference(args, rank, world):
+    """The reference arm: the reference's own CPU implementation of the path (oracle/_ref, built
+    from /root/reference at -O3 where this host runs that build, else -O2, else the C port), all
+    host cores, on the GPU arm's workload."""
     if rank != 0:
         return
+    if "WORLD_SIZE" not in os.environ:                                  # launched without torchrun: --gpus names the workload
+        world = max(args.gpus, 1)
+    from oracle.bindings import fastest_oracle
+    orc = fastest_oracle()
     cores = host_cores()
-    nquads = QUADS_PER_FACE                       # the whole C2 batch: ~6 core-seconds of CPU work
+    quads = reference_quads(world)                # the whole workload: ~6 (C2) / ~40 (C3) core-seconds per step
     times = []
-    kind = None
     for i in range(args.warmup + args.steps):
-        v, kind, dt = cpu_reference_run(nquads, cores)
+        _, dt, _ = cpu_reference_run(orc, quads, cores)
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
-    value = nquads * DIM * DIM / (ms * 1e-3)
-    sample = f"{nquads} quads x {DIM}^2 (the full C2 batch) per step, GenerateHeightMap only"
+    value = len(quads) * DIM * DIM / (ms * 1e-3)
+    sample = (f"{len(quads)} quads x {DIM}^2 (the whole workload) per step, GenerateHeightMap only "
+              f"(main.cpp:123-151; the reference's displacement + normals exist only as a GLSL shader), "
+              f"built {getattr(orc, 'flags', 'gcc -O2 -ffp-contract=off (C port)')}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "vertices/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference CPU path = height-map generation "
-                   "(main.cpp:123-151); its displacement+normals exist only as a GLSL shader"},
-        "cpu_baseline": {"value": value, "unit": "vertices/s", "cores": cores, "kind": kind, "sample": sample},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": make_config(world),
+        "cpu_baseline": {"value": value, "unit": "vertices/s", "cores": cores, "kind": orc.kind, "sample": sample},
         "e2e": {"value": value, "unit": "vertices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -158,6 +211,7 @@ def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
     import planet_b200 as pb
+    from planet_b200.sharding import PatchGather
 
     torch.cuda.set_device(local_rank)
     pb.init(local_rank)
@@ -165,18 +219,22 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    face = rank % 6
-    seed = (0.0, 0.0, 0.0) if rank < 6 else (0.0, 64.5 * (rank // 6), 0.0)
-    params = pb.fbm_params(octaves=OCTAVES, gain=GAIN, precision=pb.FAST, seed_offset=seed)
-    nq, nv, ni = QUADS_PER_FACE, pb.patch_vertex_count(PATCH), pb.patch_index_count(PATCH)
+    Q = total_quads(world)
+    lo, hi = shard_range(Q, rank, world)
+    nq = hi - lo                                                            # this rank's quads
+    params = pb.fbm_params(octaves=OCTAVES, gain=GAIN, precision=pb.FAST)
+    nv, ni = pb.patch_vertex_count(PATCH), pb.patch_index_count(PATCH)
     cam = (0.0, 0.0, -6371000.0 - 10.0)           # main.cpp:864
+    warmup = max(args.warmup, 3)
 
     quads = torch.empty((nq, 13), dtype=torch.int64, device=dev)
     indices = torch.empty(nq * ni, dtype=torch.int32, device=dev)
-    heights = torch.empty((nq, DIM, DIM), dtype=torch.float32, device=dev)
     pos = torch.empty((nq, nv, 4), dtype=torch.float32, device=dev)
     nrm = torch.empty((nq, nv, 4), dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # 2x the 126 MB L2
+    gather = PatchGather(Q, DIM, n_buffers=2, device=dev) if world > 1 else None
+    # one rank: the height maps live in a plain buffer; several: in the rank's slice of the gathered buffers
+    heights = torch.empty((nq, DIM, DIM), dtype=torch.float32, device=dev) if world == 1 else None
     L, C = pb.lib(), pb.C
     pp = C.byref(params)
     camv = (C.c_double * 3)(*cam)
@@ -184,14 +242,17 @@ def run_ours(args, rank, local_rank, world):
     sp = C.c_void_p(stream.cuda_stream)
 
     def k1():
-        pb._check(L.planet_gpu_tessellate_uniform(pp, DEPTH, face * nq, nq, quads.data_ptr(), indices.data_ptr(), sp))
+        pb._check(L.planet_gpu_tessellate_uniform(pp, DEPTH, lo, nq, quads.data_ptr(), indices.data_ptr(), sp))
 
-    def k2():
-        pb._check(L.planet_gpu_generate_height_maps(pp, quads.data_ptr(), nq, DIM, MAX_LOD, heights.data_ptr(), sp))
+    def k2(out):
+        pb._check(L.planet_gpu_generate_height_maps(pp, quads.data_ptr(), nq, DIM, MAX_LOD, out.data_ptr(), sp))
 
-    def k3():
-        pb._check(L.planet_gpu_shade(pp, quads.data_ptr(), nq, camv, heights.data_ptr(), -1.0,
-                                     pos.data_ptr(), nrm.data_ptr(), sp))
+    def k3(maps):
+        ptr = maps if isinstance(maps, int) else maps.data_ptr()
+        pb._check(L.planet_gpu_shade(pp, quads.data_ptr(), nq, camv, ptr, -1.0, pos.data_ptr(), nrm.data_ptr(), sp))
+
+    # this rank's slice of each gathered buffer (device pointers; the memory belongs to the C++ gather object)
+    shard_ptr = [gather.local(lo, nq, which=b).data_ptr() for b in range(2)] if gather is not None else None
 
     def barrier():
         if world > 1:
@@ -199,8 +260,30 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     ev = lambda: torch.cuda.Event(enable_timing=True)                      # noqa: E731
-    for _ in range(max(args.warmup, 3)):
-        k1(); k2(); k3()
+
+    def step(marks=None):
+        """One step; with `marks`, CUDA events on the launching stream around every kernel."""
+        e = [ev() for _ in range(5)] if marks is not None else None
+        if e: e[0].record()
+        k1()
+        if e: e[1].record()
+        if gather is None:
+            k2(heights)
+            if e: e[2].record()
+            k3(heights)
+            if e: e[3].record(); e[4].record()
+        else:
+            # K2 + K4: compute, push every finished tile to all GPUs, signal the peers
+            pb._check(L.planet_gpu_gather_height_maps(gather.handle, pp, quads.data_ptr(), nq, lo, DIM, MAX_LOD, sp))
+            if e: e[2].record()
+            k3(shard_ptr[L.planet_gpu_gather_last_buffer(gather.handle)])   # shade this rank's patches while the peers' maps land
+            if e: e[3].record()
+            pb._check(L.planet_gpu_gather_wait(gather.handle, 1, sp))       # every peer's shard is in this rank's buffer; release it
+            if e: e[4].record()
+        if e: marks.append(e)
+
+    for _ in range(warmup):
+        step()
     barrier()
 
     # ---- timed region: K steps, per-step CUDA events on the launching stream, L2 flushed between ----
@@ -211,36 +294,81 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     for _ in range(args.steps):
         flush.zero_()                                                      # evict L2 (not timed)
-        e = [ev() for _ in range(4)]
-        e[0].record(); k1(); e[1].record(); k2(); e[2].record(); k3(); e[3].record()
-        marks.append(e)
+        step(marks)
     barrier()
     launches = pb.launch_count() - launches0
-    t_k1 = np.array([m[0].elapsed_time(m[1]) for m in marks])
-    t_k2 = np.array([m[1].elapsed_time(m[2]) for m in marks])
-    t_k3 = np.array([m[2].elapsed_time(m[3]) for m in marks])
-    t_step = np.array([m[0].elapsed_time(m[3]) for m in marks])
+    if gather is not None:
+        gather.check()                                                     # no wait timed out
+    seg = lambda a, b: np.array([m[a].elapsed_time(m[b]) for m in marks])  # noqa: E731
+    t_k1, t_k2, t_k3, t_wait, t_step = seg(0, 1), seg(1, 2), seg(2, 3), seg(3, 4), seg(0, 4)
 
-    # ---- the same K2 batch in EXACT arithmetic (bit-identical to the reference), for the record ----
-    p_exact = pb.fbm_params(octaves=OCTAVES, gain=GAIN, precision=pb.EXACT, seed_offset=seed)
-    ppe = C.byref(p_exact)
-    ex_t = []
-    for i in range(5):
-        a, b_ = ev(), ev()
-        a.record()
-        pb._check(L.planet_gpu_generate_height_maps(ppe, quads.data_ptr(), nq, DIM, MAX_LOD, heights.data_ptr(), sp))
-        b_.record(); torch.cuda.synchronize()
-        if i >= 2:
-            ex_t.append(a.elapsed_time(b_))
-    ms_k2_exact = float(np.mean(ex_t))
-    exact_maps_host = heights.cpu().numpy() if (rank == 0 and world == 1) else None
-    k2()                                                               # restore the FAST heights for K3 / e2e
-    # parity at full size, stated in the bench line: FAST against the bit-exact mode on all 16.8 M samples,
-    # with the bound the tests use (1e-5 relative to the fractal's amplitude sum times the height scale)
-    fast_err = None
-    if exact_maps_host is not None:
-        torch.cuda.synchronize()
+    extra = {}
+    local_maps = heights if gather is None else gather.local(lo, nq)
+    if gather is not None:
+        fused_buffer = gather.gathered().clone()
+        # ---- the same step without K4 (compute only), and with the plain NCCL collective after it ----
+        plain = torch.empty((nq, DIM, DIM), dtype=torch.float32, device=dev)
+        tc, tn = [], []
+        spans = [(a, b - a) for a, b in (shard_range(Q, r, world) for r in range(world))]
+        for i in range(3 + args.steps):
+            flush.zero_()
+            a, b_ = ev(), ev()
+            a.record(); k1(); k2(plain); k3(plain); b_.record()
+            torch.cuda.synchronize()
+            if i >= 3: tc.append(a.elapsed_time(b_))
+        for i in range(3 + min(args.steps, 10)):
+            barrier()
+            flush.zero_()
+            a, b_ = ev(), ev()
+            a.record(); k1(); k2(gather.local(lo, nq, which=0)); k3(gather.local(lo, nq, which=0)); gather.nccl(spans, which=0); b_.record()
+            torch.cuda.synchronize()
+            if i >= 3: tn.append(a.elapsed_time(b_))
+        barrier()
+        same_as_nccl = bool(torch.equal(fused_buffer, gather.gathered(which=0)))
+        # the gathered buffer against the same 98 304 quads computed on THIS GPU alone
+        allq = pb.tessellate_uniform(DEPTH, first=0, nquads=Q, params=params)
+        single = pb.generate_height_maps(allq, DIM, MAX_LOD, params)
+        same_as_single = bool(torch.equal(fused_buffer, single))
+        del allq, single, fused_buffer
+        extra = {"compute_ms": float(np.mean(tc)), "nccl_step_ms": float(np.mean(tn)),
+                 "same_as_nccl": same_as_nccl, "same_as_single": same_as_single}
+        local_maps = plain
+        k2(plain)
+
+    # ---- N = 1 extras: EXACT-mode K2, full-size parity figures, K1 at a size L2 cannot absorb ----
+    ms_k2_exact, fast_err, exact_maps_host, k1_c3_ms = None, None, None, None
+    if world == 1:
+        p_exact = pb.fbm_params(octaves=OCTAVES, gain=GAIN, precision=pb.EXACT)
+        ppe = C.byref(p_exact)
+        ex_t = []
+        scratch = torch.empty_like(heights)
+        for i in range(5):
+            a, b_ = ev(), ev()
+            a.record()
+            pb._check(L.planet_gpu_generate_height_maps(ppe, quads.data_ptr(), nq, DIM, MAX_LOD, scratch.data_ptr(), sp))
+            b_.record(); torch.cuda.synchronize()
+            if i >= 2:
+                ex_t.append(a.elapsed_time(b_))
+        ms_k2_exact = float(np.mean(ex_t))
+        exact_maps_host = scratch.cpu().numpy()
+        # FAST against the bit-exact mode on all 16.8 M samples, with the bound the tests use
         fast_err = float(np.abs(heights.cpu().numpy().astype(np.float64) - exact_maps_host).max())
+        del scratch
+        # K1 at C3 size: 98 304 quads, 811 MB written -- six times the 126 MB L2
+        q3 = 6 * QUADS_PER_FACE
+        quads3 = torch.empty((q3, 13), dtype=torch.int64, device=dev)
+        idx3 = torch.empty(q3 * ni, dtype=torch.int32, device=dev)
+        t3 = []
+        for i in range(3 + 10):
+            flush.zero_()
+            a, b_ = ev(), ev()
+            a.record()
+            pb._check(L.planet_gpu_tessellate_uniform(pp, DEPTH, 0, q3, quads3.data_ptr(), idx3.data_ptr(), sp))
+            b_.record(); torch.cuda.synchronize()
+            if i >= 3:
+                t3.append(a.elapsed_time(b_))
+        k1_c3_ms = float(np.mean(t3))
+        del quads3, idx3
     fast_tol = 1e-5 * 8848.0 * float(sum(np.float32(GAIN) ** k for k in range(OCTAVES)))
 
     # ---- e2e: the host-buffer call a reference-side caller makes: H2D quads, K2, D2H heights, and
@@ -251,10 +379,10 @@ def run_ours(args, rank, local_rank, world):
     cam3 = (C.c_double * 3)(*cam)
     e2e_t = []
     for i in range(3 + args.steps):
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         pb._check(L.planet_gpu_terrain_host(pp, h_quads.data_ptr(), nq, MAX_LOD, cam3, -1.0, h_out.data_ptr(),
-                                            heights.data_ptr(), pos.data_ptr(), nrm.data_ptr()))
+                                            local_maps.data_ptr(), pos.data_ptr(), nrm.data_ptr()))
         torch.cuda.synchronize()
         if i >= 3:
             e2e_t.append(time.perf_counter() - t0)
@@ -262,142 +390,118 @@ def run_ours(args, rank, local_rank, world):
     sampler.join()
     e2e_ms = 1e3 * float(np.mean(e2e_t))
 
-    # ---- gather of finished patches (K4) ------------------------------------------------------
-    # (a) NCCL all_gather_into_tensor after the step; (b) the gather fused into K2: every height is
-    # also stored to the peers' IPC-mapped gathered buffers over NVLink while the kernel computes.
-    gather_ms, fused_step_ms, gather_identical, fused_error = None, None, None, None
-    if world > 1:
-        from planet_b200.sharding import PeerGather
-        allh = torch.empty((world * nq, DIM, DIM), dtype=torch.float32, device=dev)
-        for i in range(3):
-            dist.all_gather_into_tensor(allh, heights)
-        barrier()
-        g0, g1 = ev(), ev()
-        g0.record()
-        for _ in range(5):
-            dist.all_gather_into_tensor(allh, heights)
-        g1.record()
-        barrier()
-        gather_ms = g0.elapsed_time(g1) / 5
-
-        fused_error = None
-        pg = None
-        try:                                                        # mapping the peers' buffers (CUDA IPC)
-            pg = PeerGather((nq, DIM, DIM), device=dev)
-        except Exception as exc:                                    # noqa: BLE001
-            fused_error = f"{type(exc).__name__}: {exc}"[:200]
-        ok = torch.tensor([0 if pg is None else 1], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)                   # all ranks take the same branch
-        try:
-            if ok.item() == 0:
-                raise RuntimeError(fused_error or "a peer rank could not map the gathered buffers")
-            shard, peer_shards = pg.local_shard(), pg.peer_shards()
-            peer_arr = (C.c_void_p * len(peer_shards))(*[t.data_ptr() for t in peer_shards])
-
-            def fused_step():
-                k1()
-                pb._check(L.planet_gpu_generate_height_maps_gathered(pp, quads.data_ptr(), nq, DIM, MAX_LOD, shard.data_ptr(),
-                                                                     peer_arr, len(peer_shards), sp))
-                pb._check(L.planet_gpu_shade(pp, quads.data_ptr(), nq, camv, shard.data_ptr(), -1.0,
-                                             pos.data_ptr(), nrm.data_ptr(), sp))
-                pg.finish(stream)
-
-            for _ in range(3):
-                fused_step()
-            ts = []
-            for _ in range(args.steps):
-                barrier()
-                a, b_ = ev(), ev()
-                a.record(); fused_step(); b_.record(); torch.cuda.synchronize()
-                ts.append(a.elapsed_time(b_))
-            fused_step_ms = float(np.mean(ts))
-            k2(); dist.all_gather_into_tensor(allh, heights); torch.cuda.synchronize()
-            gather_identical = bool(torch.equal(pg.gathered, allh))
-            del shard, peer_shards
-            pg.close()
-        except Exception as exc:                                    # noqa: BLE001 -- e.g. CUDA IPC unavailable on this box
-            fused_error = f"{type(exc).__name__}: {exc}"[:200]
-            fused_step_ms, gather_identical = None, None
-
     # max over ranks (device-timed)
-    stats = torch.tensor([t_step.mean(), t_k1.mean(), t_k2.mean(), t_k3.mean(), e2e_ms,
-                          gather_ms or 0.0, fused_step_ms if fused_step_ms else 1e9, 0.0 if gather_identical else 1.0],
-                         dtype=torch.float64, device=dev)
+    mine = [t_step.mean(), t_k1.mean(), t_k2.mean(), t_k3.mean(), t_wait.mean(), e2e_ms,
+            extra.get("compute_ms", 0.0), extra.get("nccl_step_ms", 0.0),
+            0.0 if extra.get("same_as_nccl", True) else 1.0, 0.0 if extra.get("same_as_single", True) else 1.0]
+    stats = torch.tensor(mine, dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        allstats = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(allstats, stats)
+        per_rank = torch.stack(allstats).cpu().numpy()
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    ms_step, ms_k1, ms_k2, ms_k3, e2e_ms, gather_ms, fused_step_ms, gather_bad = [float(x) for x in stats.tolist()]
+    ms_step, ms_k1, ms_k2, ms_k3, ms_wait, e2e_ms, compute_ms, nccl_ms, nccl_bad, single_bad = [float(x) for x in stats.tolist()]
 
     if rank == 0:
         hbm_peak, peak_src = measured_peaks()
         fp32_tf, _ = pb.measure_fp32_peak(300.0)                           # live FFMA probe on this GPU
         info = pb.device_info()
         nominal_tf = info["sm_count"] * info["fp32_lanes_per_sm"] * 2 * info["clock_khz"] * 1e3 / 1e12
-        k2_tf = VERTS_PER_GPU * FLOP_PER_VERTEX / (ms_k2 * 1e-3) / 1e12
+        verts_rank = nq * DIM * DIM
+        total_verts = Q * DIM * DIM
+        k2_tf = verts_rank * FLOP_PER_VERTEX / (ms_k2 * 1e-3) / 1e12
         k1_bytes = nq * 104 + nq * ni * 4
-        k3_bytes = nq * DIM * DIM * 4 + nq * nv * 32 + nq * 104
-        total_verts = VERTS_PER_GPU * world
-        cores = host_cores()
-        cpu_v, cpu_kind, cpu_s = cpu_reference_run(QUADS_PER_FACE, cores)
-        # both sides computed the same thing: the CPU maps are the bytes the EXACT-mode kernel produced
-        same_bytes = None if exact_maps_host is None else (
-            exact_maps_host.tobytes() == np.ascontiguousarray(cpu_reference_run.last_maps).tobytes())
-        cpu1_v, _, cpu1_s = cpu_reference_run(1024, 1)                      # what the reference itself does: one thread
+        k3_write = nq * nv * 32
+        k3_hbm = k3_write + nq * 104 + (0 if world == 1 else verts_rank * 4)   # cold reads; see roofline_k3.note
+        k3_alg = k3_write + nq * 104 + verts_rank * 4
+        traffic, traffic_src = profiled_traffic()
+        config = make_config(world)
+        config.update({"quads_per_gpu": nq, "vertices_per_gpu": verts_rank, "precision": "FAST",
+                       "l2": "256 MiB buffer written between timed steps (L2 flush)",
+                       "step": "K1 tessellate + K2 heights + K3 shade" if world == 1 else
+                               "K1 tessellate + K2 heights with K4 fused (bulk copies to every peer over NVLink) + K3 shade + wait for the peers' shards"})
         line = {
             "metric": METRIC, "value": total_verts / (ms_step * 1e-3), "unit": "vertices/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "depth": DEPTH, "dim": DIM, "octaves": OCTAVES, "gain": GAIN,
-                       "quads_per_gpu": nq, "vertices_per_gpu": VERTS_PER_GPU, "precision": "FAST",
-                       "l2": "256 MiB buffer written between timed steps (L2 flush); step working set 730 MB",
-                       "step": "K1 tessellate + K2 heights + K3 shade"},
-            "ms": {"k1_tessellate": ms_k1, "k2_heights": ms_k2, "k3_shade": ms_k3,
-                   "k2_heights_exact_mode": ms_k2_exact},
-            "parity": {"fast_vs_exact_max_abs_m": fast_err, "tolerance_m": fast_tol,
-                       "exact_mode_bytes_equal_reference_cpu": same_bytes},
-            "roofline": {"kernel": "k_height_maps_fast<768,32,gather=0,kind=fBm>", "bound": "fp32", "achieved": k2_tf, "peak": fp32_tf,
-                         "unit": "TFLOP/s", "frac": k2_tf / fp32_tf,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
-                         # (profiles/r01zf_ncu_summary_final.txt: 1.74 MB read + 12.81 MB written): the 67 MB of
-                         # heights are still dirty in the 126 MB L2 when the kernel ends
-                         "traffic": 14550016,
+            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config,
+            "ms": {"k1_tessellate": ms_k1, "k2_heights" if world == 1 else "k2_heights_with_gather": ms_k2,
+                   "k3_shade": ms_k3, "wait_for_peers": ms_wait, "k2_heights_exact_mode": ms_k2_exact},
+            "parity": {"fast_vs_exact_max_abs_m": fast_err, "tolerance_m": fast_tol},
+            # the dominant kernel; at N > 1 its duration includes the NVLink pushes it is fused with
+            "roofline": {"kernel": "k_height_maps_fast<768,32,gather=%d,kind=fBm>" % (world > 1), "bound": "fp32",
+                         "achieved": k2_tf, "peak": fp32_tf, "unit": "TFLOP/s", "frac": k2_tf / fp32_tf,
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": "FFMA probe measured in this run", "nominal_peak": nominal_tf,
                          "frac_of_nominal": k2_tf / nominal_tf, "flop_per_vertex": FLOP_PER_VERTEX,
-                         "vertices_per_s": VERTS_PER_GPU / (ms_k2 * 1e-3)},
-            "roofline_k1": {"kernel": "k_tessellate_fused", "bound": "hbm",
+                         "vertices_per_launch": verts_rank, "ms": ms_k2},
+            "roofline_k1": {"kernel": "k_tessellate_bulk", "bound": "hbm",
                             "achieved": k1_bytes / (ms_k1 * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": k1_bytes / (ms_k1 * 1e-3) / 1e9 / hbm_peak, "bytes": k1_bytes,
-                            "peak_source": peak_src},
-            # algorithmic bytes; the 67 MB of height maps K2 just wrote are still in the 126 MB L2 when K3
-            # reads them (L2 is flushed between steps, not between K2 and K3), so HBM sees ~536 MB of it
-            "roofline_k3": {"kernel": "k_shade", "bound": "hbm", "achieved": k3_bytes / (ms_k3 * 1e-3) / 1e9,
-                            "peak": hbm_peak, "unit": "GB/s", "frac": k3_bytes / (ms_k3 * 1e-3) / 1e9 / hbm_peak,
-                            "bytes": k3_bytes, "peak_source": peak_src},
-            "cpu_baseline": {"value": cpu_v, "unit": "vertices/s", "cores": cores, "kind": cpu_kind,
-                             "sample": f"{QUADS_PER_FACE} quads x {DIM}^2 (full C2 batch), GenerateHeightMap only, "
-                                       f"{cpu_s:.2f} s wall",
-                             "single_thread_value": cpu1_v,
-                             "single_thread_sample": f"1024 quads x {DIM}^2, {cpu1_s:.2f} s wall",
-                             "same_bytes_as_gpu_exact_mode": same_bytes},
+                            "frac": k1_bytes / (ms_k1 * 1e-3) / 1e9 / hbm_peak, "bytes": k1_bytes, "ms": ms_k1,
+                            "peak_source": peak_src,
+                            "note": "write-only; at this size part of the stream is still in the 126 MB L2 when the kernel ends"},
+            # bytes that reach HBM: the two float4 streams written + the quads read.  At N = 1 the 67 MB of
+            # height maps K2 wrote in the same step are L2 hits (L2 is flushed between steps, not between
+            # K2 and K3); frac follows from bytes_hbm, bytes_algorithmic is printed beside it
+            "roofline_k3": {"kernel": "k_shade", "bound": "hbm", "achieved": k3_hbm / (ms_k3 * 1e-3) / 1e9,
+                            "peak": hbm_peak, "unit": "GB/s", "frac": k3_hbm / (ms_k3 * 1e-3) / 1e9 / hbm_peak,
+                            "bytes_hbm": k3_hbm, "bytes_algorithmic": k3_alg, "ms": ms_k3, "peak_source": peak_src},
             "e2e": {"value": total_verts / (e2e_ms * 1e-3), "unit": "vertices/s",
                     "h2d_bytes_per_step": nq * 104, "d2h_bytes_per_step": nq * DIM * DIM * 4,
-                    "ms_per_step": e2e_ms,
+                    "ms_per_step": e2e_ms, "bytes_are": "per GPU",
                     "path": "planet_gpu_terrain_host: pinned host quads -> K2 -> pinned host heights (8-chunk pipeline) + K3 on the resident maps"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
-        nccl_gather = {"value": total_verts / ((ms_step + gather_ms) * 1e-3) if world > 1 else None, "gather_ms": gather_ms,
-                       "collective": "nccl all_gather_into_tensor of height maps after the step"}
-        if world > 1 and fused_step_ms >= 1e8:                       # peer mapping failed on some rank: NCCL only
-            line["with_gather"] = dict(nccl_gather, unit="vertices/s", note="fused peer-store gather unavailable: " + str(fused_error))
-        elif world > 1:
-            line["with_gather"] = {
-                "value": total_verts / (fused_step_ms * 1e-3), "unit": "vertices/s", "ms_per_step": fused_step_ms,
-                "method": "gather fused into K2: heights stored to every peer's CUDA-IPC-mapped buffer over NVLink "
-                          "while the kernel computes (planet_gpu_generate_height_maps_gathered) + one barrier",
-                "bytes_per_gpu": nq * DIM * DIM * 4, "identical_to_nccl_all_gather": gather_bad == 0.0,
-                "nccl": nccl_gather}
+        if world == 1:
+            k1c3_bytes = 6 * QUADS_PER_FACE * (104 + ni * 4)
+            line["roofline_k1_c3"] = {"kernel": "k_tessellate_bulk", "bound": "hbm", "workload": "98304 quads (C3 size): 811 MB written, 6x the L2",
+                                      "achieved": k1c3_bytes / (k1_c3_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                      "frac": k1c3_bytes / (k1_c3_ms * 1e-3) / 1e9 / hbm_peak, "bytes": k1c3_bytes, "ms": k1_c3_ms,
+                                      "peak_source": peak_src}
+            # CPU baseline: the reference's own code on this box's host cores, on the whole C2 batch
+            from oracle.bindings import RefOracle, best_oracle
+            cores = host_cores()
+            cq = reference_quads(1)
+            o2 = best_oracle()                                             # oracle/_ref at -O2 (else the C port)
+            o2_v, o2_s, o2_maps = cpu_reference_run(o2, cq, cores)
+            fast, o3_v, o3_s, o3_maps = o2, o2_v, o2_s, o2_maps
+            if RefOracle.o3_available():                                   # the same sources at -O3 / AVX2
+                fast = RefOracle(o3=True)
+                o3_v, o3_s, o3_maps = cpu_reference_run(fast, cq, cores)
+            one_v, one_s, _ = cpu_reference_run(fast, cq[:1024], 1)         # what the reference itself does: one thread
+            same_bytes = exact_maps_host.tobytes() == np.ascontiguousarray(o2_maps).tobytes()
+            line["parity"]["exact_mode_bytes_equal_reference_cpu"] = same_bytes
+            line["cpu_baseline"] = {
+                "value": o3_v, "unit": "vertices/s", "cores": cores, "kind": fast.kind,
+                "sample": f"{len(cq)} quads x {DIM}^2 (the whole C2 batch), GenerateHeightMap only, {o3_s:.2f} s wall, "
+                          f"built {getattr(fast, 'flags', 'gcc -O2 -ffp-contract=off (C port)')}",
+                "value_O2": o2_v, "flags_O2": getattr(o2, "flags", "gcc -O2 -ffp-contract=off (C port)"),
+                "O3_bytes_equal_O2": bool(np.ascontiguousarray(o3_maps).tobytes() == np.ascontiguousarray(o2_maps).tobytes()),
+                "single_thread_value": one_v, "single_thread_sample": f"1024 quads x {DIM}^2, {one_s:.2f} s wall",
+                "same_bytes_as_gpu_exact_mode": same_bytes}
+        else:
+            line["e2e"]["per_rank_ms"] = [float(x) for x in per_rank[:, 5]]
+            line["per_rank_step_ms"] = [float(x) for x in per_rank[:, 0]]
+            gather_bytes_in = (Q - nq) * DIM * DIM * 4                       # what every GPU must receive per step
+            line["gather"] = {
+                "method": "fused into K2: every finished 128-sample tile is one 512-byte bulk copy (cp.async.bulk) to this GPU's "
+                          "buffer and to the same offset of every peer's CUDA-IPC-mapped buffer over NVLink; arrival and "
+                          "release are flags written GPU to GPU, two gathered buffers, no host barrier in the step",
+                "bytes_received_per_gpu": gather_bytes_in,
+                "nvlink_floor_ms": gather_bytes_in / 770e9 * 1e3,
+                "nvlink_floor_note": "bytes every GPU must receive / 770 GB/s per direction (measured peer copy, B200_PROFILING.md)",
+                "identical_to_nccl_all_gather": nccl_bad == 0.0,
+                "identical_to_single_gpu_buffer": single_bad == 0.0,
+                "compute_only": {"ms_per_step": compute_ms, "value": total_verts / (compute_ms * 1e-3),
+                                 "what": "the same step without K4 (K1 + K2 + K3 on the rank's shard)"},
+                "nccl": {"ms_per_step": nccl_ms, "value": total_verts / (nccl_ms * 1e-3),
+                         "what": "K1 + K2 + K3, then ncclAllGather of the height maps (planet_gpu_gather_nccl)"}}
         emit(line)
+    if gather is not None:
+        del local_maps
+        gather.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -109,14 +109,48 @@ void  planet_gpu_generate_height_map(float *data, int dim, const void *quad, int
 int planet_gpu_generate_height_maps(const planet_gpu_params *p, const planet_gpu_quad *d_quads,
                                     int64_t nquads, int dim, int max_depth, float *d_out,
                                     void *stream);
-/* K2 with the multi-GPU gather fused in: identical to planet_gpu_generate_height_maps, and every
- * height is additionally stored to the same offset of up to 7 peer buffers (peer_out: HOST array
- * of n_peers DEVICE pointers, typically this rank's shard inside each peer GPU's gathered buffer,
- * mapped with CUDA IPC / peer access).  The stores travel over NVLink while the kernel computes;
- * the buffers are complete once every rank's kernel has finished. */
+/* K2 with the multi-GPU gather fused in, for callers that map the peers' buffers themselves
+ * (planet_gpu_gather_* below does it for them): identical to planet_gpu_generate_height_maps, and
+ * every finished tile is additionally stored to the same offset of up to 7 peer buffers (peer_out:
+ * HOST array of n_peers DEVICE pointers, typically this rank's shard inside each peer GPU's
+ * gathered buffer, mapped with CUDA IPC / peer access).  The stores travel over NVLink while the
+ * kernel computes; the buffers are complete once every rank's kernel has finished. */
 int planet_gpu_generate_height_maps_gathered(const planet_gpu_params *p, const planet_gpu_quad *d_quads,
                                              int64_t nquads, int dim, int max_depth, float *d_out,
                                              float *const *peer_out, int n_peers, void *stream);
+/* ---- K4: multi-GPU gather of finished patches (one process per GPU) -------------- */
+/* The reference is a single process; here the leaf quads are split by patch range over the GPUs of
+ * one box and the ONE exchange on the path is gathering every rank's finished height maps into one
+ * buffer, in the reference's emission order (main.cpp:589-592, 604-624), on every rank.  The
+ * gather object is C++ behind this ABI: NCCL (ncclCommInitRank from `id`) for bootstrap, barriers
+ * and the plain collective; cudaIpcGetMemHandle / cudaIpcOpenMemHandle for the peer mappings the
+ * fused kernel stores through.  All ranks must call create / destroy together. */
+#define PLANET_GATHER_ID_BYTES 128
+/* rank 0 fills `id` (ncclGetUniqueId) and hands the 128 bytes to the other ranks by any means */
+int   planet_gpu_gather_unique_id(void *id);
+/* `bytes`: size of ONE gathered buffer (all ranks' shards); n_buffers 1 or 2 (2: a step never waits
+ * for the peers to finish reading the previous one).  world 1 needs no id.  NULL on error. */
+void *planet_gpu_gather_create(const void *id, int rank, int world, int64_t bytes, int n_buffers);
+void  planet_gpu_gather_destroy(void *gather);
+float *planet_gpu_gather_buffer(void *gather, int which);          /* DEVICE pointer, this rank's buffer `which` */
+int   planet_gpu_gather_last_buffer(const void *gather);           /* buffer the last gather_height_maps filled */
+/* K2 + K4 in one kernel: planet_gpu_generate_height_maps for quads [first_quad, first_quad + nquads)
+ * of the gathered buffer's quad order, written to that range of the next buffer on THIS rank and,
+ * as 512-byte bulk copies over NVLink while the kernel computes, on every peer; then signals the
+ * peers.  Stream-ordered, no host synchronisation. */
+int   planet_gpu_gather_height_maps(void *gather, const planet_gpu_params *p, const planet_gpu_quad *d_quads,
+                                    int64_t nquads, int64_t first_quad, int dim, int max_depth, void *stream);
+/* stream-ordered wait until every peer's shard of the last step has landed in this rank's buffer;
+ * release != 0 also tells the peers this rank is done reading it (they may overwrite it n_buffers
+ * steps later).  A peer that does not signal within 2 s sets an error (planet_gpu_gather_error). */
+int   planet_gpu_gather_wait(void *gather, int release, void *stream);
+/* the plain collective, for comparison and for data already in the local buffer: every rank r's
+ * bytes [offset_bytes[r], +size_bytes[r]) of buffer `which` are sent to all ranks (ncclAllGather in
+ * place for equal shards in rank order, grouped ncclBroadcast otherwise).  HOST arrays of world entries. */
+int   planet_gpu_gather_nccl(void *gather, int which, const int64_t *offset_bytes, const int64_t *size_bytes, void *stream);
+int   planet_gpu_gather_barrier(void *gather, void *stream);        /* all ranks; synchronises `stream` */
+int   planet_gpu_gather_error(void *gather);                        /* 0, or PLANET_E_CUDA after a timed-out wait */
+
 /* batched Gen::GetHeightAt (main.cpp:118-121): n points (xyz doubles), one (depth, max_depth) */
 int planet_gpu_heights_at(const planet_gpu_params *p, const double *d_xyz, int64_t n, int depth,
                           int max_depth, float *d_out, void *stream);

@@ -17,6 +17,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(HERE, "libplanet_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libplanet_ref.so")
+REF_O3_SO = os.path.join(HERE, "_ref", "libplanet_ref_o3.so")     # -O3 -march=x86-64-v3, same bits
 
 RIDGED, FBM, ZERO = 0, 1, 2
 RADIUS = 6371000.0                      # main.cpp:821
@@ -31,7 +32,7 @@ def build(force=False):
             os.path.getmtime(PORT_SO) < os.path.getmtime(os.path.join(HERE, "planet_oracle.c")):
         subprocess.check_call(["make", "-s", "-C", HERE, "port"])
     if os.path.exists("/root/reference/main.cpp") and (
-            force or not os.path.exists(REF_SO) or
+            force or not os.path.exists(REF_SO) or not os.path.exists(REF_O3_SO) or
             os.path.getmtime(REF_SO) < os.path.getmtime(os.path.join(HERE, "ref_oracle.cpp"))):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
 
@@ -221,10 +222,24 @@ class RefOracle:
             build()
         return os.path.exists(REF_SO)
 
-    def __init__(self):
+    @staticmethod
+    def o3_available():
+        """The -O3 / AVX2 build exists and this host can run it."""
+        if not RefOracle.available() or not os.path.exists(REF_O3_SO):
+            return False
+        try:
+            flags = next(l for l in open("/proc/cpuinfo") if l.startswith("flags")).split()
+        except (OSError, StopIteration):
+            return False
+        return all(f in flags for f in ("avx2", "bmi2", "fma"))
+
+    def __init__(self, o3=False):
         if not self.available():
             raise RuntimeError("oracle/_ref/libplanet_ref.so not built (needs /root/reference)")
-        L = self.L = C.CDLL(REF_SO)
+        if o3 and not self.o3_available():
+            raise RuntimeError("oracle/_ref/libplanet_ref_o3.so not built or not runnable on this CPU")
+        self.flags = "-O3 -march=x86-64-v3 -ffp-contract=off" if o3 else "-O2 -ffp-contract=off"
+        L = self.L = C.CDLL(REF_O3_SO if o3 else REF_SO)
         f, d, i, l, u64, vp = C.c_float, C.c_double, C.c_int, C.c_long, C.c_uint64, C.c_void_p
         sig = {
             "ref_perlin_tables": (None, [vp, vp]), "ref_perlin_random": (i, [i]),
@@ -397,3 +412,9 @@ class RefOracle:
 def best_oracle():
     """The reference itself when its build travelled here, else the port."""
     return RefOracle() if RefOracle.available() else PortOracle()
+
+
+def fastest_oracle():
+    """For timing the CPU side without sandbagging it: the reference at -O3 / AVX2 where that build
+    runs, else best_oracle().  Same bits either way (tests/test_oracle_golden.py)."""
+    return RefOracle(o3=True) if RefOracle.o3_available() else best_oracle()

@@ -65,6 +65,16 @@ def lib():
             "planet_gpu_generate_height_map": (None, [vp, i, vp, i]),
             "planet_gpu_generate_height_maps": (i, [pp, vp, i64, i, i, vp, vp]),
             "planet_gpu_generate_height_maps_gathered": (i, [pp, vp, i64, i, i, vp, vp, i, vp]),
+            "planet_gpu_gather_unique_id": (i, [vp]),
+            "planet_gpu_gather_create": (vp, [vp, i, i, i64, i]),
+            "planet_gpu_gather_destroy": (None, [vp]),
+            "planet_gpu_gather_buffer": (vp, [vp, i]),
+            "planet_gpu_gather_last_buffer": (i, [vp]),
+            "planet_gpu_gather_height_maps": (i, [vp, pp, vp, i64, i64, i, i, vp]),
+            "planet_gpu_gather_wait": (i, [vp, i, vp]),
+            "planet_gpu_gather_nccl": (i, [vp, i, vp, vp, vp]),
+            "planet_gpu_gather_barrier": (i, [vp, vp]),
+            "planet_gpu_gather_error": (i, [vp]),
             "planet_gpu_heights_at": (i, [pp, vp, i64, i, i, vp, vp]),
             "planet_gpu_noise": (i, [vp, i64, i, d, f, i, i, vp, vp]),
             "planet_gpu_tessellate_uniform": (i, [pp, i, i64, i64, vp, vp, vp]),
@@ -102,7 +112,10 @@ EXPORTED_SYMBOLS = [
     "planet_gpu_abi_version", "planet_gpu_default_params", "planet_gpu_init", "planet_gpu_shutdown",
     "planet_gpu_last_error", "planet_gpu_device_info", "planet_gpu_set_params",
     "planet_gpu_get_height_at", "planet_gpu_generate_height_map", "planet_gpu_generate_height_maps",
-    "planet_gpu_generate_height_maps_gathered", "planet_gpu_heights_at", "planet_gpu_noise", "planet_gpu_tessellate_uniform",
+    "planet_gpu_generate_height_maps_gathered", "planet_gpu_gather_unique_id", "planet_gpu_gather_create",
+    "planet_gpu_gather_destroy", "planet_gpu_gather_buffer", "planet_gpu_gather_last_buffer",
+    "planet_gpu_gather_height_maps", "planet_gpu_gather_wait", "planet_gpu_gather_nccl",
+    "planet_gpu_gather_barrier", "planet_gpu_gather_error", "planet_gpu_heights_at", "planet_gpu_noise", "planet_gpu_tessellate_uniform",
     "planet_gpu_quads_from_ids", "planet_gpu_patch_mesh", "planet_gpu_patch_vertex_count",
     "planet_gpu_patch_index_count", "planet_gpu_strip_index", "planet_gpu_uniform_leaf_id",
     "planet_gpu_max_lod", "planet_gpu_max_skirt_size",

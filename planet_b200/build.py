@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libplanet_gpu.so")
-SOURCES = ["planet_api.cu", "k0_lod.cu", "k1_tessellate.cu", "k2_heights.cu", "k3_shade.cu", "height_map_cache.cu"]
+SOURCES = ["planet_api.cu", "k0_lod.cu", "k1_tessellate.cu", "k2_heights.cu", "k3_shade.cu", "k4_gather.cu", "height_map_cache.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-    subprocess.check_call([nvcc, "-shared", "-o", SO, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    subprocess.check_call([nvcc, "-shared", "-o", SO, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
     return SO
 
 

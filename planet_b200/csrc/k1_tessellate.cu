@@ -17,6 +17,7 @@
 // held in registers by the index-stream CTAs and written with 16-byte stores, rebased per
 // quad so that all patches index one merged vertex buffer.
 #include "planet_common.cuh"
+#include "planet_tma.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -235,6 +236,73 @@ k_tessellate_fused(int depth, int64_t first, int64_t nquads, double radius, Quad
     }
 }
 
+// K1 with the index stream leaving each SM as bulk copies (TMA, SASS UBLKCP).  The first
+// `quad_blocks` CTAs walk QuadIDs to corners as above.  Every other CTA keeps its share of the
+// strip in registers, assembles the rebased strip of one quad (ni * 4 bytes: 8 144 at the
+// reference's n = 30) in one of NB shared-memory buffers -- 16-byte STS, no global store
+// instructions at all -- and thread 0 hands the buffer to the TMA unit as ONE
+// cp.async.bulk shared -> global.  Up to NB - 1 quads per CTA are in flight while the next one is
+// assembled, so HBM always has several 8 KB requests per SM queued whatever the warp occupancy is
+// (the per-thread-store version had to keep 16-byte stores of many warps in flight for that and
+// reached 0.66 of the copy peak).  One __syncthreads per quad.
+constexpr int BULK_THREADS = 128;
+constexpr int BULK_KV = 8;                      // strip vectors (uint4) a thread keeps in registers
+constexpr int BULK_NB = 4;                      // staging buffers per CTA
+
+__global__ void __launch_bounds__(BULK_THREADS)
+k_tessellate_bulk(int depth, int64_t first, int64_t nquads, double radius, Quad *__restrict__ quads,
+                  int quad_blocks, int n, int nv, int ni, uint32_t *__restrict__ indices,
+                  const uint32_t *__restrict__ strip)
+{
+    extern __shared__ __align__(128) uint32_t s_buf[];                 // NB buffers of ni words (ni % 4 == 0)
+    if ((int)blockIdx.x < quad_blocks) {
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nquads;
+             i += (int64_t)quad_blocks * blockDim.x)
+            store_quad(quads + i, quad_from_id(uniform_leaf_id(first + i, depth), radius));
+        return;
+    }
+    const int nvec = ni / 4;
+    const bool in_regs = nvec <= BULK_KV * BULK_THREADS;               // n <= 44
+    uint4 reg[BULK_KV];
+#pragma unroll
+    for (int j = 0; j < BULK_KV; j++) {
+        const int v = threadIdx.x + j * BULK_THREADS;
+        reg[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (in_regs && v < nvec)
+            reg[j] = strip ? __ldg(reinterpret_cast<const uint4 *>(strip) + v)
+                           : make_uint4(strip_index(4 * v, n), strip_index(4 * v + 1, n), strip_index(4 * v + 2, n), strip_index(4 * v + 3, n));
+    }
+    const int64_t qstride = (int64_t)gridDim.x - quad_blocks;
+    int it = 0;
+    for (int64_t q = (int64_t)blockIdx.x - quad_blocks; q < nquads; q += qstride, it++) {
+        uint4 *buf = reinterpret_cast<uint4 *>(s_buf + (size_t)(it % BULK_NB) * ni);
+        const uint32_t base = (uint32_t)q * (uint32_t)nv;              // idx[q][k] = q*nv + strip[k]
+        if (in_regs) {
+#pragma unroll
+            for (int j = 0; j < BULK_KV; j++) {
+                const int v = threadIdx.x + j * BULK_THREADS;
+                if (v < nvec) buf[v] = make_uint4(reg[j].x + base, reg[j].y + base, reg[j].z + base, reg[j].w + base);
+            }
+        } else {                                                       // large patches: the strip comes from L1/L2
+            for (int v = threadIdx.x; v < nvec; v += BULK_THREADS) {
+                const uint4 sv = strip ? __ldg(reinterpret_cast<const uint4 *>(strip) + v)
+                                       : make_uint4(strip_index(4 * v, n), strip_index(4 * v + 1, n), strip_index(4 * v + 2, n), strip_index(4 * v + 3, n));
+                buf[v] = make_uint4(sv.x + base, sv.y + base, sv.z + base, sv.w + base);
+            }
+        }
+        tma::fence_smem_writes();
+        // the buffer the NEXT quad is assembled in was handed to the TMA unit NB - 1 quads ago:
+        // all but the latest NB - 2 copies have been read out of shared memory after this wait
+        if (threadIdx.x == 0) tma::wait_read<BULK_NB - 2>();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tma::store_bulk(indices + q * ni, buf, (uint32_t)ni * 4u);
+            tma::commit();
+        }
+    }
+    if (threadIdx.x == 0) tma::wait_all<0>();
+}
+
 // the reference's static patch: vertices (main.cpp:402-425) and indices (:427-474)
 __global__ void k_patch_mesh(int n, float *__restrict__ verts, uint32_t *__restrict__ indices)
 {
@@ -331,24 +399,42 @@ int launch_tessellate_uniform(const planet_gpu_params *p, int depth, int64_t fir
         int grid = (int)std::min<int64_t>((nquads + 31) / 32, (int64_t)sm_count_k1() * 16);
         k_quads_uniform<<<grid, 32, 0, stream>>>(depth, first, nquads, p->radius, d_quads);
     } else {
-        size_t smem = (size_t)ni * sizeof(uint32_t);
         const bool vec4 = (ni % 4 == 0) && (reinterpret_cast<uintptr_t>(d_indices) & 15) == 0;
-        if (smem > 48 * 1024) {
-            PLANET_CUDA(cudaFuncSetAttribute(k_tessellate_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            PLANET_CUDA(cudaFuncSetAttribute(k_tessellate_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
-        // indices are rebased to the caller's buffer: quad 0 of this call is vertex block 0
-        int quad_blocks = d_quads ? (int)std::min<int64_t>((nquads + 255) / 256, sm_count_k1()) : 0;
         static const int idx_per_sm = [] {                               // tuning knob: index-stream CTAs per SM
             const char *e = getenv("PLANET_K1_IDX_PER_SM");
-            return e ? std::max(1, std::min(8, atoi(e))) : 6;
+            return e ? std::max(1, std::min(8, atoi(e))) : 0;
         }();
-        int idx_blocks = (int)std::min<int64_t>(nquads, (int64_t)sm_count_k1() * idx_per_sm);
+        static const bool no_bulk = getenv("PLANET_K1_NO_BULK") != nullptr;   // test knob: the per-thread-store path
         const uint32_t *strip = cached_strip(n, ni, stream);
-        if (vec4) k_tessellate_fused<4><<<quad_blocks + idx_blocks, 256, smem, stream>>>(
-                      depth, first, nquads, p->radius, d_quads, quad_blocks, n, nv, ni, d_indices, strip);
-        else      k_tessellate_fused<2><<<quad_blocks + idx_blocks, 256, smem, stream>>>(
-                      depth, first, nquads, p->radius, d_quads, quad_blocks, n, nv, ni, d_indices, strip);
+        const size_t bulk_smem = (size_t)BULK_NB * ni * sizeof(uint32_t);
+        if (vec4 && !no_bulk && bulk_smem <= 200 * 1024) {
+            // index stream as bulk copies: one 16-byte aligned request of ni*4 bytes per quad
+            static size_t configured[64] = {};                           // per device
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (bulk_smem > 48 * 1024 && bulk_smem > configured[dev & 63]) {
+                PLANET_CUDA(cudaFuncSetAttribute(k_tessellate_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem));
+                configured[dev & 63] = bulk_smem;
+            }
+            const int per_sm = idx_per_sm ? idx_per_sm : (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / bulk_smem));
+            int quad_blocks = d_quads ? (int)std::min<int64_t>((nquads + BULK_THREADS - 1) / BULK_THREADS, sm_count_k1()) : 0;
+            int idx_blocks = (int)std::min<int64_t>(nquads, (int64_t)sm_count_k1() * per_sm);
+            k_tessellate_bulk<<<quad_blocks + idx_blocks, BULK_THREADS, bulk_smem, stream>>>(
+                depth, first, nquads, p->radius, d_quads, quad_blocks, n, nv, ni, d_indices, strip);
+        } else {
+            size_t smem = (size_t)ni * sizeof(uint32_t);
+            if (smem > 48 * 1024) {
+                PLANET_CUDA(cudaFuncSetAttribute(k_tessellate_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                PLANET_CUDA(cudaFuncSetAttribute(k_tessellate_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            }
+            // indices are rebased to the caller's buffer: quad 0 of this call is vertex block 0
+            int quad_blocks = d_quads ? (int)std::min<int64_t>((nquads + 255) / 256, sm_count_k1()) : 0;
+            int idx_blocks = (int)std::min<int64_t>(nquads, (int64_t)sm_count_k1() * (idx_per_sm ? idx_per_sm : 6));
+            if (vec4) k_tessellate_fused<4><<<quad_blocks + idx_blocks, 256, smem, stream>>>(
+                          depth, first, nquads, p->radius, d_quads, quad_blocks, n, nv, ni, d_indices, strip);
+            else      k_tessellate_fused<2><<<quad_blocks + idx_blocks, 256, smem, stream>>>(
+                          depth, first, nquads, p->radius, d_quads, quad_blocks, n, nv, ni, d_indices, strip);
+        }
     }
     count_launch();
     return check_cuda(cudaGetLastError(), "tessellate launch");

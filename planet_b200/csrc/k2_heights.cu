@@ -45,6 +45,7 @@
 //    position costs 3 DFMA + one F2I per axis.
 #include "planet_common.cuh"
 #include "planet_call_surface.cuh"
+#include "planet_tma.cuh"
 
 #include <algorithm>
 
@@ -52,11 +53,7 @@
 
 namespace planet {
 
-// Fused gather (multi-GPU): besides its own buffer, a kernel can store every height straight
-// into the same position of up to 7 peers' buffers (CUDA-IPC mapped, NVLink peer stores), so the
-// all-gather of finished patches costs 7 extra store instructions per thread instead of a
-// collective after the kernel.
-struct PeerOut { float *ptr[7]; int n; };
+// (PeerOut, the fused multi-GPU gather, is declared in planet_common.cuh)
 
 // =====================================================================================
 // EXACT kernels
@@ -75,7 +72,7 @@ k_height_maps_exact(const Quad *__restrict__ quads, int64_t total, int dim, Heig
     __shared__ unsigned char s_perm[256];
     __shared__ float s_grad[48];
     stage_small_tables(s_perm, s_grad);
-    const int dim2 = dim * dim;
+    const int64_t dim2 = (int64_t)dim * dim;                          // dim <= 32768 (check_height_args)
     const double div = __ddiv_rn(1.0, (double)(dim - 3));            // main.cpp:134
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -182,6 +179,19 @@ k_noise_exact(const double *__restrict__ xyz, int64_t n, int kind, double lacuna
         else v = PerlinfBm(x, y, z, lacunarity, gain, octaves);
         out[i] = v;
     }
+}
+
+// flags[r] >= want for every rank r != rank (one thread per rank)
+__global__ void k_gather_wait(const uint32_t *flags, uint32_t want, int rank, int world, uint32_t *error)
+{
+    if ((int)threadIdx.x < world && (int)threadIdx.x != rank) gather_wait_flag(flags + threadIdx.x, want, error);
+}
+
+int launch_gather_wait(const uint32_t *flags, uint32_t want, int rank, int world, uint32_t *error, cudaStream_t stream)
+{
+    k_gather_wait<<<1, 32, 0, stream>>>(flags, want, rank, world, error);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "gather wait launch");
 }
 
 // =====================================================================================
@@ -615,17 +625,41 @@ template <int NTHREADS, int REPL, bool GATHER, int KIND>
 __global__ void __launch_bounds__(NTHREADS, REPL == 32 ? 1 : 2)
 k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, HeightCfg cfg,
                    float *__restrict__ out, int64_t nwtiles, int out_aligned8,
-                   uint64_t magic_dim, uint64_t magic_dim2, uint32_t one_bits, PeerOut peers)
+                   uint64_t magic_dim, uint64_t magic_dim2, uint32_t one_bits, PeerOut peers, int bulk_stores)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using L = Layout<REPL>;
     unsigned char *smem = tables_at<REPL>(smem_raw);
     // the peer pointers wait in shared memory until the stores: held in registers across the
-    // octave loop they cost it 14 rematerialised address adds
-    __shared__ float *s_peer[7];
-    if (GATHER && threadIdx.x < 7) s_peer[threadIdx.x] = peers.ptr[threadIdx.x];
+    // octave loop they cost it 14 rematerialised address adds.  s_peer[0] is the kernel's own
+    // buffer: destination d of a finished tile is s_peer[d], d = 0 .. peers.n
+    __shared__ float *s_peer[8];
+    if (GATHER && threadIdx.x < 8) s_peer[threadIdx.x] = threadIdx.x == 0 ? out : peers.ptr[threadIdx.x - 1];
+    if constexpr (GATHER) {
+        // the buffer this launch overwrites on the peers must have been released by them
+        // (k4_gather.cu: double-buffered gathered buffers, no host barrier inside a step)
+        if (peers.release && (int)threadIdx.x < peers.world && (int)threadIdx.x != peers.rank)
+            gather_wait_flag(peers.release + threadIdx.x, peers.release_min, peers.error);
+    }
     build_tables<REPL>(smem);
     __syncthreads();
+    // Staging for the fused gather: a finished 128-sample tile (512 B) is assembled in shared
+    // memory and leaves the SM as ONE bulk copy per destination (planet_tma.cuh) instead of a
+    // float2 store per lane per destination.  The buffers live in the slack the 32 KB alignment
+    // of the tables leaves in front of (or behind) them: two per warp when it is large enough
+    // (always, in practice: the dynamic array starts ~1 KB into the shared window), else one.
+    float *stage = nullptr;
+    int stage_bufs = 0;
+    if constexpr (GATHER) {
+        const uint32_t front = (uint32_t)(smem - smem_raw);
+        const uint32_t back = (uint32_t)(PLANET_K2_ALIGN ? L::P1_BYTES : 0) - front;
+        const uint32_t per_warp = WTILE * sizeof(float);
+        unsigned char *region = front >= back ? smem_raw : smem + L::TABLES + (NTHREADS / 32) * MAX_WTILE_QUADS * sizeof(TileQuad);
+        const uint32_t room = front >= back ? front : back;
+        stage_bufs = bulk_stores ? (int)min(2u, room / ((NTHREADS / 32) * per_warp)) : 0;
+        region += (16u - ((uint32_t)__cvta_generic_to_shared(region) & 15u)) & 15u;
+        stage = reinterpret_cast<float *>(region) + (threadIdx.x >> 5) * stage_bufs * WTILE;
+    }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int WARPS = NTHREADS / 32;
@@ -670,11 +704,12 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
         *reinterpret_cast<float2 *>(out + o) = h2;
         if constexpr (GATHER) {
 #pragma unroll
-            for (int r = 0; r < 7; r++)                              // NVLink peer stores (fused gather)
-                if (r < peers.n) __stcs(reinterpret_cast<float2 *>(((float *volatile *)s_peer)[r] + o), h2);
+            for (int r = 0; r < 7; r++)                              // NVLink peer stores (tiles the bulk path cannot take)
+                if (r < peers.n) __stcs(reinterpret_cast<float2 *>(((float *volatile *)s_peer)[r + 1] + o), h2);
         }
     };
 
+    int buf = 0;                                                     // staging buffer of the fused gather in use
     while (wt < wt_end) {
         const int64_t base = wt * WTILE;
         const int n_here = (int)min((int64_t)WTILE, total - base);           // samples in this warp tile
@@ -728,6 +763,30 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
                 float value[S];
                 positions_regular(r, p);
                 fractal_loop<REPL, S, false>(tab, p, oct, octaves, KIND, cfg.gain, one_bits, value);
+                if constexpr (GATHER) {
+                    if (stage_bufs) {
+                        // fused gather: the tile is assembled in the warp's staging buffer and pushed to
+                        // every destination (this GPU + the peers over NVLink) by lanes 0 .. n, one
+                        // 512-byte bulk copy each
+                        float *sb = stage + buf * WTILE;
+                        *reinterpret_cast<float2 *>(sb + (t & (SUB - 1)) * (32 * S) + lane * S) =
+                            make_float2(value[0] * cfg.height_scale, value[1] * cfg.height_scale);
+                        if ((t & (SUB - 1)) == SUB - 1) {
+                            tma::fence_smem_writes();
+                            __syncwarp();
+                            if (lane <= peers.n) {
+                                float *dst = ((float *volatile *)s_peer)[lane] + (o - lane * S - (SUB - 1) * 32 * S);
+                                tma::store_bulk(dst, sb, WTILE * sizeof(float));
+                                tma::commit();
+                                // the buffer written next was handed over one tile ago (two buffers) / just now (one)
+                                if (stage_bufs == 2) tma::wait_read<1>(); else tma::wait_read<0>();
+                            }
+                            buf ^= stage_bufs - 1;
+                            __syncwarp();
+                        }
+                        continue;
+                    }
+                }
                 store_pair(o, value);
             }
             wt += run;
@@ -798,7 +857,7 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
                         if constexpr (GATHER) {
 #pragma unroll
                             for (int r = 0; r < 7; r++)
-                                if (r < peers.n) ((float *volatile *)s_peer)[r][o + sidx] = h;
+                                if (r < peers.n) ((float *volatile *)s_peer)[r + 1][o + sidx] = h;
                         }
                     }
             }
@@ -820,6 +879,9 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
         r_base += WTILE;                                                     // the next tile of this warp
         if (small_maps) { const uint32_t dq = div_magic(r_base, magic_dim2); q_first += dq; r_base -= dq * dim2; }
         else if (r_base >= dim2) { r_base -= dim2; q_first++; }
+    }
+    if constexpr (GATHER) {
+        if (stage_bufs && lane <= peers.n) tma::wait_all<0>();               // every pushed tile has been written
     }
 }
 
@@ -975,12 +1037,13 @@ int launch_height_maps_gathered(const planet_gpu_params *p, const Quad *d_quads,
     HeightCfg cfg = make_cfg(p, max_depth);
     int64_t total = nquads * (int64_t)dim * dim;
     if (total == 0) return 0;
-    int max_oct = octaves_for(cfg.fixed_octaves, 31, max_depth > 0 ? max_depth : 1);
-    if (cfg.fixed_octaves <= 0) max_oct = 6 + 12 * 31 / (max_depth > 0 ? max_depth : 1);
-    bool use_fast = p->precision == PLANET_PRECISION_FAST &&
-                    fast_applicable(cfg.lacunarity, cfg.fixed_octaves > 0 ? cfg.fixed_octaves : 32) &&
-                    (cfg.fixed_octaves > 0 || max_depth >= 12);   // 6 + 12*31/max_depth <= 32
-    (void)max_oct;
+    // FAST needs every octave's window inside the 64-bit fixed-point word (<= 32 octaves) and the
+    // magic-number row division exact (dim^3 < 2^40).  The quads live on the device, so the octave
+    // bound is taken at the deepest id the 5-bit depth field can hold (main.cpp:27): with the
+    // reference's max_depth = 18 that is 6 + 12*31/18 = 26.  Anything else runs EXACT on the GPU.
+    const int max_oct = octaves_for(cfg.fixed_octaves, 31, max_depth != 0 ? max_depth : 1);
+    bool use_fast = p->precision == PLANET_PRECISION_FAST && dim <= 8192 &&
+                    fast_applicable(cfg.lacunarity, max_oct);
     if (use_fast) {
         int rc = prepare_fast();
         if (rc) return rc;
@@ -989,10 +1052,13 @@ int launch_height_maps_gathered(const planet_gpu_params *p, const Quad *d_quads,
         const uint64_t m1 = (one40 + dim - 1) / dim, m2 = (one40 + (uint64_t)dim * dim - 1) / ((uint64_t)dim * dim);
         int al = (reinterpret_cast<uintptr_t>(d_out) & 7) == 0;
         for (int r = 0; r < peers.n; r++) al = al && (reinterpret_cast<uintptr_t>(peers.ptr[r]) & 7) == 0;
-        const bool gather = peers.n > 0, ridged = cfg.kind == PLANET_NOISE_RIDGED;
+        const bool gather = peers.n > 0 || peers.release != nullptr, ridged = cfg.kind == PLANET_NOISE_RIDGED;
         uint32_t one_bits = fast::ONE_BITS;
         PeerOut peers_arg = peers;
-        void *args[] = { (void *)&d_quads, &total, &dim, &cfg, (void *)&d_out, &nwtiles, &al, (void *)&m1, (void *)&m2, &one_bits, &peers_arg };
+        // tiles leave the SM as 512-byte bulk copies when every destination is 16-byte aligned
+        int bulk = gather && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && !getenv("PLANET_K2_NO_BULK");
+        for (int r = 0; r < peers.n; r++) bulk = bulk && (reinterpret_cast<uintptr_t>(peers.ptr[r]) & 15) == 0;
+        void *args[] = { (void *)&d_quads, &total, &dim, &cfg, (void *)&d_out, &nwtiles, &al, (void *)&m1, (void *)&m2, &one_bits, &peers_arg, &bulk };
         auto launch_fast = [&](const void *kern, int grid, int threads, size_t smem, cudaStream_t st) -> int {
             return check_cuda(cudaLaunchKernel(kern, dim3(grid), dim3(threads), args, smem, st), "height map kernel launch");
         };
@@ -1011,12 +1077,14 @@ int launch_height_maps_gathered(const planet_gpu_params *p, const Quad *d_quads,
         // EXACT arithmetic, large batch: same roundings on the replicated tables (1 CTA per SM)
         int rc = prepare_fast();
         if (rc) return rc;
+        if (peers.release) { rc = launch_gather_wait(peers.release, peers.release_min, peers.rank, peers.world, peers.error, stream); if (rc) return rc; }
         constexpr int NT = 1024;
         const uint64_t m1 = ((1ull << 40) + dim - 1) / dim;
         int grid = (int)std::min<int64_t>((total + NT - 1) / NT, sm_count());
         auto kern = peers.n > 0 ? fast::k_height_maps_exact_tab<NT, true> : fast::k_height_maps_exact_tab<NT, false>;
         kern<<<grid, NT, fast::smem_bytes<32>(0), stream>>>(d_quads, total, dim, cfg, d_out, m1, peers);
     } else {
+        if (peers.release) { int rc = launch_gather_wait(peers.release, peers.release_min, peers.rank, peers.world, peers.error, stream); if (rc) return rc; }
         int64_t blocks = (total + 255) / 256;
         int grid = (int)std::min<int64_t>(blocks, (int64_t)sm_count() * 8);
         k_height_maps_exact<<<grid, 256, 0, stream>>>(d_quads, total, dim, cfg, d_out, peers);

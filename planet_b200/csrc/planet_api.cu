@@ -15,7 +15,6 @@ namespace planet {
 
 // launchers (k1_tessellate.cu, k2_heights.cu, k3_shade.cu)
 int launch_height_maps(const planet_gpu_params *, const Quad *, int64_t, int, int, float *, cudaStream_t);
-struct PeerOut { float *ptr[7]; int n; };
 int launch_height_maps_gathered(const planet_gpu_params *, const Quad *, int64_t, int, int, float *, const PeerOut &, cudaStream_t);
 int launch_heights_at(const planet_gpu_params *, const double *, int64_t, int, int, float *, cudaStream_t);
 int launch_height_map_seam(const planet_gpu_params *, const Quad *, int, int, float *, cudaStream_t);
@@ -132,6 +131,7 @@ static int check_height_args(const planet_gpu_params *p, int dim, int max_depth)
     int rc = validate_params(p);
     if (rc) return rc;
     if (dim <= 3) return set_error(PLANET_E_INVALID, "dim %d <= 3 (main.cpp:128 asserts dim > 3)", dim);
+    if (dim > 32768) return set_error(PLANET_E_UNSUPPORTED, "dim %d > 32768 (a single map would exceed 4 GiB)", dim);
     if (p->fixed_octaves <= 0 && max_depth == 0)
         return set_error(PLANET_E_INVALID, "max_depth == 0 divides by zero at main.cpp:827");
     return 0;
@@ -451,6 +451,7 @@ int planet_gpu_tessellate_uniform(const planet_gpu_params *p, int depth, int64_t
     if (first < 0 || nquads < 0 || first + nquads > leaves)
         return set_error(PLANET_E_INVALID, "leaf range [%lld, %lld) outside [0, %lld)", (long long)first,
                          (long long)(first + nquads), (long long)leaves);
+    if (nquads > 0 && !d_quads && !d_indices) return set_error(PLANET_E_INVALID, "both d_quads and d_indices are NULL");
     return launch_tessellate_uniform(p, depth, first, nquads, (Quad *)d_quads, d_indices, (cudaStream_t)stream);
 }
 

@@ -94,9 +94,44 @@ struct HeightCfg {
 };
 
 HeightCfg make_cfg(const planet_gpu_params *p, int max_depth);
+
+// Fused gather (multi-GPU, K4): besides its own buffer a height-map kernel can store every finished
+// tile straight into the same position of up to 7 peers' buffers (CUDA-IPC mapped, the stores
+// travel over NVLink), so the all-gather of finished patches rides under the arithmetic instead of
+// being a collective after the kernel.  `release` (optional): flags in LOCAL memory, one per rank,
+// that the peers bump when they are done READING the buffer this launch is about to overwrite
+// (k4_gather.cu); the kernel waits for release[r] >= release_min for every peer r before it
+// computes.  `error`: set to 1 if that wait times out (a peer died); the kernel then runs on.
+struct PeerOut {
+    float *ptr[7];
+    int n;
+    const uint32_t *release;
+    uint32_t release_min;
+    int rank, world;
+    uint32_t *error;
+};
 int validate_params(const planet_gpu_params *p);
 
 #ifdef __CUDACC__
+// Spin until a flag another GPU writes into this GPU's memory reaches `want` (wrap-safe compare).
+// Bounded: after ~2 s without progress the peer is taken for dead, *error is set and the caller
+// runs on (a hung kernel would take the whole box with it).
+__device__ __forceinline__ void gather_wait_flag(const uint32_t *flag, uint32_t want, uint32_t *error)
+{
+    uint64_t t0 = 0;
+    for (uint32_t spins = 0;; spins++) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int32_t)(v - want) >= 0) return;
+        if ((spins & 1023u) == 1023u) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (!t0) t0 = now;
+            else if (now - t0 > 2000000000ull) { if (error) atomicExch(error, 1u); return; }
+        }
+    }
+}
+
 // =====================================================================================
 // exact arithmetic: unfused IEEE ops, in the reference's evaluation order
 // =====================================================================================

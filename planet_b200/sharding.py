@@ -2,8 +2,10 @@
 
 Every height map carries its own 1-texel border (main.cpp:135-141) and depends only on its
 104-byte Quad, so ranks take contiguous leaf ranges and never exchange anything while computing.
-The only collective is the optional gather of finished patches into one buffer; it runs on
-torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+The only exchange is the gather of finished patches into one buffer on every rank (K4).  On GPUs
+that is the C++ gather object behind the C-ABI (PatchGather below: NCCL + CUDA IPC + the fused
+K2 kernel); `gather_patches` is the same exchange on torch.distributed for the CPU (gloo) tests
+of the host-side logic."""
 import torch
 import torch.distributed as dist
 
@@ -43,84 +45,89 @@ def gather_patches(local, n_units=None):
     return torch.cat([out[r * cmax:r * cmax + c] for r, c in enumerate(all_counts)])
 
 
-class PeerGather:
-    """All-gather of finished patches by direct peer writes over NVLink, overlapped with compute.
+class PatchGather:
+    """K4 through the C-ABI (planet_gpu_gather_*, csrc/k4_gather.cu): every rank's finished height
+    maps in one buffer on every rank.  The C++ side owns everything -- NCCL communicator, CUDA IPC
+    mappings of the peers' buffers, the GPU-to-GPU arrival / release flags; this class only hands
+    the 128-byte NCCL unique id from rank 0 to the others over the existing process group (any
+    transport would do: the C++ test driver uses a file) and wraps the calls.
 
-    Every rank owns a full-size `gathered` buffer; the buffers are mapped into all ranks of the
-    node through CUDA IPC.  As soon as a chunk of a rank's shard is finished on the compute
-    stream, `push()` enqueues one device-to-device copy per peer on a side stream (copy engines,
-    no SM time), so the transfer of chunk c runs under the kernels of chunk c+1.  `finish()`
-    drains the side stream and synchronises the ranks.  Same result as one NCCL all-gather at the
-    end, without the serial 0.8 ms (8 GPUs, 67 MB shards).
+        g = PatchGather(n_quads_total, dim)                 # collective
+        g.height_maps(quads_of_my_shard, first_quad, max_depth, params)   # K2 + gather, stream-ordered
+        ... K3 on g.local(first_quad, n) ...
+        g.wait(release=True)                                 # the whole buffer is complete on this rank
+        full = g.gathered()                                  # float32[n_quads_total, dim, dim] view
+        g.close()                                            # collective
     """
 
-    def __init__(self, shard_shape, dtype=torch.float32, device=None):
-        if not dist.is_initialized():
-            raise RuntimeError("PeerGather needs an initialised process group")
-        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+    def __init__(self, n_quads, dim, n_buffers=2, device=None):
+        import ctypes as C
+        from . import lib, PlanetGpuError
+        self.L, self.C = lib(), C
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.n_quads, self.dim, self.n_buffers = n_quads, dim, n_buffers
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.shard_rows = shard_shape[0]
-        full = (self.world * shard_shape[0],) + tuple(shard_shape[1:])
-        self.gathered = torch.empty(full, dtype=dtype, device=self.device)
-        # exchange IPC handles of the gathered buffers
-        handle = self.gathered.untyped_storage()._share_cuda_()
-        handles = [None] * self.world
-        dist.all_gather_object(handles, handle)
-        self.peers = []
-        for r, h in enumerate(handles):
-            if r == self.rank:
-                self.peers.append(self.gathered)
-                continue
-            storage = torch.UntypedStorage._new_shared_cuda(*((self.device.index,) + tuple(h[1:])))
-            t = torch.empty(0, dtype=dtype, device=self.device).set_(storage, 0, full)
-            self.peers.append(t)
-        # one side stream per peer so copies to different peers use different copy engines / links
-        self.side = [torch.cuda.Stream(device=self.device) for _ in range(max(self.world - 1, 1))]
-        dist.barrier()
+        uid = None
+        if self.world > 1:
+            box = [None]
+            if self.rank == 0:
+                buf = C.create_string_buffer(128)
+                rc = self.L.planet_gpu_gather_unique_id(buf)
+                box[0] = bytes(buf.raw) if rc == 0 else self.L.planet_gpu_last_error().decode()
+            dist.broadcast_object_list(box, src=0)
+            if not isinstance(box[0], bytes):
+                raise PlanetGpuError("planet_gpu_gather_unique_id: " + str(box[0]))
+            uid = C.create_string_buffer(box[0], 128)
+        self.bytes = n_quads * dim * dim * 4
+        self.handle = self.L.planet_gpu_gather_create(uid, self.rank, self.world, self.bytes, n_buffers)
+        if not self.handle:
+            raise PlanetGpuError("planet_gpu_gather_create: " + self.L.planet_gpu_last_error().decode())
+
+    def _check(self, rc):
+        from . import _check
+        _check(rc)
+
+    def _view(self, which):
+        """float32[n_quads, dim, dim] tensor over gathered buffer `which` (memory owned by the C++ side)."""
+        ptr = self.L.planet_gpu_gather_buffer(self.handle, which)
+        n = self.n_quads * self.dim * self.dim
+        iface = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        holder = type("GatherView", (), {"__cuda_array_interface__": iface})()
+        return torch.as_tensor(holder, device=self.device).view(self.n_quads, self.dim, self.dim)
+
+    def gathered(self, which=None):
+        return self._view(self.L.planet_gpu_gather_last_buffer(self.handle) if which is None else which)
+
+    def local(self, first_quad, n, which=None):
+        return self.gathered(which)[first_quad:first_quad + n]
+
+    def height_maps(self, quads, first_quad, max_depth, params, stream=None):
+        """K2 with the gather fused in for this rank's quads (int64[n, 13] device tensor)."""
+        from . import _stream
+        self._check(self.L.planet_gpu_gather_height_maps(self.handle, self.C.byref(params), quads.data_ptr(), quads.shape[0],
+                                                         first_quad, self.dim, max_depth, _stream(stream)))
+
+    def wait(self, release=True, stream=None):
+        from . import _stream
+        self._check(self.L.planet_gpu_gather_wait(self.handle, 1 if release else 0, _stream(stream)))
+
+    def nccl(self, spans, which=0, stream=None):
+        """The plain collective on data already in the local buffer: spans = [(first_quad, n_quads)] per rank."""
+        from . import _stream
+        per = self.dim * self.dim * 4
+        off = (self.C.c_int64 * self.world)(*[lo * per for lo, _ in spans])
+        size = (self.C.c_int64 * self.world)(*[n * per for _, n in spans])
+        self._check(self.L.planet_gpu_gather_nccl(self.handle, which, off, size, _stream(stream)))
+
+    def barrier(self, stream=None):
+        from . import _stream
+        self._check(self.L.planet_gpu_gather_barrier(self.handle, _stream(stream)))
+
+    def check(self):
+        self._check(self.L.planet_gpu_gather_error(self.handle))
 
     def close(self):
-        """Drop the mappings of the peers' buffers before the owning processes go away."""
-        torch.cuda.synchronize(self.device)
-        dist.barrier()
-        self.peers = []
-        dist.barrier()
-
-    def my_rows(self):
-        lo = self.rank * self.shard_rows
-        return lo, lo + self.shard_rows
-
-    def local_shard(self):
-        """The slice of this rank's own gathered buffer that its kernels should write into."""
-        lo, hi = self.my_rows()
-        return self.gathered[lo:hi]
-
-    def peer_shards(self):
-        """This rank's shard inside every PEER's gathered buffer (for kernels that store to peers
-        themselves, e.g. planet_gpu_generate_height_maps_gathered)."""
-        lo, hi = self.my_rows()
-        return [self.peers[(self.rank + k) % self.world][lo:hi] for k in range(1, self.world)]
-
-    def push(self, row_lo, row_hi, compute_stream=None):
-        """Rows [row_lo, row_hi) of the local shard are complete on `compute_stream`: copy them into
-        every peer's gathered buffer on the side stream."""
-        compute_stream = compute_stream or torch.cuda.current_stream(self.device)
-        ev = torch.cuda.Event()
-        ev.record(compute_stream)
-        lo, _ = self.my_rows()
-        src = self.gathered[lo + row_lo: lo + row_hi]
-        for k in range(1, self.world):                          # staggered: rank r's k-th stream feeds peer r+k
-            r = (self.rank + k) % self.world
-            st = self.side[k - 1]
-            st.wait_event(ev)
-            with torch.cuda.stream(st):
-                self.peers[r][lo + row_lo: lo + row_hi].copy_(src, non_blocking=True)
-
-    def finish(self, compute_stream=None):
-        compute_stream = compute_stream or torch.cuda.current_stream(self.device)
-        for st in self.side:
-            ev = torch.cuda.Event()
-            ev.record(st)
-            compute_stream.wait_event(ev)
-        torch.cuda.synchronize(self.device)
-        dist.barrier()                                          # every peer's writes into my buffer have landed
-        return self.gathered
+        if self.handle:
+            self.L.planet_gpu_gather_destroy(self.handle)
+            self.handle = None
