@@ -244,6 +244,23 @@ def run_ours(args, rank, local_rank, world):
     def k1():
         pb._check(L.planet_gpu_tessellate_uniform(pp, DEPTH, lo, nq, quads.data_ptr(), indices.data_ptr(), sp))
 
+    # N > 1: K1 in its two independent halves -- the quads first (K2 needs them), the index stream
+    # (pure HBM writes) on a side stream beside K3, whose share of the NVLink pushes leaves HBM idle
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    side_p = C.c_void_p(side.cuda_stream) if side is not None else None
+    # K3 pushes every n-th map (0: K2 pushes all).  Worth it only where the step is NVLink-bound: every GPU
+    # receives (N-1)/N of 403 MB at ~660 GB/s while K2 computes its 1/N of the planet at ~39 Gvert/s, so the
+    # transfer outlasts K2 from N = 6 up (8 GPUs: 0.53 ms against 0.32 ms) and is hidden under it below
+    nvlink_ms = (Q - nq) * DIM * DIM * 4 / 660e9 * 1e3
+    k2_ms_est = nq * DIM * DIM / 39e9 * 1e3
+    shade_share = int(os.environ.get("PLANET_GATHER_SHADE_SHARE", "2" if nvlink_ms > k2_ms_est else "0"))
+
+    def k1_quads():
+        pb._check(L.planet_gpu_tessellate_uniform(pp, DEPTH, lo, nq, quads.data_ptr(), None, sp))
+
+    def k1_indices():
+        pb._check(L.planet_gpu_tessellate_uniform(pp, DEPTH, lo, nq, None, indices.data_ptr(), side_p))
+
     def k2(out):
         pb._check(L.planet_gpu_generate_height_maps(pp, quads.data_ptr(), nq, DIM, MAX_LOD, out.data_ptr(), sp))
 
@@ -265,23 +282,36 @@ def run_ours(args, rank, local_rank, world):
         """One step; with `marks`, CUDA events on the launching stream around every kernel."""
         e = [ev() for _ in range(5)] if marks is not None else None
         if e: e[0].record()
-        k1()
-        if e: e[1].record()
         if gather is None:
+            k1()
+            if e: e[1].record()
             k2(heights)
             if e: e[2].record()
             k3(heights)
             if e: e[3].record(); e[4].record()
         else:
-            # K2 + K4: compute, push every finished tile to all GPUs, signal the peers
+            fork = torch.cuda.Event()
+            fork.record(stream)
+            k1_quads()
+            if e: e[1].record()
+            # K2 + K4: compute, push finished tiles to all GPUs as bulk copies (the share left to K3 excepted)
             pb._check(L.planet_gpu_gather_height_maps(gather.handle, pp, quads.data_ptr(), nq, lo, DIM, MAX_LOD, sp))
             if e: e[2].record()
-            k3(shard_ptr[L.planet_gpu_gather_last_buffer(gather.handle)])   # shade this rank's patches while the peers' maps land
+            side.wait_event(fork)
+            k1_indices()                                                    # beside K3, on the side stream
+            join = torch.cuda.Event()
+            join.record(side)
+            # K3 on this rank's patches (maps read from the gathered buffer) + its share of the pushes + signal
+            pb._check(L.planet_gpu_gather_shade(gather.handle, pp, quads.data_ptr(), nq, lo, camv, -1.0,
+                                                pos.data_ptr(), nrm.data_ptr(), sp))
+            stream.wait_event(join)
             if e: e[3].record()
             pb._check(L.planet_gpu_gather_wait(gather.handle, 1, sp))       # every peer's shard is in this rank's buffer; release it
             if e: e[4].record()
         if e: marks.append(e)
 
+    if gather is not None:
+        pb._check(L.planet_gpu_gather_set_shade_share(gather.handle, shade_share))
     for _ in range(warmup):
         step()
     barrier()
@@ -411,7 +441,7 @@ def run_ours(args, rank, local_rank, world):
         verts_rank = nq * DIM * DIM
         total_verts = Q * DIM * DIM
         k2_tf = verts_rank * FLOP_PER_VERTEX / (ms_k2 * 1e-3) / 1e12
-        k1_bytes = nq * 104 + nq * ni * 4
+        k1_bytes = nq * 104 + (nq * ni * 4 if world == 1 else 0)         # N > 1: the timed K1 segment is the quads half
         k3_write = nq * nv * 32
         k3_hbm = k3_write + nq * 104 + (0 if world == 1 else verts_rank * 4)   # cold reads; see roofline_k3.note
         k3_alg = k3_write + nq * 104 + verts_rank * 4
@@ -420,14 +450,16 @@ def run_ours(args, rank, local_rank, world):
         config.update({"quads_per_gpu": nq, "vertices_per_gpu": verts_rank, "precision": "FAST",
                        "l2": "256 MiB buffer written between timed steps (L2 flush)",
                        "step": "K1 tessellate + K2 heights + K3 shade" if world == 1 else
-                               "K1 tessellate + K2 heights with K4 fused (bulk copies to every peer over NVLink) + K3 shade + wait for the peers' shards"})
+                               "K1 quads + K2 heights with K4 fused (bulk copies to every peer over NVLink) + K3 shade with its share of "
+                               "K4 (K1's index stream beside it) + wait for the peers' shards"})
         line = {
             "metric": METRIC, "value": total_verts / (ms_step * 1e-3), "unit": "vertices/s",
             "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config,
-            "ms": {"k1_tessellate": ms_k1, "k2_heights" if world == 1 else "k2_heights_with_gather": ms_k2,
-                   "k3_shade": ms_k3, "wait_for_peers": ms_wait, "k2_heights_exact_mode": ms_k2_exact},
+            "ms": ({"k1_tessellate": ms_k1, "k2_heights": ms_k2, "k3_shade": ms_k3, "k2_heights_exact_mode": ms_k2_exact} if world == 1 else
+                   {"k1_quads": ms_k1, "k2_heights_with_gather": ms_k2, "k3_shade_with_gather_and_k1_indices_beside_it": ms_k3,
+                    "wait_for_peers": ms_wait}),
             "parity": {"fast_vs_exact_max_abs_m": fast_err, "tolerance_m": fast_tol},
             # the dominant kernel; at N > 1 its duration includes the NVLink pushes it is fused with
             "roofline": {"kernel": "k_height_maps_fast<768,32,gather=%d,kind=fBm>" % (world > 1), "bound": "fp32",
@@ -482,16 +514,22 @@ def run_ours(args, rank, local_rank, world):
                 "single_thread_value": one_v, "single_thread_sample": f"1024 quads x {DIM}^2, {one_s:.2f} s wall",
                 "same_bytes_as_gpu_exact_mode": same_bytes}
         else:
+            line.pop("roofline_k1")                                          # the timed K1 segment at N > 1 is the quads half only
             line["e2e"]["per_rank_ms"] = [float(x) for x in per_rank[:, 5]]
             line["per_rank_step_ms"] = [float(x) for x in per_rank[:, 0]]
             gather_bytes_in = (Q - nq) * DIM * DIM * 4                       # what every GPU must receive per step
             line["gather"] = {
-                "method": "fused into K2: every finished 128-sample tile is one 512-byte bulk copy (cp.async.bulk) to this GPU's "
-                          "buffer and to the same offset of every peer's CUDA-IPC-mapped buffer over NVLink; arrival and "
-                          "release are flags written GPU to GPU, two gathered buffers, no host barrier in the step",
+                "method": "fused into K2 and K3: K2 sends every finished 128-sample tile as one 512-byte bulk copy (cp.async.bulk) to "
+                          "this GPU's buffer and to the same offset of every peer's CUDA-IPC-mapped buffer over NVLink; "
+                          f"every {shade_share}-th map is left to K3, which sends it as one 4 KB bulk copy per peer from the "
+                          "shared-memory copy it shades from; arrival and release are flags written GPU to GPU, two gathered "
+                          "buffers, no host barrier in the step",
+                "shade_share": shade_share,
                 "bytes_received_per_gpu": gather_bytes_in,
-                "nvlink_floor_ms": gather_bytes_in / 770e9 * 1e3,
-                "nvlink_floor_note": "bytes every GPU must receive / 770 GB/s per direction (measured peer copy, B200_PROFILING.md)",
+                "nvlink_floor_ms": gather_bytes_in / 660e9 * 1e3,
+                "nvlink_floor_note": "bytes every GPU must receive / 660 GB/s: what this box's NVLink sustains per direction when all "
+                                     "GPUs push to all peers with no arithmetic in the way (profiles/r02l_push_only_8gpu.txt; one "
+                                     "GPU pushing alone: 700, copy engines all-to-all: 480)",
                 "identical_to_nccl_all_gather": nccl_bad == 0.0,
                 "identical_to_single_gpu_buffer": single_bad == 0.0,
                 "compute_only": {"ms_per_step": compute_ms, "value": total_verts / (compute_ms * 1e-3),

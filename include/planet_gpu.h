@@ -140,6 +140,25 @@ int   planet_gpu_gather_last_buffer(const void *gather);           /* buffer the
  * peers.  Stream-ordered, no host synchronisation. */
 int   planet_gpu_gather_height_maps(void *gather, const planet_gpu_params *p, const planet_gpu_quad *d_quads,
                                     int64_t nquads, int64_t first_quad, int dim, int max_depth, void *stream);
+/* Spreading the NVLink transfer over K2 AND K3: with every >= 2, planet_gpu_gather_height_maps leaves
+ * every `every`-th map to the shade kernel, which stages each map in shared memory anyway and sends
+ * those as one 4 KB bulk copy per peer (0 = off: K2 pushes everything).  planet_gpu_gather_shade is
+ * planet_gpu_shade for the quads of the preceding gather_height_maps, reading their maps from the
+ * gathered buffer; when a share was left to it, it pushes it and signals the peers (so it MUST
+ * follow every gather_height_maps while a share is set). */
+int   planet_gpu_gather_set_shade_share(void *gather, int every);
+int   planet_gpu_gather_shade(void *gather, const planet_gpu_params *p, const planet_gpu_quad *d_quads, int64_t nquads,
+                              int64_t first_quad, const double *cam_pos, float max_skirt, float *d_pos4, float *d_nrm4,
+                              void *stream);
+/* The same exchange by the copy engines, for callers that want the transfer to run under the
+ * kernels that FOLLOW K2 as well: begin (next buffer; waits, stream-ordered, for the peers' release
+ * of it), then any kernels that write bytes of planet_gpu_gather_buffer(g, last_buffer) on
+ * `stream`, each followed by push (those bytes go to the same offset of every peer's buffer, one
+ * cudaMemcpyAsync per peer on the gather's own streams, ordered behind `stream` by an event), then
+ * publish (each peer is signalled as soon as its copies are done), then planet_gpu_gather_wait. */
+int   planet_gpu_gather_begin(void *gather, void *stream);
+int   planet_gpu_gather_push(void *gather, int64_t offset_bytes, int64_t size_bytes, void *stream);
+int   planet_gpu_gather_publish(void *gather);
 /* stream-ordered wait until every peer's shard of the last step has landed in this rank's buffer;
  * release != 0 also tells the peers this rank is done reading it (they may overwrite it n_buffers
  * steps later).  A peer that does not signal within 2 s sets an error (planet_gpu_gather_error). */

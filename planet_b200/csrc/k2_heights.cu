@@ -756,6 +756,11 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
             const int octaves = tq[0].octaves;
             uint32_t r = r_base + (uint32_t)(lane * S);
             int64_t o = base + lane * S;                                     // even
+            // (fused gather) maps left to the shade kernel's push are only stored locally
+            bool push_this_quad = true;
+            if constexpr (GATHER)
+                if (stage_bufs && peers.k3_every > 0)
+                    push_this_quad = !shade_pushes_quad(peers.quad0 + q_first, peers.k3_every);
 #pragma unroll 1
             for (int t = 0; t < run * SUB; t++, r += 32 * S, o += 32 * S) {
                 Fixed3 p[S];
@@ -764,7 +769,7 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
                 positions_regular(r, p);
                 fractal_loop<REPL, S, false>(tab, p, oct, octaves, KIND, cfg.gain, one_bits, value);
                 if constexpr (GATHER) {
-                    if (stage_bufs) {
+                    if (stage_bufs && push_this_quad) {
                         // fused gather: the tile is assembled in the warp's staging buffer and pushed to
                         // every destination (this GPU + the peers over NVLink) by lanes 0 .. n, one
                         // 512-byte bulk copy each
@@ -784,6 +789,10 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
                             buf ^= stage_bufs - 1;
                             __syncwarp();
                         }
+                        continue;
+                    }
+                    if (stage_bufs) {                                        // this quad's map travels from the shade kernel
+                        *reinterpret_cast<float2 *>(out + o) = make_float2(value[0] * cfg.height_scale, value[1] * cfg.height_scale);
                         continue;
                     }
                 }
@@ -1029,6 +1038,22 @@ int launch_height_maps(const planet_gpu_params *p, const Quad *d_quads, int64_t 
 {
     PeerOut none = {};
     return launch_height_maps_gathered(p, d_quads, nquads, dim, max_depth, d_out, none, stream);
+}
+
+// does a gathered launch with these arguments push its tiles as bulk copies (the FAST kernel on the
+// replicated tables, every destination 16-byte aligned)?  Only then can part of the pushing be
+// left to the shade kernel (PeerOut::k3_every).
+bool height_maps_push_in_bulk(const planet_gpu_params *p, int64_t nquads, int dim, int max_depth, const float *d_out,
+                              const PeerOut &peers)
+{
+    HeightCfg cfg = make_cfg(p, max_depth);
+    const int64_t total = nquads * (int64_t)dim * dim;
+    const int max_oct = octaves_for(cfg.fixed_octaves, 31, max_depth != 0 ? max_depth : 1);
+    bool ok = p->precision == PLANET_PRECISION_FAST && dim <= 8192 && fast_applicable(cfg.lacunarity, max_oct) &&
+              total > k2_small_max() && !(dim & 1) && (dim * dim) % fast::WTILE == 0 &&
+              (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && !getenv("PLANET_K2_NO_BULK");
+    for (int r = 0; r < peers.n; r++) ok = ok && (reinterpret_cast<uintptr_t>(peers.ptr[r]) & 15) == 0;
+    return ok;
 }
 
 int launch_height_maps_gathered(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads, int dim,

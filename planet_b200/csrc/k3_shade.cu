@@ -29,6 +29,7 @@
 // With the quad's own height map the sampler coordinate of main.cpp:358 is the centre of
 // texel (vx+1, vy+1), so GL_LINEAR filtering (render.cpp:429-430) is a direct read.
 #include "planet_common.cuh"
+#include "planet_tma.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -111,11 +112,14 @@ __device__ __forceinline__ float sample_bilinear(const float *tex, int dim, floa
 // STAGE: height map staged in shared memory (else taps read global via L1).
 // RECT:  each quad reads its map through a texrect (pool slot + corners + pixel size) with
 //        bilinear filtering -- the cache / parent-fallback path (main.cpp:191-237, 334-346, 358).
-template <bool STAGE, bool RECT>
+// PUSH:  (fused multi-GPU gather, K4) the staged map of every k3_every-th quad is also sent to the
+//        peers' gathered buffers, one bulk copy of the whole map per peer (planet_tma.cuh): the
+//        share of the NVLink transfer the height-map kernel left to this one (PeerOut::k3_every).
+template <bool STAGE, bool RECT, bool PUSH = false>
 __global__ void __launch_bounds__(THREADS)
 k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, double cam_y, double cam_z,
         const float *__restrict__ heights, const planet_gpu_texrect *__restrict__ rects, float max_skirt,
-        float4 *__restrict__ pos4, float4 *__restrict__ nrm4, int warp_smem_bytes)
+        float4 *__restrict__ pos4, float4 *__restrict__ nrm4, int warp_smem_bytes, PeerOut peers = PeerOut())
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int dim = n + 2, dim2 = dim * dim, w = n + 2, nv = n * n + 4 * n;
@@ -129,6 +133,8 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
     const double div = __ddiv_rn(1.0, (double)(n - 1));              // main.cpp:404
     const unsigned magic_w = (unsigned)(((1ull << 32) + (unsigned)w - 1) / (unsigned)w);   // ceil(2^32 / w)
 
+    __shared__ float *s_peer[7];                                     // PUSH: the peers' buffers (indexed by lane below)
+    if (PUSH && threadIdx.x < 7) s_peer[threadIdx.x] = peers.ptr[threadIdx.x];
     for (int i = threadIdx.x; i < n; i += blockDim.x)                // UV.x / UV.y values, main.cpp:406-420
         s_uv[i] = __double2float_rn(__dmul_rn((double)i, div));
     __syncthreads();
@@ -149,6 +155,10 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
             c.n = f3((float)nd.x, (float)nd.y, (float)nd.z);
             s_corner[lane] = c;
         }
+        if (PUSH) {                                                  // the previous pushed map has left shared memory
+            if (lane < peers.n) tma::wait_read<0>();
+            __syncwarp();
+        }
         if (STAGE) {
             if ((dim2 & 3) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0) {
                 const float4 *H4 = reinterpret_cast<const float4 *>(H);
@@ -156,6 +166,16 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
                     reinterpret_cast<float4 *>(s_h)[i] = __ldcs(H4 + i);
             } else {
                 for (int i = lane; i < dim2; i += 32) s_h[i] = __ldcs(H + i);
+            }
+        }
+        if (PUSH) {
+            if (shade_pushes_quad(peers.quad0 + qi, peers.k3_every)) {
+                tma::fence_smem_writes();
+                __syncwarp();
+                if (lane < peers.n) {
+                    tma::store_bulk(s_peer[lane] + qi * dim2, s_h, (uint32_t)dim2 * 4u);
+                    tma::commit();
+                }
             }
         }
         __syncwarp();
@@ -259,13 +279,35 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
             }
         }
     }
+    if (PUSH) { if (lane < peers.n) tma::wait_all<0>(); }
 }
 
 } // namespace shade
 
+int launch_shade_push(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads, const double *cam,
+                      const float *d_heights, const planet_gpu_texrect *d_rects, float max_skirt, float *d_pos4,
+                      float *d_nrm4, const PeerOut *peers, cudaStream_t stream);
+
 int launch_shade(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads, const double *cam,
                  const float *d_heights, const planet_gpu_texrect *d_rects, float max_skirt, float *d_pos4,
                  float *d_nrm4, cudaStream_t stream)
+{
+    return launch_shade_push(p, d_quads, nquads, cam, d_heights, d_rects, max_skirt, d_pos4, d_nrm4, nullptr, stream);
+}
+
+// can the shade kernel push maps for the fused gather (map staged in shared memory, 16-byte granular)?
+bool shade_can_push(const planet_gpu_params *p, const float *d_heights)
+{
+    const int n = p->patch_verts, dim = n + 2, np = (n + 31) & ~31;
+    if (n < 2 || n > 254) return false;
+    const size_t col_bytes = 128 + (size_t)shade::COL_STRIDE * np * sizeof(float);
+    return col_bytes + (size_t)dim * dim * sizeof(float) <= 200 * 1024 && (dim * dim) % 4 == 0 &&
+           (reinterpret_cast<uintptr_t>(d_heights) & 15) == 0;
+}
+
+int launch_shade_push(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads, const double *cam,
+                      const float *d_heights, const planet_gpu_texrect *d_rects, float max_skirt, float *d_pos4,
+                      float *d_nrm4, const PeerOut *peers, cudaStream_t stream)
 {
     if (nquads == 0) return 0;
     const int n = p->patch_verts;
@@ -291,13 +333,18 @@ int launch_shade(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads
         PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev & 63] = smem;
     }
     int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(6, 2048 / (warps * 32)), budget / smem));
     if (const char *e = getenv("PLANET_K3_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));   // tuning knob
     int grid = (int)std::min<int64_t>((nquads + warps - 1) / warps, (int64_t)sms * per_sm);
     float4 *pos = reinterpret_cast<float4 *>(d_pos4), *nrm = reinterpret_cast<float4 *>(d_nrm4);
-    if (d_rects)
+    if (peers && peers->n > 0 && peers->k3_every > 0) {
+        if (d_rects || !stage) return set_error(PLANET_E_UNSUPPORTED, "shade kernel cannot push this map layout");
+        shade::k_shade<true, false, true><<<grid, warps * 32, smem, stream>>>(
+            d_quads, nquads, n, cam[0], cam[1], cam[2], d_heights, nullptr, max_skirt, pos, nrm, (int)per_warp, *peers);
+    } else if (d_rects)
         shade::k_shade<true, true><<<grid, warps * 32, smem, stream>>>(
             d_quads, nquads, n, cam[0], cam[1], cam[2], d_heights, d_rects, max_skirt, pos, nrm, (int)per_warp);
     else if (stage)

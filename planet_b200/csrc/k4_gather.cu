@@ -34,6 +34,10 @@ namespace planet {
 
 int launch_height_maps_gathered(const planet_gpu_params *, const Quad *, int64_t, int, int, float *, const PeerOut &, cudaStream_t);
 int launch_gather_wait(const uint32_t *, uint32_t, int, int, uint32_t *, cudaStream_t);
+bool height_maps_push_in_bulk(const planet_gpu_params *, int64_t, int, int, const float *, const PeerOut &);
+bool shade_can_push(const planet_gpu_params *, const float *);
+int launch_shade_push(const planet_gpu_params *, const Quad *, int64_t, const double *, const float *,
+                      const planet_gpu_texrect *, float, float *, float *, const PeerOut *, cudaStream_t);
 
 namespace {
 
@@ -120,8 +124,16 @@ struct Gather {
     ncclComm_t comm = nullptr;
     char *base = nullptr;               // [flags | buffer 0 | buffer 1]
     char *peer_base[8] = {};            // the peers' allocations mapped here; peer_base[rank] == base
-    uint32_t step = 0;                  // fused gathers issued so far
+    uint32_t step = 0;                  // gathers issued so far (fused or copy-engine)
     int last_buffer = 0;
+    // copy-engine path: one stream per peer and a ring of events that order the copies behind the
+    // kernels of the caller's stream
+    int k3_every = 0;                   // > 0: the shade kernel pushes every k3_every-th quad (planet_gpu_gather_set_shade_share)
+    PeerOut pending = {};               // the peers of the step whose shade-kernel share is still to be pushed
+    bool shade_pending = false;
+    cudaStream_t push_stream[7] = {};
+    cudaEvent_t ring[32] = {};
+    int ring_at = 0;
 
     float *buffer(int r, int b) const { return reinterpret_cast<float *>(peer_base[r] + FLAG_BYTES + (size_t)b * stride); }
     uint32_t *flags(int r) const { return reinterpret_cast<uint32_t *>(peer_base[r]); }
@@ -178,6 +190,8 @@ void *planet_gpu_gather_create(const void *id, int rank, int world, int64_t byte
         char msg[400];
         snprintf(msg, sizeof msg, "%s", planet_gpu_last_error());
         for (int r = 0; r < 8; r++) if (r != g->rank && g->peer_base[r]) cudaIpcCloseMemHandle(g->peer_base[r]);
+        for (auto &st : g->push_stream) if (st) cudaStreamDestroy(st);
+        for (auto &e : g->ring) if (e) cudaEventDestroy(e);
         if (g->base) cudaFree(g->base);
         if (g->comm) nccl_api().CommDestroy(g->comm);
         delete g;
@@ -212,6 +226,10 @@ void *planet_gpu_gather_create(const void *id, int rank, int world, int64_t byte
             if (check_cuda(cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return fail("peer mapping");
             g->peer_base[r] = (char *)p;
         }
+        for (int k = 0; k < world - 1; k++)
+            if (check_cuda(cudaStreamCreateWithFlags(&g->push_stream[k], cudaStreamNonBlocking), "push stream")) return fail("streams");
+        for (auto &e : g->ring)
+            if (check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event")) return fail("events");
         if (nccl_barrier(g, nullptr)) return fail("barrier");            // every rank has mapped every buffer
     }
     return g;
@@ -229,6 +247,8 @@ void planet_gpu_gather_destroy(void *gather)
     for (int r = 0; r < g->world; r++)
         if (r != g->rank && g->peer_base[r]) cudaIpcCloseMemHandle(g->peer_base[r]);
     if (g->world > 1) nccl_barrier(g, nullptr);
+    for (auto &st : g->push_stream) if (st) cudaStreamDestroy(st);
+    for (auto &e : g->ring) if (e) cudaEventDestroy(e);
     if (g->base) cudaFree(g->base);
     if (g->comm) nccl_api().CommDestroy(g->comm);
     delete g;
@@ -272,6 +292,16 @@ int planet_gpu_gather_height_maps(void *gather, const planet_gpu_params *p, cons
         peers.rank = g->rank; peers.world = g->world;
         peers.error = g->flags(g->rank) + FLAG_ERROR;
     }
+    // part of the pushing may be left to the shade kernel (planet_gpu_gather_shade must then follow)
+    g->shade_pending = false;
+    peers.quad0 = first_quad;
+    if (g->world > 1 && g->k3_every > 1 && nquads > 0 && dim == p->patch_verts + 2 &&
+        height_maps_push_in_bulk(p, nquads, dim, max_depth, g->buffer(g->rank, b) + off, peers) &&
+        shade_can_push(p, g->buffer(g->rank, b) + off)) {
+        peers.k3_every = g->k3_every;
+        g->pending = peers;
+        g->shade_pending = true;
+    }
     if (nquads > 0) {
         rc = launch_height_maps_gathered(p, (const Quad *)d_quads, nquads, dim, max_depth, g->buffer(g->rank, b) + off, peers, stream);
         if (rc) return rc;
@@ -279,12 +309,103 @@ int planet_gpu_gather_height_maps(void *gather, const planet_gpu_params *p, cons
         rc = launch_gather_wait(peers.release, peers.release_min, g->rank, g->world, peers.error, stream);
         if (rc) return rc;
     }
-    if (g->world > 1) {
+    if (g->world > 1 && !g->shade_pending) {
         k_gather_signal<<<1, 32, 0, stream>>>(g->peer_flags(), FLAG_ARRIVE + g->rank, step);
         count_launch();
         PLANET_CUDA(cudaGetLastError());
     }
     return 0;
+}
+
+int planet_gpu_gather_set_shade_share(void *gather, int every)
+{
+    Gather *g = (Gather *)gather;
+    if (!g || every < 0 || every == 1) return set_error(PLANET_E_INVALID, "gather_set_shade_share(%d): 0 (off) or >= 2", every);
+    g->k3_every = every;
+    return 0;
+}
+
+// K3 for the quads of the last planet_gpu_gather_height_maps, reading their maps from the gathered
+// buffer; pushes the share of the maps that call left to it, then signals the peers
+int planet_gpu_gather_shade(void *gather, const planet_gpu_params *p, const planet_gpu_quad *d_quads, int64_t nquads,
+                            int64_t first_quad, const double *cam_pos, float max_skirt, float *d_pos4, float *d_nrm4,
+                            void *stream_)
+{
+    Gather *g = (Gather *)gather;
+    if (!g) return set_error(PLANET_E_INVALID, "gather is NULL");
+    if (!ensure_init()) return PLANET_E_NO_DEVICE;
+    int rc = validate_params(p);
+    if (rc) return rc;
+    if (!cam_pos || nquads < 0 || (nquads > 0 && !d_quads)) return set_error(PLANET_E_INVALID, "NULL argument");
+    const int dim = p->patch_verts + 2;
+    const size_t texels = (size_t)dim * dim;
+    if (first_quad < 0 || (size_t)(first_quad + nquads) * texels * sizeof(float) > g->bytes)
+        return set_error(PLANET_E_INVALID, "quads [%lld, %lld) outside the gathered buffer", (long long)first_quad, (long long)(first_quad + nquads));
+    if (g->shade_pending && g->pending.quad0 != first_quad)
+        return set_error(PLANET_E_INVALID, "gather_shade must cover the quads of the preceding gather_height_maps");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (max_skirt < 0.0f) max_skirt = planet_gpu_max_skirt_size(p->radius, p->patch_verts);
+    const float *maps = g->buffer(g->rank, g->last_buffer) + (size_t)first_quad * texels;
+    rc = launch_shade_push(p, (const Quad *)d_quads, nquads, cam_pos, maps, nullptr, max_skirt, d_pos4, d_nrm4,
+                           g->shade_pending ? &g->pending : nullptr, stream);
+    if (rc) return rc;
+    if (g->shade_pending) {
+        g->shade_pending = false;
+        k_gather_signal<<<1, 32, 0, stream>>>(g->peer_flags(), FLAG_ARRIVE + g->rank, g->step);
+        count_launch();
+        PLANET_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+// ---- the copy-engine path: begin / push / publish -------------------------------------------------
+// The fused kernel above couples the NVLink transfer to the arithmetic: a warp that has to wait for
+// the link cannot compute, and the transfer ends with the kernel, so nothing after K2 overlaps it.
+// Here the height-map kernels run undisturbed in chunks and every finished chunk is handed to the
+// copy engines (one cudaMemcpyAsync per peer on the gather's own streams, ordered behind the chunk
+// by an event), so the transfer also runs under the kernels that FOLLOW K2 (K3, the index stream).
+int planet_gpu_gather_begin(void *gather, void *stream_)
+{
+    Gather *g = (Gather *)gather;
+    if (!g) return set_error(PLANET_E_INVALID, "gather is NULL");
+    const uint32_t step = ++g->step;
+    g->last_buffer = (int)((step - 1) % (uint32_t)g->nbuf);
+    if (g->world > 1 && step > (uint32_t)g->nbuf)                      // the peers have released the buffer this step overwrites
+        return launch_gather_wait(g->flags(g->rank) + FLAG_RELEASE, step - (uint32_t)g->nbuf, g->rank, g->world,
+                                  g->flags(g->rank) + FLAG_ERROR, (cudaStream_t)stream_);
+    return 0;
+}
+
+int planet_gpu_gather_push(void *gather, int64_t offset_bytes, int64_t size_bytes, void *stream_)
+{
+    Gather *g = (Gather *)gather;
+    if (!g || offset_bytes < 0 || size_bytes < 0 || (size_t)(offset_bytes + size_bytes) > g->bytes)
+        return set_error(PLANET_E_INVALID, "gather_push: range outside the buffer");
+    if (g->world == 1 || size_bytes == 0) return 0;
+    cudaEvent_t ev = g->ring[g->ring_at++ & 31];
+    PLANET_CUDA(cudaEventRecord(ev, (cudaStream_t)stream_));
+    const char *src = reinterpret_cast<const char *>(g->buffer(g->rank, g->last_buffer)) + offset_bytes;
+    for (int k = 0; k < g->world - 1; k++) {
+        char *dst = reinterpret_cast<char *>(g->buffer((g->rank + 1 + k) % g->world, g->last_buffer)) + offset_bytes;
+        PLANET_CUDA(cudaStreamWaitEvent(g->push_stream[k], ev, 0));
+        PLANET_CUDA(cudaMemcpyAsync(dst, src, (size_t)size_bytes, cudaMemcpyDeviceToDevice, g->push_stream[k]));
+    }
+    return 0;
+}
+
+// every push so far has been queued: each peer is told (arrive flag) as soon as ITS copies are done
+int planet_gpu_gather_publish(void *gather)
+{
+    Gather *g = (Gather *)gather;
+    if (!g) return set_error(PLANET_E_INVALID, "gather is NULL");
+    for (int k = 0; k < g->world - 1; k++) {
+        PeerFlags one = {};
+        one.n = 1;
+        one.ptr[0] = g->flags((g->rank + 1 + k) % g->world);
+        k_gather_signal<<<1, 32, 0, g->push_stream[k]>>>(one, FLAG_ARRIVE + g->rank, g->step);
+        count_launch();
+    }
+    return check_cuda(cudaGetLastError(), "gather publish launch");
 }
 
 int planet_gpu_gather_wait(void *gather, int release, void *stream_)

@@ -95,6 +95,14 @@ struct HeightCfg {
 
 HeightCfg make_cfg(const planet_gpu_params *p, int max_depth);
 
+// Fused gather: is quad q (index in the gathered buffer) one of the 1-in-`every` whose map the shade
+// kernel pushes instead of the height-map kernel?  The q >> 2 term rotates the residue so that the
+// pushing does not always fall on the same warp of the shade kernel's 4-warp CTAs.
+__host__ __device__ inline bool shade_pushes_quad(int64_t q, int every)
+{
+    return every > 0 && ((q >> 2) + q) % every == every - 1;
+}
+
 // Fused gather (multi-GPU, K4): besides its own buffer a height-map kernel can store every finished
 // tile straight into the same position of up to 7 peers' buffers (CUDA-IPC mapped, the stores
 // travel over NVLink), so the all-gather of finished patches rides under the arithmetic instead of
@@ -109,6 +117,12 @@ struct PeerOut {
     uint32_t release_min;
     int rank, world;
     uint32_t *error;
+    // split of the pushing between K2 and K3: with k3_every > 0, quads whose index in the gathered
+    // buffer is congruent to k3_every - 1 modulo k3_every are NOT pushed by the height-map kernel;
+    // the shade kernel, which stages every map in shared memory anyway, pushes them as one 4 KB
+    // bulk copy per peer (the NVLink transfer is then spread over both kernels)
+    int64_t quad0;      // index in the gathered buffer of the launch's first quad
+    int k3_every;
 };
 int validate_params(const planet_gpu_params *p);
 

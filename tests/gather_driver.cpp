@@ -1,6 +1,6 @@
 // Multi-process test driver for K4 (planet_gpu_gather_*): one process per GPU, no Python, no torch.
 //
-//   gather_driver <world> <depth> <mode>      mode: fast | exact | ragged | nccl
+//   gather_driver <world> <depth> <mode>      mode: fast | exact | ragged | nccl | ce | split
 //
 // The parent forks `world` ranks before any CUDA call.  Rank 0 writes the NCCL unique id to a file
 // in a scratch directory, the others read it (the C-ABI leaves the transport to the caller).  The
@@ -12,7 +12,8 @@
 //   2. computes ALL quads' height maps on its own GPU with the plain K2 call;
 //   3. checks that the gathered buffer equals that buffer byte for byte (sharding and gathering
 //      are invisible in the result).
-// `nccl` does step 1 with the plain K2 call into the local buffer + planet_gpu_gather_nccl.
+// `nccl` does step 1 with the plain K2 call into the local buffer + planet_gpu_gather_nccl, `ce` with
+// planet_gpu_gather_begin / _push / _publish (chunks handed to the copy engines).
 // Exit code 0 and one line "gather ok ..." per rank on success.
 #include <cstdio>
 #include <cstdlib>
@@ -81,6 +82,38 @@ static int run_rank(int rank, int world, int depth, const std::string &mode, con
         std::vector<int64_t> off(world), size(world);
         for (int r = 0; r < world; r++) { off[r] = lo[r] * texels * 4; size[r] = (lo[r + 1] - lo[r]) * texels * 4; }
         CHECK(planet_gpu_gather_nccl(g, 0, off.data(), size.data(), stream));
+    } else if (mode == "split") {
+        // the NVLink transfer spread over K2 and K3: every 4th map travels from the shade kernel
+        float *d_pos = nullptr, *d_nrm = nullptr;
+        const int nv = planet_gpu_patch_vertex_count(params.patch_verts);
+        CUDA_OK(cudaMalloc((void **)&d_pos, sizeof(float) * 4 * nv * n));
+        CUDA_OK(cudaMalloc((void **)&d_nrm, sizeof(float) * 4 * nv * n));
+        const double cam[3] = { 0.0, 0.0, -6371010.0 };
+        CHECK(planet_gpu_gather_set_shade_share(g, 4));
+        for (int step = 0; step < 3; step++) {
+            params.seed_offset[1] = 0.25 * step;
+            CHECK(planet_gpu_gather_height_maps(g, &params, d_quads, n, first, dim, max_lod, stream));
+            CHECK(planet_gpu_gather_shade(g, &params, d_quads, n, first, cam, -1.0f, d_pos, d_nrm, stream));
+            CHECK(planet_gpu_gather_wait(g, /*release*/ 1, stream));
+        }
+        which = planet_gpu_gather_last_buffer(g);
+        CUDA_OK(cudaStreamSynchronize(stream));
+        cudaFree(d_pos); cudaFree(d_nrm);
+    } else if (mode == "ce") {
+        // the copy-engine path: plain K2 in four chunks, every finished chunk pushed to the peers
+        for (int step = 0; step < 3; step++) {
+            params.seed_offset[1] = 0.25 * step;
+            CHECK(planet_gpu_gather_begin(g, stream));
+            float *buf = planet_gpu_gather_buffer(g, planet_gpu_gather_last_buffer(g));
+            for (int c = 0; c < 4; c++) {
+                const int64_t a = n * c / 4, b = n * (c + 1) / 4;
+                CHECK(planet_gpu_generate_height_maps(&params, d_quads + a, b - a, dim, max_lod, buf + (first + a) * texels, stream));
+                CHECK(planet_gpu_gather_push(g, (first + a) * texels * 4, (b - a) * texels * 4, stream));
+            }
+            CHECK(planet_gpu_gather_publish(g));
+            CHECK(planet_gpu_gather_wait(g, /*release*/ 1, stream));
+        }
+        which = planet_gpu_gather_last_buffer(g);
     } else {
         for (int step = 0; step < 3; step++) {
             // every step computes a different terrain (seed offset), so a step satisfied by an earlier
@@ -116,7 +149,7 @@ static int run_rank(int rank, int world, int depth, const std::string &mode, con
 
 int main(int argc, char **argv)
 {
-    if (argc < 4) { fprintf(stderr, "usage: gather_driver <world> <depth> fast|exact|ragged|nccl\n"); return 2; }
+    if (argc < 4) { fprintf(stderr, "usage: gather_driver <world> <depth> fast|exact|ragged|nccl|ce|split\n"); return 2; }
     const int world = atoi(argv[1]), depth = atoi(argv[2]);
     const std::string mode = argv[3];
     char dir[] = "/tmp/planet_gather_XXXXXX";
@@ -124,7 +157,7 @@ int main(int argc, char **argv)
     std::vector<pid_t> kids;
     for (int r = 0; r < world; r++) {
         pid_t pid = fork();                                   // before any CUDA call: every rank gets a fresh context
-        if (pid == 0) _exit(run_rank(r, world, depth, mode, dir));
+        if (pid == 0) { const int code = run_rank(r, world, depth, mode, dir); fflush(stdout); fflush(stderr); _exit(code); }
         kids.push_back(pid);
     }
     int worst = 0;
