@@ -464,3 +464,62 @@ long ref_captured_buffer(long i, void *out, long cap)
 }
 
 } /* extern "C" */
+
+
+/* ------------------------------------------------------------------------- */
+/* the reference's own caller on the GPU library (-DPLANET_REAL_CALLER)        */
+/* ------------------------------------------------------------------------- */
+/* The "switch unchanged" claim, executed: this same translation unit -- the reference's main.cpp
+ * #include'd above, unmodified -- built as a PROGRAM whose HeightMapGenerator is the GPU one
+ * (planet_b200/host/planet_host.h, PLANET_HOST_NO_TYPES: the reference's own Vec3d / Quad /
+ * HeightMapGenerator are used, nothing is restated), installed exactly where main.cpp:843-847
+ * installs CreateHeightMapGenerator<Perlin>():
+ *     InitPlanet(planet, radius, hmap_gen)          main.cpp:847 -> :280, :495
+ *     RenderPlanet(planet, cam_info)                main.cpp:1087 -> :600
+ * so ProcessQuad's GetHeightAt calls (main.cpp:552, 555) and GetHeightMapForQuad's
+ * GenerateHeightMap calls (main.cpp:244) go through the two function pointers into
+ * libplanet_gpu.so.  What the reference then hands to glTexImage2D (render.cpp:426) is written to
+ * stdout: int64 leaf count, the leaf Quads (104 B each), int64 map count, the maps (w*h floats).
+ * tests/test_real_caller.py compares them with what the CPU generator produced in the
+ * reference's real main() (golden frame_quads / frame_height_maps).
+ *   usage: ref_gpu_caller [frames] [cpu]   (further frames fly 20 km east per frame, reusing the cache;
+ *                                           "cpu": the same program with the reference's CPU generator
+ *                                           installed instead -- the other side of the comparison on a box
+ *                                           that has no /root/reference and no golden for later frames)
+ */
+#ifdef PLANET_REAL_CALLER
+#define PLANET_HOST_NO_TYPES
+#include "../planet_b200/host/planet_host.h"
+
+static void write_all(const void *p, size_t n) { if (fwrite(p, 1, n, stdout) != n) exit(4); }
+
+int main(int argc, char **argv)
+{
+    const int frames = argc > 1 ? atoi(argv[1]) : 1;
+    const double radius = 6371000.0;                                   /* main.cpp:821 */
+    const bool cpu = argc > 2 && !strcmp(argv[2], "cpu");
+    HeightMapGenerator hmap_gen = cpu ? g_gen                          /* main.cpp:843 as it is */
+                                      : CreateGpuHeightMapGenerator(); /* instead of main.cpp:843 */
+    if (!hmap_gen.GenerateHeightMap || !hmap_gen.GetHeightAt) return 3;
+    static Planet planet;                                              /* zero-initialised, main.cpp:846 */
+    if (!InitPlanet(planet, radius, hmap_gen)) return 1;               /* main.cpp:847 */
+    for (int f = 0; f < frames; f++) {
+        CameraInfo cam_info = {};
+        const double a = 20000.0 * f / radius;
+        cam_info.position = V3d(sin(a) * (radius + 10.0), 0.0, -cos(a) * (radius + 10.0));   /* frame 0: main.cpp:864 */
+        cam_info.rotation = Mat3Identity();
+        InitCameraInfo(cam_info, DegToRad(50.0f), 800.0f / 600.0f, 1.0f, 20000000.0f);      /* main.cpp:1072-1075 */
+        fakegl::reset_frame();
+        RenderPlanet(planet, cam_info);                                /* main.cpp:1087 */
+        int64_t n = planet.quads.num;
+        write_all(&n, sizeof n);
+        write_all(planet.quads.data, (size_t)n * sizeof(Quad));
+        int64_t m = (int64_t)fakegl::height_maps.size();
+        write_all(&m, sizeof m);
+        for (const fakegl::HeightMap &hm : fakegl::height_maps) write_all(hm.texels.data(), hm.texels.size() * sizeof(float));
+    }
+    fflush(stdout);
+    if (!cpu) planet_gpu_shutdown();
+    return 0;
+}
+#endif
