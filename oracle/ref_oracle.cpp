@@ -463,6 +463,24 @@ long ref_captured_buffer(long i, void *out, long cap)
     return (long)b.size();
 }
 
+/* ---- vec3.h / math.h: the reference's own vector functions on arrays ---- */
+/* a, b: n x 3, t: n.  out: n x 33 = Dot, LengthSq, Length, Normalize[3], SafeNormalize[3], Cross[3],
+ * Slerp[3], a+b[3], a-b[3], a*t[3], t*a[3], a/t[3], -a[3]  (vec3.h:25-72), once per instantiation. */
+} /* extern "C" */
+template <class V, class T> static void vec3_ops(const T *a, const T *b, const T *t, long n, T *out)
+{
+    for (long i = 0; i < n; i++) {
+        V A = { a[3*i], a[3*i+1], a[3*i+2] }, B = { b[3*i], b[3*i+1], b[3*i+2] };
+        T *o = out + 33 * i;
+        V r[10] = { Normalize(A), SafeNormalize(A), Cross(A, B), Slerp(A, B, t[i]), A + B, A - B, A * t[i], t[i] * A, A / t[i], -A };
+        o[0] = Dot(A, B); o[1] = LengthSq(A); o[2] = Length(A);
+        for (int k = 0; k < 10; k++) { o[3 + 3*k] = r[k].x; o[4 + 3*k] = r[k].y; o[5 + 3*k] = r[k].z; }
+    }
+}
+extern "C" {
+void ref_vec3_ops_f32(const float *a, const float *b, const float *t, long n, float *out) { vec3_ops<Vec3, float>(a, b, t, n, out); }
+void ref_vec3_ops_f64(const double *a, const double *b, const double *t, long n, double *out) { vec3_ops<Vec3d, double>(a, b, t, n, out); }
+
 } /* extern "C" */
 
 

@@ -13,20 +13,48 @@
 // in shared memory instead (k2_heights.cu).
 #pragma once
 
+#include <cmath>
+
 #include "planet_common.cuh"
 
 #ifdef __CUDACC__
 
 // ---- vec3.h / math.h -----------------------------------------------------------------------
 // The reference instantiates one struct twice through macros ("we don't want templates"); here
-// it is one template with the reference's two names as aliases.
+// it is one template with the reference's two names as aliases.  Every product and sum is a
+// separately rounded IEEE operation, as in the reference's x86-64 build: nvcc's default
+// (-fmad=true) would contract a.x*b.x + a.y*b.y into an FMA and change the last bit of Dot, Cross
+// and everything built on them, so on the device the arithmetic goes through the _rn intrinsics
+// (which are never contracted) and the results are bit-identical to vec3.h on the host
+// (tests/test_call_surface.py runs them in a kernel against the reference's own vec3.h).
+namespace planet { namespace rn {
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ float  add(float a, float b)   { return __fadd_rn(a, b); }
+__device__ __forceinline__ float  sub(float a, float b)   { return __fsub_rn(a, b); }
+__device__ __forceinline__ float  mul(float a, float b)   { return __fmul_rn(a, b); }
+__device__ __forceinline__ float  div(float a, float b)   { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float  root(float a)           { return __fsqrt_rn(a); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double root(double a)          { return __dsqrt_rn(a); }
+#else
+template <class T> inline T add(T a, T b) { return a + b; }
+template <class T> inline T sub(T a, T b) { return a - b; }
+template <class T> inline T mul(T a, T b) { return a * b; }
+template <class T> inline T div(T a, T b) { return a / b; }
+template <class T> inline T root(T a)     { return std::sqrt(a); }
+#endif
+} }
+
 template <class T> struct TVec3
 {
     T x, y, z;
-    __host__ __device__ TVec3 &operator+=(TVec3 v) { x += v.x; y += v.y; z += v.z; return *this; }
-    __host__ __device__ TVec3 &operator-=(TVec3 v) { x -= v.x; y -= v.y; z -= v.z; return *this; }
-    __host__ __device__ TVec3 &operator*=(T s) { x *= s; y *= s; z *= s; return *this; }
-    __host__ __device__ TVec3 &operator/=(T s) { x /= s; y /= s; z /= s; return *this; }
+    __host__ __device__ TVec3 &operator+=(TVec3 v) { using namespace planet::rn; x = add(x, v.x); y = add(y, v.y); z = add(z, v.z); return *this; }
+    __host__ __device__ TVec3 &operator-=(TVec3 v) { using namespace planet::rn; x = sub(x, v.x); y = sub(y, v.y); z = sub(z, v.z); return *this; }
+    __host__ __device__ TVec3 &operator*=(T s) { using namespace planet::rn; x = mul(x, s); y = mul(y, s); z = mul(z, s); return *this; }
+    __host__ __device__ TVec3 &operator/=(T s) { using namespace planet::rn; x = div(x, s); y = div(y, s); z = div(z, s); return *this; }
 };
 typedef TVec3<float> Vec3;
 typedef TVec3<double> Vec3d;
@@ -38,24 +66,34 @@ template <class T> __host__ __device__ inline TVec3<T> operator*(T a, TVec3<T> b
 template <class T> __host__ __device__ inline TVec3<T> operator/(TVec3<T> a, T b) { return a /= b; }
 template <class T> __host__ __device__ inline TVec3<T> operator-(TVec3<T> v) { return v *= T(-1.0); }
 
-template <class T> __host__ __device__ inline T Dot(TVec3<T> a, TVec3<T> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <class T> __host__ __device__ inline T Dot(TVec3<T> a, TVec3<T> b)                         // vec3.h:46: (x + y) + z
+{
+    using namespace planet::rn;
+    return add(add(mul(a.x, b.x), mul(a.y, b.y)), mul(a.z, b.z));
+}
 template <class T> __host__ __device__ inline T LengthSq(TVec3<T> v) { return Dot(v, v); }
-template <class T> __host__ __device__ inline T Length(TVec3<T> v) { return sqrt(LengthSq(v)); }
+template <class T> __host__ __device__ inline T Length(TVec3<T> v) { return planet::rn::root(LengthSq(v)); }
 template <class T> __host__ __device__ inline TVec3<T> Normalize(TVec3<T> v) { return v / Length(v); }
 template <class T> __host__ __device__ inline TVec3<T> SafeNormalize(TVec3<T> v, T epsilon = T(0.0001))
 {
     T len2 = LengthSq(v);
     if (len2 < epsilon) return TVec3<T>{ T(0), T(0), T(0) };
-    return v / T(sqrt(len2));
+    return v / planet::rn::root(len2);
 }
 template <class T> __host__ __device__ inline TVec3<T> Cross(TVec3<T> a, TVec3<T> b)
 {
-    return TVec3<T>{ a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x };
+    using namespace planet::rn;
+    return TVec3<T>{ sub(mul(a.y, b.z), mul(a.z, b.y)), sub(mul(a.z, b.x), mul(a.x, b.z)), sub(mul(a.x, b.y), mul(a.y, b.x)) };
 }
+// vec3.h:68-72.  theta is a float whatever T is; the sines take T((1 - t) * theta).  acos and sin
+// are the device math library's here (<= 2 ulp from glibc's), so Slerp agrees with the host to a
+// few ulp, not bit for bit -- the one function of this surface with a tolerance.
 template <class T> __host__ __device__ inline TVec3<T> Slerp(TVec3<T> a, TVec3<T> b, T t)
 {
-    float theta = acos(Dot(a, b) / (Length(a) * Length(b)));        // vec3.h:70 keeps theta in float
-    return (T(sin((T(1.0) - t) * theta)) * a + T(sin(t * theta)) * b) / T(sin(theta));
+    using namespace planet::rn;
+    float theta = std::acos(div(Dot(a, b), mul(Length(a), Length(b))));
+    T th = T(theta);
+    return (T(std::sin(mul(sub(T(1.0), t), th))) * a + T(std::sin(mul(t, th))) * b) / T(std::sin(theta));      // Sin(float): the divisor is a float sine in both instantiations
 }
 __host__ __device__ inline Vec3 V3(float x, float y, float z) { return Vec3{ x, y, z }; }
 __host__ __device__ inline Vec3 V3(float s) { return Vec3{ s, s, s }; }
