@@ -241,17 +241,28 @@ typedef struct planet_gpu_texrect {
 void *planet_gpu_cache_create(int dim, int cache_max, int map_max, int extra_slots);
 void  planet_gpu_cache_destroy(void *cache);
 int   planet_gpu_cache_count(const void *cache);
-/* The reference's per-leaf loop (main.cpp:655-660) for one frame's leaf list, bookkeeping only
- * (HOST, no device needed): per quad the texrect it would draw with, in order, with the
- * reference's probe order, LRU choice, fallback rule and budget accounting
- * (generations_per_frame = 100 at main.cpp:653); *n_generate = maps that must be generated. */
-int   planet_gpu_cache_plan_frame(void *cache, const planet_gpu_quad *h_quads, int64_t n,
-                                  int generations_per_frame, planet_gpu_texrect *h_rects, int64_t *n_generate);
-/* plan + ONE batched K2 launch that generates every miss into its pool slot.  h_rects (HOST) gets
- * the texrects; d_rects (DEVICE, may be NULL) a copy for planet_gpu_shade_cached. */
+/* One frame of the reference's per-leaf loop (main.cpp:655-660 calling GetHeightMapForQuad) with
+ * the leaf quads ALREADY ON THE DEVICE (planet_gpu_select_lod's output): the bookkeeping -- the
+ * reference's probe order, LRU choice, fallback rule and budget accounting (generations_per_frame
+ * = 100 at main.cpp:653) -- runs in one kernel on device-resident tables, every miss of the frame
+ * is generated by ONE batched K2 launch into its pool slot, and d_rects (DEVICE, n entries)
+ * receives the texrect each quad draws with, for planet_gpu_shade_cached.  The host reads back two
+ * integers (*n_generated, may be NULL, and an error flag); `stream` is synchronised once for that.
+ * A frame that fails (pool exhausted, allocation or launch error) leaves the cache unchanged. */
+int   planet_gpu_cache_frame_device(void *cache, const planet_gpu_params *p, const planet_gpu_quad *d_quads,
+                                    int64_t n, int max_lod, int generations_per_frame,
+                                    planet_gpu_texrect *d_rects, int64_t *n_generated, void *stream);
+/* the same frame for a caller whose leaf list is in HOST memory: uploads the quads, runs the
+ * device frame, downloads the texrects to h_rects; d_rects (DEVICE, may be NULL) keeps a copy */
 int   planet_gpu_cache_frame(void *cache, const planet_gpu_params *p, const planet_gpu_quad *h_quads,
                              int64_t n, int max_lod, int generations_per_frame,
                              planet_gpu_texrect *h_rects, planet_gpu_texrect *d_rects, void *stream);
+/* Planning only, on the HOST (no device needed, nothing is generated): the same bookkeeping code
+ * run with one lane on a host copy of the tables, for callers that want the decisions without a
+ * GPU (capacity planning, tests).  A cache object is either planned here or driven by the two
+ * calls above, not both.  *n_generate = maps the frame would generate. */
+int   planet_gpu_cache_plan_frame(void *cache, const planet_gpu_quad *h_quads, int64_t n,
+                                  int generations_per_frame, planet_gpu_texrect *h_rects, int64_t *n_generate);
 const float *planet_gpu_cache_pool(void *cache);      /* DEVICE pointer to slot 0 */
 /* copies the maps in the given pool slots to HOST memory (n x dim x dim floats); synchronous */
 int   planet_gpu_cache_read_slots(void *cache, const int32_t *slots, int64_t n, float *h_out);

@@ -375,6 +375,15 @@ class RefOracle:
     def reset_cache(self):
         self.L.ref_reset_cache()
 
+    def cache_lookup(self, quads, budget=100, radius=RADIUS):
+        """GetHeightMapForQuad (main.cpp:191-278) over an arbitrary quad list as one frame.
+        Returns (float32[n, 8] = texture name, corners[4], pixel_size[2], generated flag; cache.count)."""
+        q = np.ascontiguousarray(quads, QUAD_DTYPE)
+        out = np.zeros((len(q), 8), np.float32)
+        self.L.ref_cache_lookup.restype = C.c_long
+        count = self.L.ref_cache_lookup(C.c_double(radius), _p(q), C.c_long(len(q)), C.c_int(budget), _p(out))
+        return out, int(count)
+
     def run_reference_main(self, scratch_dir):
         """The reference's real main() for one headless frame (its local `Perlin` functor)."""
         rc = self.L.ref_run_reference_main(scratch_dir.encode())

@@ -400,6 +400,31 @@ long ref_frame_quads(void *out, long cap)
     return n;
 }
 
+/* ---- GetHeightMapForQuad (main.cpp:191-278) on an ARBITRARY quad list, as one frame ---- */
+/* The loop of main.cpp:652-660 + :682 for a caller-chosen list (duplicates, a quad together with
+ * its parent, quads whose cached entry is evicted earlier in the same list ...): per quad, out8 =
+ * { GL texture name, corners[4], pixel_size[2], 1 if this lookup generated a map }.  The functor is
+ * switched to ConstantZero for the duration: only the bookkeeping is of interest. */
+long ref_cache_lookup(double radius, const void *quads, long n, int budget, float *out8)
+{
+    if (!ensure_planet(radius)) return -1;
+    OracleFunctorConfig saved = g_cfg; g_cfg.kind = ORACLE_ZERO;
+    const Quad *q = (const Quad *)quads;
+    int left = budget;
+    for (long i = 0; i < n; i++) {
+        fakegl::reset_frame();
+        TextureRect r = GetHeightMapForQuad(g_planet, q[i], left);
+        float *o = out8 + 8 * i;
+        o[0] = (float)r.texture;
+        o[1] = r.corners[0].x; o[2] = r.corners[0].y; o[3] = r.corners[1].x; o[4] = r.corners[1].y;
+        o[5] = r.pixel_size.x; o[6] = r.pixel_size.y;
+        o[7] = fakegl::height_maps.empty() ? 0.0f : 1.0f;
+    }
+    g_planet.render_tick++;
+    g_cfg = saved;
+    return g_planet.cache.count;
+}
+
 /* ---- the reference's real main(), one headless frame ---- */
 int ref_run_reference_main(const char *scratch_dir)
 {

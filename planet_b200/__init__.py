@@ -98,6 +98,7 @@ def lib():
             "planet_gpu_cache_count": (i, [vp]),
             "planet_gpu_cache_plan_frame": (i, [vp, vp, i64, i, vp, C.POINTER(i64)]),
             "planet_gpu_cache_frame": (i, [vp, pp, vp, i64, i, i, vp, vp, vp]),
+            "planet_gpu_cache_frame_device": (i, [vp, pp, vp, i64, i, i, vp, C.POINTER(i64), vp]),
             "planet_gpu_cache_pool": (vp, [vp]),
             "planet_gpu_cache_read_slots": (i, [vp, vp, i64, vp]),
             "planet_gpu_shade_cached": (i, [pp, vp, i64, vp, vp, vp, f, vp, vp, vp]),
@@ -128,7 +129,7 @@ EXPORTED_SYMBOLS = [
     "planet_gpu_select_lod", "planet_gpu_shade", "planet_gpu_generate_height_maps_host",
     "planet_gpu_terrain_host",
     "planet_gpu_cache_create", "planet_gpu_cache_destroy", "planet_gpu_cache_count",
-    "planet_gpu_cache_plan_frame", "planet_gpu_cache_frame", "planet_gpu_cache_pool",
+    "planet_gpu_cache_plan_frame", "planet_gpu_cache_frame", "planet_gpu_cache_frame_device", "planet_gpu_cache_pool",
     "planet_gpu_cache_read_slots", "planet_gpu_shade_cached", "planet_gpu_measure_fp32_peak",
     "planet_gpu_launch_count",
 ]
@@ -409,6 +410,18 @@ class HeightMapCache:
         _check(lib().planet_gpu_cache_frame(self.handle, C.byref(params), q.ctypes.data, len(q), max_lod,
                                             generations_per_frame, rects.ctypes.data, d_rects.data_ptr(), _stream(stream)))
         return rects, d_rects
+
+    def frame_device(self, d_quads, max_lod, params=None, generations_per_frame=100, stream=None):
+        """The frame with the leaf quads already on the device (K0's output): bookkeeping in one
+        kernel on device-resident tables + one batched K2 launch.  Returns (device texrects, maps generated)."""
+        torch = _torch()
+        params = params or default_params()
+        n = d_quads.shape[0]
+        d_rects = torch.empty((n, 8), dtype=torch.int32, device="cuda")
+        n_gen = C.c_int64(0)
+        _check(lib().planet_gpu_cache_frame_device(self.handle, C.byref(params), d_quads.data_ptr(), n, max_lod,
+                                                   generations_per_frame, d_rects.data_ptr(), C.byref(n_gen), _stream(stream)))
+        return d_rects, n_gen.value
 
     def pool_ptr(self):
         return lib().planet_gpu_cache_pool(self.handle)

@@ -1,19 +1,41 @@
 // height_map_cache.cu -- the step after the path: residency of generated
-// height maps.
+// height maps, with the decisions taken ON THE DEVICE.
 //
 // Replaces HeightMapCache / MapFind (main.cpp:75-102) and GetHeightMapForQuad
 // (main.cpp:191-278).  The reference keeps one GL texture per cached quad and, for every leaf of
 // every frame, looks the quad up, generates on a miss (32x32 map on the CPU + glTexImage2D),
 // evicts the least recently used entry beyond 1 024, and -- once the per-frame budget of 100
 // generations (main.cpp:652-653) is spent -- borrows the parent's map with remapped texture
-// corners.  Here the textures are slots of ONE device-resident pool and a whole frame is one call:
-//   * the bookkeeping (hash probe order, LRU choice, fallback rule, budget accounting) runs on the
-//     host exactly in the reference's per-quad order, so every decision is the reference's;
-//   * all misses of the frame are generated by ONE batched K2 launch (the missing quads are
-//     uploaded as one array) and one scatter kernel moves the finished maps to their pool slots;
-//   * K3 then reads each quad's map through its texrect (slot, corners, pixel size).
-// Slots freed by eviction are only reused from the next frame on, because the reference had
-// already drawn with a texture before deleting it, while here shading follows generation.
+// corners.  Here the textures are slots of ONE device-resident pool, the bookkeeping (id table,
+// slot table, last-used ticks, free-slot stack) lives in device memory, and a whole frame is:
+//
+//   k_plan_frame (one CTA)  leaf quads (device, straight from K0) -> texrects + the miss list
+//     phase 1, all warps   one warp per leaf probes the id table as it stood at the start of the
+//                          frame for the leaf and for its parent (a 32-wide compare per step);
+//     phase 2, one warp    walks the leaves in order and resolves them against what the frame has
+//                          changed so far: a probe result is still good if the table slot still
+//                          holds the id (an eviction earlier in the frame empties it), ids inserted
+//                          this frame are looked up in the frame's insertion list; a miss spends
+//                          budget, falls back to the parent or generates; an eviction is ONE
+//                          packed-key maximum over the table (age, then lowest slot) by the warp;
+//     phase 3, all warps   the missing quads are compacted into the K2 batch.
+//   K2                     ONE batched launch generates every miss (main.cpp:244 once per quad);
+//   k_scatter_maps         moves the finished maps to their pool slots;
+//   K3 (shade_cached)      reads each quad's map through its texrect.
+//
+// The host reads back two integers per frame (misses, error), no quads, no texrects.  Every
+// decision -- probe order (lo32 ^ hi32, linear, first match), who is evicted (oldest tick, lowest
+// table slot on ties), the fallback rule, the budget -- is the reference's; tests/test_cache.py
+// checks them against the reference's own GetHeightMapForQuad on a 30-frame flight with hits,
+// fallbacks and evictions.  The bookkeeping is a template over the number of cooperating lanes:
+// 32 inside the kernel, 1 for planet_gpu_cache_plan_frame, the planning-only entry that runs the
+// SAME code on a host copy of the state (no device needed; no terrain is computed there).
+//
+// A frame works on a copy of the state (two state buffers, ping-pong) and becomes current only
+// when the plan succeeded and the generation was launched: a failed frame -- pool exhausted,
+// allocation or launch error -- leaves the cache exactly as it was (no entry ever points at a
+// slot that was not generated).  Slots freed by eviction are reused from the next frame on: the
+// reference had already drawn with a texture before deleting it, here shading follows generation.
 #include "planet_common.cuh"
 
 #include <cstring>
@@ -23,102 +45,266 @@ namespace planet {
 
 int launch_height_maps(const planet_gpu_params *, const Quad *, int64_t, int, int, float *, cudaStream_t);
 
-struct Cache {
-    int dim, cache_max, map_max, pool_slots;
-    int count = 0;
-    uint32_t render_tick = 0;
-    std::vector<uint64_t> quad_ids;          // main.cpp:81
-    std::vector<int> slot_of;                // main.cpp:82: GLuint height_maps[] -> pool slot
-    std::vector<uint32_t> last_tick_used;    // main.cpp:83
-    std::vector<int> free_slots, deferred;   // deferred: freed this frame, reusable next frame
-    float *d_pool = nullptr;
-    // staging for the per-frame batch
-    Quad *d_miss_quads = nullptr; float *d_miss_maps = nullptr; int *d_miss_slots = nullptr;
-    size_t miss_cap = 0;
-    std::vector<Quad> h_miss_quads; std::vector<int> h_miss_slots;
+namespace cache {
+
+// ---- the bookkeeping state: one blob of 32-bit words, in host or device memory ---------------
+enum { H_COUNT, H_TICK, H_NFREE, H_NDEFERRED, H_NGEN, H_ERROR, H_WORDS = 8 };
+enum { ERR_POOL_EXHAUSTED = 1 };
+
+struct Shape { int dim, cache_max, map_max, pool_slots; };
+
+struct State {                 // views into one blob
+    int32_t *hdr;              // H_*
+    uint64_t *ids;             // [map_max] QuadID value, 0 = empty          (main.cpp:81)
+    int32_t *slot_of;          // [map_max] pool slot instead of a GL name   (main.cpp:82)
+    uint32_t *last_tick;       // [map_max]                                  (main.cpp:83)
+    int32_t *free_slots;       // [pool_slots] stack of unused pool slots
+    int32_t *deferred;         // [pool_slots] freed this frame, reusable next frame
+};
+__host__ __device__ inline size_t state_words(const Shape &s) { return H_WORDS + (size_t)s.map_max * 4 + (size_t)s.pool_slots * 2; }
+__host__ __device__ inline State state_at(void *blob, const Shape &s)
+{
+    int32_t *w = (int32_t *)blob;
+    State v;
+    v.hdr = w;
+    v.ids = (uint64_t *)(w + H_WORDS);                                   // 8-byte aligned: H_WORDS is even
+    v.slot_of = w + H_WORDS + 2 * s.map_max;
+    v.last_tick = (uint32_t *)(w + H_WORDS + 3 * s.map_max);
+    v.free_slots = w + H_WORDS + 4 * s.map_max;
+    v.deferred = v.free_slots + s.pool_slots;
+    return v;
+}
+
+// per-leaf scratch of one frame
+struct Scratch {
+    int32_t *own, *par;        // [n] phase-1 probe results (table index or -1)
+    int32_t *inserted;         // [n] table indices filled this frame, in order
+    int32_t *miss_src;         // [n] leaf index of the k-th generated map
+    int32_t *miss_slot;        // [n] its pool slot
 };
 
-// main.cpp:86-102 -- probes ALL map_max slots from hash(key) and returns the first whose id
-// equals `find` (find == 0 locates the first empty slot of the key's probe sequence)
-static int map_find(const Cache &c, uint64_t key, uint64_t find)
+// ---- lanes: 32 on the device (one warp), 1 on the host --------------------------------------
+template <int LANES> struct Lanes;
+template <> struct Lanes<1> {
+    static __host__ __device__ int lane() { return 0; }
+    static __host__ __device__ unsigned ballot(bool p) { return p ? 1u : 0u; }
+    static __host__ __device__ unsigned long long max64(unsigned long long v) { return v; }
+    static __host__ __device__ void sync() {}
+};
+#ifdef __CUDACC__
+template <> struct Lanes<32> {
+    static __device__ int lane() { return threadIdx.x & 31; }
+    static __device__ unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+    static __device__ unsigned long long max64(unsigned long long v)
+    {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, d);
+            v = o > v ? o : v;
+        }
+        return v;
+    }
+    static __device__ void sync() { __syncwarp(); }
+};
+#endif
+__host__ __device__ inline int first_bit(unsigned b)
 {
-    uint32_t hash = uint32_t(key) ^ uint32_t(key >> 32);
-    for (int i = 0; i < c.map_max; i++) {
-        int index = (int)((hash + (uint32_t)i) % (uint32_t)c.map_max);
-        if (c.quad_ids[index] == find) return index;
+#ifdef __CUDA_ARCH__
+    return __ffs((int)b) - 1;
+#else
+    return __builtin_ctz(b);
+#endif
+}
+
+__host__ __device__ inline uint32_t hash_of(uint64_t key) { return (uint32_t)key ^ (uint32_t)(key >> 32); }   // main.cpp:91
+
+// MapFind (main.cpp:86-102): the first table index in probe order from hash(key) whose id equals
+// `want` (want == 0: the first empty slot of the key's probe sequence); LANES slots per step.
+template <int LANES>
+__host__ __device__ inline int find(const uint64_t *ids, int map_max, uint64_t key, uint64_t want)
+{
+    const uint32_t h = hash_of(key) % (uint32_t)map_max;
+    for (int base = 0; base < map_max; base += LANES) {
+        const int i = base + Lanes<LANES>::lane();
+        uint32_t index = h + (uint32_t)i;                                // < 2 * map_max
+        if (index >= (uint32_t)map_max) index -= (uint32_t)map_max;
+        const unsigned hit = Lanes<LANES>::ballot(i < map_max && ids[index] == want);
+        if (hit) {
+            uint32_t r = h + (uint32_t)(base + first_bit(hit));
+            return (int)(r >= (uint32_t)map_max ? r - (uint32_t)map_max : r);
+        }
     }
     return -1;
 }
 
-static uint64_t parent_id(uint64_t id)                                // main.cpp:57-65
+// an id among the table slots filled earlier in this frame (there are at most n of them)
+template <int LANES>
+__host__ __device__ inline int find_inserted(const State &st, const int32_t *inserted, int n_inserted, uint64_t want)
 {
-    uint64_t depth = quad_depth(id);
-    uint64_t mask = ~(3ull << (2 * (depth - 1)));
-    return (id - (1ull << 55)) & mask;
+    for (int base = 0; base < n_inserted; base += LANES) {
+        const int j = base + Lanes<LANES>::lane();
+        const unsigned hit = Lanes<LANES>::ballot(j < n_inserted && st.ids[inserted[j]] == want);
+        if (hit) return inserted[base + first_bit(hit)];
+    }
+    return -1;
 }
-static int child_index(uint64_t id) { return (int)((id >> (2 * (quad_depth(id) - 1))) & 3); }   // main.cpp:51-55
 
-// GetHeightMapForQuad (main.cpp:191-278) for one quad; appends to the frame's miss list.
-static int plan_quad(Cache &c, const planet_gpu_quad &q, int &generations_left, planet_gpu_texrect &r)
+// the entry main.cpp:249-261 evicts: the largest tick age (signed, as there), the lowest table
+// index among equals -- one packed key (age << 32 | ~index), one maximum
+template <int LANES>
+__host__ __device__ inline int oldest(const State &st, int map_max, uint32_t tick)
 {
-    const float dim = (float)c.dim;
-    r.corners[0] = r.corners[1] = 1.5f / dim;                         // main.cpp:197
-    r.corners[2] = r.corners[3] = (dim - 1.5f) / dim;                 // main.cpp:198
-    r.pixel_size[0] = r.pixel_size[1] = 1.0f / dim;                   // main.cpp:199
-    r.flags = PLANET_TEXRECT_HIT;
-
-    int index = map_find(c, q.id, q.id);                              // main.cpp:203
-    if (index < 0) {
-        const int depth = (int)quad_depth(q.id);
-        if (generations_left <= 0 && depth > 0) {                     // main.cpp:208
-            const uint64_t pid = parent_id(q.id);
-            index = map_find(c, pid, pid);
-            if (index >= 0) {                                         // main.cpp:212-236: the child's quadrant of the parent's map
-                const int ci = child_index(q.id);
-                float x0 = 1.5f, y0 = x0, x1 = dim / 2.0f - 0.5f, y1 = x1;
-                if (ci == 1 || ci == 3) { x0 = dim / 2.0f + 0.5f; x1 = dim - 1.5f; }
-                if (ci == 2 || ci == 3) { y0 = dim / 2.0f + 0.5f; y1 = dim - 1.5f; }
-                r.corners[0] = x0 / dim; r.corners[1] = y0 / dim;
-                r.corners[2] = x1 / dim; r.corners[3] = y1 / dim;
-                r.pixel_size[0] = r.pixel_size[1] = ((dim / 2.0f - 1.0f) / (float)(c.dim - 3)) / dim;
-                r.flags = PLANET_TEXRECT_PARENT;
+    unsigned long long best = 0;
+    for (int base = 0; base < map_max; base += LANES) {
+        const int i = base + Lanes<LANES>::lane();
+        if (i < map_max && st.ids[i] != 0) {
+            const int age = (int)(tick - st.last_tick[i]);
+            if (age >= 0) {
+                const unsigned long long key = ((unsigned long long)(uint32_t)age << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)i);
+                best = key > best ? key : best;
             }
-        }
-        if (generations_left > 0 || index < 0) {                      // main.cpp:239
-            generations_left--;
-            if (c.count == c.cache_max) {                             // main.cpp:247-266: evict the least recently used
-                int lru = 0, delta_ticks = -1;
-                for (int i = 0; i < c.map_max; i++) {
-                    int delta = (int)(c.render_tick - c.last_tick_used[i]);
-                    if (c.quad_ids[i] != 0 && delta > delta_ticks) { lru = i; delta_ticks = delta; }
-                }
-                c.deferred.push_back(c.slot_of[lru]);                 // DeleteTexture, effective next frame
-                c.quad_ids[lru] = 0;
-                c.count--;
-            }
-            if (c.free_slots.empty())
-                return set_error(PLANET_E_INVALID, "height-map pool exhausted: more than %d generations in one frame "
-                                 "beyond the cache size", c.pool_slots - c.cache_max);
-            const int slot = c.free_slots.back();
-            c.free_slots.pop_back();
-            index = map_find(c, q.id, 0);                             // main.cpp:268
-            c.quad_ids[index] = q.id;
-            c.slot_of[index] = slot;
-            c.count++;
-            Quad hq;
-            memcpy(&hq, &q, sizeof hq);
-            c.h_miss_quads.push_back(hq);
-            c.h_miss_slots.push_back(slot);
-            r.flags = PLANET_TEXRECT_GENERATED;
-            // a map generated for this quad is its own: full-map corners (set above)
-            r.corners[0] = r.corners[1] = 1.5f / dim;
-            r.corners[2] = r.corners[3] = (dim - 1.5f) / dim;
-            r.pixel_size[0] = r.pixel_size[1] = 1.0f / dim;
         }
     }
-    c.last_tick_used[index] = c.render_tick;                          // main.cpp:275
-    r.slot = c.slot_of[index];
-    return 0;
+    best = Lanes<LANES>::max64(best);
+    return best ? (int)(0xFFFFFFFFu - (uint32_t)best) : 0;                // nothing qualified: slot 0, as main.cpp:249
+}
+
+__host__ __device__ inline uint64_t parent_of(uint64_t id)                // main.cpp:57-65
+{
+    return (id - (1ull << 55)) & ~(3ull << (2 * (quad_depth(id) - 1)));
+}
+
+// the texture window a quad samples: its own map (border texel excluded), or its quadrant of the
+// parent's map (main.cpp:197-199, 212-236).  Bit 0 of the child index selects the x half, bit 1
+// the y half.
+__host__ __device__ inline void window(planet_gpu_texrect &r, int dim_i, int quadrant)
+{
+    const float dim = (float)dim_i;
+    const float lo = 1.5f, hi = dim - 1.5f;
+    if (quadrant < 0) {
+        r.corners[0] = r.corners[1] = lo / dim;
+        r.corners[2] = r.corners[3] = hi / dim;
+        r.pixel_size[0] = r.pixel_size[1] = 1.0f / dim;
+        return;
+    }
+    const float below = dim / 2.0f - 0.5f, above = dim / 2.0f + 0.5f;
+    r.corners[0] = ((quadrant & 1) ? above : lo) / dim;
+    r.corners[1] = ((quadrant & 2) ? above : lo) / dim;
+    r.corners[2] = ((quadrant & 1) ? hi : below) / dim;
+    r.corners[3] = ((quadrant & 2) ? hi : below) / dim;
+    r.pixel_size[0] = r.pixel_size[1] = ((dim / 2.0f - 1.0f) / (float)(dim_i - 3)) / dim;
+}
+
+// phase 1 for one leaf: where the leaf and its parent sit in the table as the frame starts
+template <int LANES>
+__host__ __device__ inline void probe_leaf(const State &st, const Shape &sh, const planet_gpu_quad *quads, int64_t i, const Scratch &sc)
+{
+    const uint64_t id = quads[i].id;
+    const int own = find<LANES>(st.ids, sh.map_max, id, id);
+    int par = -1;
+    if (own < 0 && quad_depth(id) > 0) { const uint64_t pid = parent_of(id); par = find<LANES>(st.ids, sh.map_max, pid, pid); }
+    if (Lanes<LANES>::lane() == 0) { sc.own[i] = own; sc.par[i] = par; }
+}
+
+// phase 2: the frame's leaves in order (main.cpp:655-660 calling :191-278).  All lanes of the
+// cooperating group execute this with identical control flow; lane 0 writes.
+template <int LANES>
+__host__ __device__ inline void resolve_frame(State st, const Shape &sh, const planet_gpu_quad *quads, int64_t n, int budget,
+                                              const Scratch &sc, planet_gpu_texrect *rects)
+{
+    const bool writer = Lanes<LANES>::lane() == 0;
+    // textures deleted last frame are gone now: their slots return to the stack
+    int n_free = st.hdr[H_NFREE];
+    const int n_deferred = st.hdr[H_NDEFERRED];
+    for (int j = Lanes<LANES>::lane(); j < n_deferred; j += LANES) st.free_slots[n_free + j] = st.deferred[j];
+    n_free += n_deferred;
+    Lanes<LANES>::sync();
+    int count = st.hdr[H_COUNT], n_gen = 0, n_inserted = 0, n_evicted = 0, error = 0;
+    const uint32_t tick = (uint32_t)st.hdr[H_TICK];
+
+    for (int64_t i = 0; i < n && !error; i++) {
+        const uint64_t id = quads[i].id;
+        planet_gpu_texrect r;
+        r.flags = PLANET_TEXRECT_HIT;
+        window(r, sh.dim, -1);
+        // the leaf itself: the start-of-frame probe if that slot still holds it, else this frame's insertions
+        int index = sc.own[i];
+        if (index >= 0 && st.ids[index] != id) index = -1;
+        if (index < 0 && n_inserted) index = find_inserted<LANES>(st, sc.inserted, n_inserted, id);
+        if (index < 0) {
+            if (budget <= 0 && quad_depth(id) > 0) {                         // main.cpp:208: budget spent -> try the parent's map
+                const uint64_t pid = parent_of(id);
+                int p = sc.par[i];
+                if (p >= 0 && st.ids[p] != pid) p = -1;
+                if (p < 0 && n_inserted) p = find_inserted<LANES>(st, sc.inserted, n_inserted, pid);
+                if (p >= 0) {
+                    index = p;
+                    r.flags = PLANET_TEXRECT_PARENT;
+                    window(r, sh.dim, (int)((id >> (2 * (quad_depth(id) - 1))) & 3));   // GetChildIndex, main.cpp:51-55
+                }
+            }
+            if (budget > 0 || index < 0) {                                   // main.cpp:239: generate
+                budget--;
+                if (count == sh.cache_max) {                                 // main.cpp:247-266
+                    const int victim = oldest<LANES>(st, sh.map_max, tick);
+                    if (writer) { st.deferred[n_evicted] = st.slot_of[victim]; st.ids[victim] = 0; }
+                    n_evicted++;
+                    count--;
+                    Lanes<LANES>::sync();
+                }
+                if (n_free == 0) { error = ERR_POOL_EXHAUSTED; break; }
+                const int slot = st.free_slots[--n_free];
+                index = find<LANES>(st.ids, sh.map_max, id, 0);              // main.cpp:268: first empty slot of the probe sequence
+                if (writer) {
+                    st.ids[index] = id; st.slot_of[index] = slot;
+                    sc.inserted[n_inserted] = index;
+                    sc.miss_src[n_gen] = (int32_t)i; sc.miss_slot[n_gen] = slot;
+                }
+                n_inserted++; n_gen++; count++;
+                r.flags = PLANET_TEXRECT_GENERATED;
+                window(r, sh.dim, -1);                                       // a generated map is the quad's own
+                Lanes<LANES>::sync();
+            }
+        }
+        if (writer) {
+            st.last_tick[index] = tick;                                      // main.cpp:275
+            r.slot = st.slot_of[index];
+            rects[i] = r;
+        }
+        Lanes<LANES>::sync();
+    }
+    if (writer) {
+        st.hdr[H_COUNT] = count; st.hdr[H_TICK] = (int32_t)(tick + 1);       // main.cpp:682
+        st.hdr[H_NFREE] = n_free; st.hdr[H_NDEFERRED] = n_evicted;
+        st.hdr[H_NGEN] = n_gen; st.hdr[H_ERROR] = error;
+    }
+}
+
+// ---- the device frame -----------------------------------------------------------------
+constexpr int PLAN_THREADS = 1024;
+
+__global__ void __launch_bounds__(PLAN_THREADS)
+k_plan_frame(const int32_t *__restrict__ cur, int32_t *__restrict__ next, Shape sh, const planet_gpu_quad *__restrict__ quads,
+             int64_t n, int budget, Scratch sc, planet_gpu_texrect *__restrict__ rects, Quad *__restrict__ miss_quads)
+{
+    // the frame works on a copy; the host makes it current when the frame went through
+    const size_t words = state_words(sh);
+    for (size_t w = threadIdx.x; w < words; w += PLAN_THREADS) next[w] = cur[w];
+    __syncthreads();
+    const State st = state_at(next, sh);
+    const int warp = threadIdx.x >> 5;
+    for (int64_t i = warp; i < n; i += PLAN_THREADS / 32) probe_leaf<32>(st, sh, quads, i, sc);
+    __syncthreads();
+    if (warp == 0) resolve_frame<32>(st, sh, quads, n, budget, sc, rects);
+    __syncthreads();
+    // the K2 batch: the missing quads, compacted (13 eight-byte words each)
+    const int n_gen = st.hdr[H_ERROR] ? 0 : st.hdr[H_NGEN];
+    const uint64_t *src = reinterpret_cast<const uint64_t *>(quads);
+    uint64_t *dst = reinterpret_cast<uint64_t *>(miss_quads);
+    for (int w = threadIdx.x; w < n_gen * 13; w += PLAN_THREADS) {
+        const int k = w / 13, part = w - k * 13;
+        dst[w] = src[(size_t)sc.miss_src[k] * 13 + part];
+    }
 }
 
 __global__ void k_scatter_maps(const float *__restrict__ maps, const int *__restrict__ slots, int n, int texels,
@@ -134,24 +320,131 @@ __global__ void k_scatter_maps(const float *__restrict__ maps, const int *__rest
     }
 }
 
+struct Cache {
+    Shape sh;
+    enum { UNUSED, HOST_PLANNED, DEVICE_PLANNED } mode = UNUSED;
+    int count = 0;                           // host copy of H_COUNT after the last successful frame
+    // planning-only mode: the state in host memory (two copies, like the device)
+    std::vector<int32_t> h_state[2];
+    std::vector<int32_t> h_scratch;
+    // device mode
+    int32_t *d_state[2] = { nullptr, nullptr };
+    int current = 0;
+    float *d_pool = nullptr;
+    int32_t *d_scratch = nullptr; Quad *d_miss_quads = nullptr; planet_gpu_quad *d_quads = nullptr; planet_gpu_texrect *d_rects = nullptr;
+    size_t leaf_cap = 0;
+    float *d_miss_maps = nullptr; size_t miss_cap = 0;
+    int32_t *h_hdr = nullptr;                // pinned: the two integers a frame reads back
+};
+
+static void fresh_state(const Shape &sh, int32_t *blob)
+{
+    memset(blob, 0, state_words(sh) * sizeof(int32_t));
+    State st = state_at(blob, sh);
+    for (int k = 0; k < sh.map_max; k++) st.slot_of[k] = -1;
+    for (int k = 0; k < sh.pool_slots; k++) st.free_slots[k] = sh.pool_slots - 1 - k;   // slot 0 is handed out first
+    st.hdr[H_NFREE] = sh.pool_slots;
+}
+
+static Scratch scratch_at(int32_t *base, size_t n)
+{
+    return Scratch{ base, base + n, base + 2 * n, base + 3 * n, base + 4 * n };
+}
+
+static int latch(Cache *c, int mode)
+{
+    if (c->mode == Cache::UNUSED) c->mode = (decltype(c->mode))mode;
+    if (c->mode != mode)
+        return set_error(PLANET_E_INVALID, "this cache is already %s: planet_gpu_cache_plan_frame (host bookkeeping only) and "
+                         "planet_gpu_cache_frame / _frame_device (device bookkeeping) keep separate states",
+                         c->mode == Cache::HOST_PLANNED ? "planned on the host" : "planned on the device");
+    return 0;
+}
+
+static int pool_exhausted(const Cache *c)
+{
+    return set_error(PLANET_E_INVALID, "height-map pool exhausted: more than %d generations in one frame beyond the cache size "
+                     "(the frame was dropped, the cache is unchanged)", c->sh.pool_slots - c->sh.cache_max);
+}
+
+static int ensure_device(Cache *c, int64_t n)
+{
+    if (!ensure_init()) return PLANET_E_NO_DEVICE;
+    if (!c->d_state[0]) {
+        const size_t bytes = state_words(c->sh) * sizeof(int32_t);
+        std::vector<int32_t> init(state_words(c->sh));
+        fresh_state(c->sh, init.data());
+        PLANET_CUDA(cudaMalloc(&c->d_state[0], bytes));
+        PLANET_CUDA(cudaMalloc(&c->d_state[1], bytes));
+        PLANET_CUDA(cudaMemcpy(c->d_state[0], init.data(), bytes, cudaMemcpyHostToDevice));
+        PLANET_CUDA(cudaMallocHost(&c->h_hdr, H_WORDS * sizeof(int32_t)));
+        c->current = 0;
+    }
+    if (!c->d_pool) PLANET_CUDA(cudaMalloc(&c->d_pool, (size_t)c->sh.pool_slots * c->sh.dim * c->sh.dim * sizeof(float)));
+    if ((size_t)n > c->leaf_cap) {
+        cudaFree(c->d_scratch); cudaFree(c->d_miss_quads); cudaFree(c->d_quads); cudaFree(c->d_rects);   // cudaFree(nullptr) is a no-op
+        c->d_scratch = nullptr; c->d_miss_quads = nullptr; c->d_quads = nullptr; c->d_rects = nullptr; c->leaf_cap = 0;
+        const size_t want = (size_t)n + 1024;
+        PLANET_CUDA(cudaMalloc(&c->d_scratch, want * 5 * sizeof(int32_t)));
+        PLANET_CUDA(cudaMalloc(&c->d_miss_quads, want * sizeof(Quad)));
+        PLANET_CUDA(cudaMalloc(&c->d_quads, want * sizeof(planet_gpu_quad)));
+        PLANET_CUDA(cudaMalloc(&c->d_rects, want * sizeof(planet_gpu_texrect)));
+        c->leaf_cap = want;
+    }
+    return 0;
+}
+
+// plan on the device, generate the misses, make the frame current.  d_quads / d_rects: device.
+static int frame_on_device(Cache *c, const planet_gpu_params *p, const planet_gpu_quad *d_quads, int64_t n, int max_lod,
+                           int budget, planet_gpu_texrect *d_rects, int64_t *n_generated, cudaStream_t stream)
+{
+    int rc = ensure_device(c, n);
+    if (rc) return rc;
+    const Scratch sc = scratch_at(c->d_scratch, c->leaf_cap);
+    int32_t *cur = c->d_state[c->current], *next = c->d_state[c->current ^ 1];
+    k_plan_frame<<<1, PLAN_THREADS, 0, stream>>>(cur, next, c->sh, d_quads, n, budget, sc, d_rects, c->d_miss_quads);
+    count_launch();
+    PLANET_CUDA(cudaGetLastError());
+    PLANET_CUDA(cudaMemcpyAsync(c->h_hdr, next, H_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    PLANET_CUDA(cudaStreamSynchronize(stream));                          // the frame's one read-back: misses, error
+    if (c->h_hdr[H_ERROR]) return pool_exhausted(c);
+    const int64_t n_gen = c->h_hdr[H_NGEN];
+    const int texels = c->sh.dim * c->sh.dim;
+    if (n_gen > 0) {
+        if ((size_t)n_gen > c->miss_cap) {
+            cudaFree(c->d_miss_maps);
+            c->d_miss_maps = nullptr; c->miss_cap = 0;
+            PLANET_CUDA(cudaMalloc(&c->d_miss_maps, ((size_t)n_gen + 256) * texels * sizeof(float)));
+            c->miss_cap = (size_t)n_gen + 256;
+        }
+        rc = launch_height_maps(p, c->d_miss_quads, n_gen, c->sh.dim, max_lod, c->d_miss_maps, stream);
+        if (rc) return rc;
+        k_scatter_maps<<<(int)std::min<int64_t>(n_gen, 1184), 128, 0, stream>>>(c->d_miss_maps, sc.miss_slot, (int)n_gen, texels, c->d_pool);
+        count_launch();
+        PLANET_CUDA(cudaGetLastError());
+    }
+    c->current ^= 1;                                                     // the frame went through
+    c->count = c->h_hdr[H_COUNT];
+    if (n_generated) *n_generated = n_gen;
+    return 0;
+}
+
+} // namespace cache
 } // namespace planet
 
 using namespace planet;
+using namespace planet::cache;
 
 extern "C" {
 
 void *planet_gpu_cache_create(int dim, int cache_max, int map_max, int extra_slots)
 {
-    if (dim <= 3 || cache_max <= 0 || map_max < cache_max || extra_slots < 0) {
-        set_error(PLANET_E_INVALID, "cache_create(dim=%d, cache_max=%d, map_max=%d, extra=%d)", dim, cache_max, map_max, extra_slots);
+    if (dim <= 3 || cache_max <= 0 || map_max <= cache_max || extra_slots < 0 || map_max > (1 << 24) || cache_max + (int64_t)extra_slots > (1 << 24)) {
+        set_error(PLANET_E_INVALID, "cache_create(dim=%d, cache_max=%d, map_max=%d, extra=%d): need dim > 3, 0 < cache_max < map_max", dim, cache_max, map_max, extra_slots);
         return nullptr;
     }
     Cache *c = new Cache();
-    c->dim = dim; c->cache_max = cache_max; c->map_max = map_max; c->pool_slots = cache_max + extra_slots;
-    c->quad_ids.assign(map_max, 0);
-    c->slot_of.assign(map_max, -1);
-    c->last_tick_used.assign(map_max, 0);
-    for (int s = c->pool_slots - 1; s >= 0; s--) c->free_slots.push_back(s);
+    c->sh = Shape{ dim, cache_max, map_max, cache_max + extra_slots };
     return c;
 }
 
@@ -159,10 +452,9 @@ void planet_gpu_cache_destroy(void *cache)
 {
     Cache *c = (Cache *)cache;
     if (!c) return;
-    if (c->d_pool) cudaFree(c->d_pool);
-    if (c->d_miss_quads) cudaFree(c->d_miss_quads);
-    if (c->d_miss_maps) cudaFree(c->d_miss_maps);
-    if (c->d_miss_slots) cudaFree(c->d_miss_slots);
+    cudaFree(c->d_state[0]); cudaFree(c->d_state[1]); cudaFree(c->d_pool); cudaFree(c->d_scratch);
+    cudaFree(c->d_miss_quads); cudaFree(c->d_quads); cudaFree(c->d_rects); cudaFree(c->d_miss_maps);
+    if (c->h_hdr) cudaFreeHost(c->h_hdr);
     delete c;
 }
 
@@ -172,31 +464,34 @@ int planet_gpu_cache_plan_frame(void *cache, const planet_gpu_quad *h_quads, int
                                 planet_gpu_texrect *h_rects, int64_t *n_generate)
 {
     Cache *c = (Cache *)cache;
-    if (!c || (n > 0 && (!h_quads || !h_rects))) return set_error(PLANET_E_INVALID, "NULL argument");
-    // textures deleted last frame are gone now
-    for (int s : c->deferred) c->free_slots.push_back(s);
-    c->deferred.clear();
-    c->h_miss_quads.clear();
-    c->h_miss_slots.clear();
-    int left = generations_per_frame;                                // main.cpp:653
-    for (int64_t i = 0; i < n; i++) {                                 // main.cpp:655-660, in leaf order
-        int rc = plan_quad(*c, h_quads[i], left, h_rects[i]);
-        if (rc) return rc;
+    if (!c || n < 0 || (n > 0 && (!h_quads || !h_rects))) return set_error(PLANET_E_INVALID, "NULL argument");
+    int rc = latch(c, Cache::HOST_PLANNED);
+    if (rc) return rc;
+    const size_t words = state_words(c->sh);
+    if (c->h_state[0].empty()) {
+        c->h_state[0].resize(words); c->h_state[1].resize(words);
+        fresh_state(c->sh, c->h_state[0].data());
+        c->current = 0;
     }
-    c->render_tick++;                                                 // main.cpp:682
-    if (n_generate) *n_generate = (int64_t)c->h_miss_quads.size();
+    // the same three phases as k_plan_frame, one lane
+    int32_t *cur = c->h_state[c->current].data(), *next = c->h_state[c->current ^ 1].data();
+    memcpy(next, cur, words * sizeof(int32_t));
+    c->h_scratch.resize((size_t)n * 5 + 1);
+    const Scratch sc = scratch_at(c->h_scratch.data(), (size_t)n);
+    const State st = state_at(next, c->sh);
+    for (int64_t i = 0; i < n; i++) probe_leaf<1>(st, c->sh, h_quads, i, sc);
+    resolve_frame<1>(st, c->sh, h_quads, n, generations_per_frame, sc, h_rects);
+    if (st.hdr[H_ERROR]) return pool_exhausted(c);
+    c->current ^= 1;
+    c->count = st.hdr[H_COUNT];
+    if (n_generate) *n_generate = st.hdr[H_NGEN];
     return 0;
 }
 
 const float *planet_gpu_cache_pool(void *cache)
 {
     Cache *c = (Cache *)cache;
-    if (!c) return nullptr;
-    if (!c->d_pool) {
-        if (!ensure_init()) return nullptr;
-        size_t bytes = (size_t)c->pool_slots * c->dim * c->dim * sizeof(float);
-        if (check_cuda(cudaMalloc(&c->d_pool, bytes), "cache pool")) return nullptr;
-    }
+    if (!c || ensure_device(c, 0)) return nullptr;
     return c->d_pool;
 }
 
@@ -205,13 +500,25 @@ int planet_gpu_cache_read_slots(void *cache, const int32_t *slots, int64_t n, fl
     Cache *c = (Cache *)cache;
     if (!c || !slots || !h_out) return set_error(PLANET_E_INVALID, "NULL argument");
     if (!planet_gpu_cache_pool(cache)) return PLANET_E_CUDA;
-    const size_t texels = (size_t)c->dim * c->dim;
+    const size_t texels = (size_t)c->sh.dim * c->sh.dim;
     PLANET_CUDA(cudaDeviceSynchronize());
     for (int64_t i = 0; i < n; i++) {
-        if (slots[i] < 0 || slots[i] >= c->pool_slots) return set_error(PLANET_E_INVALID, "slot %d out of range", slots[i]);
+        if (slots[i] < 0 || slots[i] >= c->sh.pool_slots) return set_error(PLANET_E_INVALID, "slot %d out of range", slots[i]);
         PLANET_CUDA(cudaMemcpy(h_out + i * texels, c->d_pool + (size_t)slots[i] * texels, texels * sizeof(float), cudaMemcpyDeviceToHost));
     }
     return 0;
+}
+
+int planet_gpu_cache_frame_device(void *cache, const planet_gpu_params *p, const planet_gpu_quad *d_quads, int64_t n,
+                                  int max_lod, int generations_per_frame, planet_gpu_texrect *d_rects,
+                                  int64_t *n_generated, void *stream)
+{
+    Cache *c = (Cache *)cache;
+    if (!c || n < 0 || n > (1 << 24) || (n > 0 && (!d_quads || !d_rects))) return set_error(PLANET_E_INVALID, "cache_frame_device: bad argument");
+    int rc = validate_params(p);
+    if (rc) return rc;
+    if ((rc = latch(c, Cache::DEVICE_PLANNED))) return rc;
+    return frame_on_device(c, p, d_quads, n, max_lod, generations_per_frame, d_rects, n_generated, (cudaStream_t)stream);
 }
 
 int planet_gpu_cache_frame(void *cache, const planet_gpu_params *p, const planet_gpu_quad *h_quads, int64_t n,
@@ -219,39 +526,19 @@ int planet_gpu_cache_frame(void *cache, const planet_gpu_params *p, const planet
                            planet_gpu_texrect *d_rects, void *stream_)
 {
     Cache *c = (Cache *)cache;
-    if (!ensure_init()) return PLANET_E_NO_DEVICE;
+    if (!c || n < 0 || n > (1 << 24) || (n > 0 && (!h_quads || !h_rects))) return set_error(PLANET_E_INVALID, "cache_frame: bad argument");
     int rc = validate_params(p);
     if (rc) return rc;
+    if ((rc = latch(c, Cache::DEVICE_PLANNED))) return rc;
+    if ((rc = ensure_device(c, n))) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
-    int64_t n_gen = 0;
-    rc = planet_gpu_cache_plan_frame(cache, h_quads, n, generations_per_frame, h_rects, &n_gen);
+    // host quads in, host texrects out: the same device frame between one upload and one download
+    if (n > 0) PLANET_CUDA(cudaMemcpyAsync(c->d_quads, h_quads, n * sizeof(planet_gpu_quad), cudaMemcpyHostToDevice, stream));
+    planet_gpu_texrect *rects = d_rects ? d_rects : c->d_rects;
+    rc = frame_on_device(c, p, c->d_quads, n, max_lod, generations_per_frame, rects, nullptr, stream);
     if (rc) return rc;
-    if (!planet_gpu_cache_pool(cache)) return PLANET_E_CUDA;
-    const int texels = c->dim * c->dim;
-    if (n_gen > 0) {
-        if ((size_t)n_gen > c->miss_cap) {
-            cudaFree(c->d_miss_quads); cudaFree(c->d_miss_maps); cudaFree(c->d_miss_slots);     // cudaFree(nullptr) is a no-op
-            c->d_miss_quads = nullptr; c->d_miss_maps = nullptr; c->d_miss_slots = nullptr;
-            c->miss_cap = 0;
-            const size_t want = (size_t)n_gen + 256;
-            PLANET_CUDA(cudaMalloc(&c->d_miss_quads, want * sizeof(Quad)));
-            PLANET_CUDA(cudaMalloc(&c->d_miss_maps, want * texels * sizeof(float)));
-            PLANET_CUDA(cudaMalloc(&c->d_miss_slots, want * sizeof(int)));
-            c->miss_cap = want;
-        }
-        PLANET_CUDA(cudaMemcpyAsync(c->d_miss_quads, c->h_miss_quads.data(), n_gen * sizeof(Quad), cudaMemcpyHostToDevice, stream));
-        PLANET_CUDA(cudaMemcpyAsync(c->d_miss_slots, c->h_miss_slots.data(), n_gen * sizeof(int), cudaMemcpyHostToDevice, stream));
-        // one batched K2 launch for every miss of the frame (main.cpp:244 once per quad in the reference)
-        rc = launch_height_maps(p, c->d_miss_quads, n_gen, c->dim, max_lod, c->d_miss_maps, stream);
-        if (rc) return rc;
-        k_scatter_maps<<<(int)std::min<int64_t>(n_gen, 1184), 128, 0, stream>>>(c->d_miss_maps, c->d_miss_slots, (int)n_gen, texels, c->d_pool);
-        count_launch();
-        PLANET_CUDA(cudaGetLastError());
-        // the host vectors are read by the async copies above
-        PLANET_CUDA(cudaStreamSynchronize(stream));
-    }
-    if (d_rects && n > 0)
-        PLANET_CUDA(cudaMemcpyAsync(d_rects, h_rects, n * sizeof(planet_gpu_texrect), cudaMemcpyHostToDevice, stream));
+    if (n > 0) PLANET_CUDA(cudaMemcpyAsync(h_rects, rects, n * sizeof(planet_gpu_texrect), cudaMemcpyDeviceToHost, stream));
+    PLANET_CUDA(cudaStreamSynchronize(stream));
     return 0;
 }
 

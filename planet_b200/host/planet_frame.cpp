@@ -2,8 +2,9 @@
 //
 // Mirrors the structure of the reference's main.cpp with the terrain path moved behind the C-ABI:
 //   InitPlanet   (main.cpp:280-516)  -> patch mesh + strip indices from K1, max_lod, skirt size
-//   RenderPlanet (main.cpp:600-683)  -> K0 LOD selection, height-map cache (one batched K2 launch
-//                                       per frame), K3 displacement + normals through texrects
+//   RenderPlanet (main.cpp:600-683)  -> K0 LOD selection, height-map cache (bookkeeping in one kernel on
+//                                       device tables + one batched K2 launch per frame), K3 displacement
+//                                       + normals through texrects; the leaf quads never visit the host
 // No window, no GL: the vertex/normal/index buffers stay in device memory, which is where a
 // CUDA-GL interop draw would read them.  Prints what the reference's title bar shows
 // (main.cpp:1029-1037) plus timings through the reference's timing.h macro names.
@@ -32,8 +33,8 @@ struct Planet                                                        // main.cpp
     uint32_t *d_patch_indices;                                       // triangle strip, main.cpp:427-474
     planet_gpu_params params;
     void *cache;                                                     // HeightMapCache, main.cpp:78-84
-    std::vector<Quad> quads;                                         // List<Quad> quads, main.cpp:178
-    Quad *d_quads; planet_gpu_texrect *d_rects; float *d_pos4, *d_nrm4;
+    Quad *d_quads;                                                   // List<Quad> quads (main.cpp:178), device-resident
+    planet_gpu_texrect *d_rects; float *d_pos4, *d_nrm4;
     int64_t capacity;
 };
 
@@ -79,14 +80,12 @@ static bool RenderPlanet(Planet &planet, const Vec3d &cam_position)  // main.cpp
     CHECK(planet_gpu_select_lod(&planet.params, cam, planet.max_lod, (planet_gpu_quad *)planet.d_quads,
                                 planet.capacity, &n, nullptr));
     if (n > 4096) { LOG_ERROR("%lld leaf quads exceed the demo's vertex buffers", (long long)n); return false; }
-    planet.quads.resize((size_t)n);
-    CUDA_OK(cudaMemcpy(planet.quads.data(), planet.d_quads, sizeof(Quad) * n, cudaMemcpyDeviceToHost));
-    END_TIMED_BLOCK(ProcessQuads);
+    END_TIMED_BLOCK(ProcessQuads);                                   // the leaves stay on the device
 
     BEGIN_TIMED_BLOCK(HeightMaps);                                   // main.cpp:652-660, generations_per_frame = 100
-    std::vector<planet_gpu_texrect> rects((size_t)n);
-    CHECK(planet_gpu_cache_frame(planet.cache, &planet.params, (const planet_gpu_quad *)planet.quads.data(), n,
-                                 planet.max_lod, 100, rects.data(), planet.d_rects, nullptr));
+    int64_t generated = 0;                                           // bookkeeping on the device, one batched K2 launch for the misses
+    CHECK(planet_gpu_cache_frame_device(planet.cache, &planet.params, (const planet_gpu_quad *)planet.d_quads, n,
+                                        planet.max_lod, 100, planet.d_rects, &generated, nullptr));
     END_TIMED_BLOCK(HeightMaps);
 
     BEGIN_TIMED_BLOCK(Draw);                                         // main.cpp:662-679 + the GLSL stage
@@ -96,10 +95,13 @@ static bool RenderPlanet(Planet &planet, const Vec3d &cam_position)  // main.cpp
     CUDA_OK(cudaDeviceSynchronize());
     END_TIMED_BLOCK(Draw);
 
-    int generated = 0, fallback = 0;
-    for (const auto &r : rects) { generated += r.flags == PLANET_TEXRECT_GENERATED; fallback += r.flags == PLANET_TEXRECT_PARENT; }
+    // for the statistics line only (the reference prints tri_count, main.cpp:1030): which quads borrowed a parent's map
+    std::vector<planet_gpu_texrect> rects((size_t)n);
+    CUDA_OK(cudaMemcpy(rects.data(), planet.d_rects, sizeof(planet_gpu_texrect) * n, cudaMemcpyDeviceToHost));
+    int fallback = 0;
+    for (const auto &r : rects) fallback += r.flags == PLANET_TEXRECT_PARENT;
     const int tri_count = (int)n * (planet.patch_verts - 1) * (planet.patch_verts - 1) * 2;   // main.cpp:1030
-    printf("tris: %d, quads: %d, generated: %d, parent fallback: %d, cached: %d\n", tri_count, (int)n, generated,
+    printf("tris: %d, quads: %d, generated: %d, parent fallback: %d, cached: %d\n", tri_count, (int)n, (int)generated,
            fallback, planet_gpu_cache_count(planet.cache));
     return true;
 }

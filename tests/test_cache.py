@@ -74,6 +74,78 @@ def test_plan_frame_makes_the_reference_decisions(frames):
     cache.close()
 
 
+def awkward_lists(port):
+    """(quad list, budget) per call: lists that are NOT one frame's leaf set -- a quad twice, a quad
+    together with its parent, cached quads placed behind enough new ones that they are evicted before
+    their own turn comes, quads with no cached parent and no budget.  These are the cases where a
+    probe of the table as it stood at the start of the frame is not the answer."""
+    f0d4, f0d5, f1d5 = port.uniform_quads(0, 4), port.uniform_quads(0, 5), port.uniform_quads(1, 5)
+    roots = np.concatenate([port.uniform_quads(f, 0) for f in range(6)])
+    return [
+        (f0d4, 2000),                                                  # 256 parents, all generated
+        (f0d5[:900], 100),                                             # 100 generated, 800 borrow the parent's quadrant
+        (np.concatenate([f0d5[900:902], f0d5[900:902], f0d4[:2], f0d5[:3], f0d5[901:903]]), 1),   # duplicates, parent + child
+        (f1d5[:800], 5000),                                            # fills the cache: evictions start mid-list
+        (np.concatenate([f1d5[800:1000], f0d4[:64], f0d5[:40]]), 5000),    # the old entries at the back are evicted before their turn
+        (np.concatenate([roots, port.uniform_quads(2, 3)[:20], f1d5[1000:1024]]), 0),   # no budget: roots and orphans generate anyway
+        (np.concatenate([f1d5[::7], f0d5[::5], f0d4[::3]]), 37),
+    ]
+
+
+def run_lists(ref, port, plan):
+    """Every list through the reference's GetHeightMapForQuad and through `plan`; same decisions."""
+    ref.reset_cache()
+    tex_owner, slot_owner = {}, {}
+    for k, (quads, budget) in enumerate(awkward_lists(port)):
+        want, want_count = ref.cache_lookup(quads, budget)
+        rects, n_gen, count = plan(quads, budget)
+        gen = want[:, 7] != 0
+        assert n_gen == int(gen.sum()) and count == want_count, (k, n_gen, int(gen.sum()), count, want_count)
+        assert ((rects["flags"] == pb.TEXRECT_GENERATED) == gen).all(), k
+        for q, t, r, g in zip(quads, want[:, 0], rects, gen):
+            if g:
+                tex_owner[int(t)] = int(q["id"]); slot_owner[int(r["slot"])] = int(q["id"])
+        assert [tex_owner[int(t)] for t in want[:, 0]] == [slot_owner[int(s)] for s in rects["slot"]], k
+        assert rects["corners"].tobytes() == want[:, 1:5].tobytes(), k
+        assert rects["pixel_size"].tobytes() == want[:, 5:7].tobytes(), k
+        assert ((rects["flags"] == pb.TEXRECT_PARENT) == (want[:, 5] != np.float32(1.0 / 32))).all(), k
+
+
+def test_plan_frame_on_lists_that_are_not_a_leaf_set(ref, port):
+    cache = pb.HeightMapCache(32, 1024, 1499, extra_slots=6000)
+
+    def plan(quads, budget):
+        rects, n_gen = cache.plan_frame(quads, budget)
+        return rects, n_gen, cache.count
+    run_lists(ref, port, plan)
+    cache.close()
+
+
+def test_a_failed_frame_leaves_the_cache_unchanged(frames):
+    cache = pb.HeightMapCache(32, 8, 11, extra_slots=4)
+    few = frames[2]["quads"][:6]
+    r0, n0 = cache.plan_frame(few, 100)
+    assert n0 == 6 and cache.count == 6
+    with pytest.raises(pb.PlanetGpuError, match="pool exhausted"):
+        cache.plan_frame(frames[2]["quads"], 100)
+    assert cache.count == 6
+    r1, n1 = cache.plan_frame(few, 100)                         # still all hits, on the same slots
+    assert n1 == 0 and (r1["slot"] == r0["slot"]).all() and (r1["flags"] == pb.TEXRECT_HIT).all()
+    cache.close()
+
+
+def test_one_cache_is_planned_on_the_host_or_on_the_device_not_both(frames):
+    cache = pb.HeightMapCache(32, 1024, 1499, extra_slots=64)
+    cache.plan_frame(frames[0]["quads"], 100)
+    import ctypes as C
+    q = np.ascontiguousarray(frames[0]["quads"])
+    rects = np.zeros(len(q), pb.TEXRECT_DTYPE)
+    p = pb.default_params()
+    rc = pb.lib().planet_gpu_cache_frame(cache.handle, C.byref(p), q.ctypes.data, len(q), 18, 100, rects.ctypes.data, None, None)
+    assert rc == -2 and b"already planned on the host" in pb.lib().planet_gpu_last_error()
+    cache.close()
+
+
 def test_draw_uniforms_of_the_glsl_stage_are_pinned(frames, port):
     """The GLSL stage itself cannot be executed here, but everything it is fed can be pinned: the
     per-quad uniforms P[4], N[4] and SkirtSize of the oracle (and of K3, which computes them the
@@ -118,4 +190,49 @@ def test_cache_frames_generate_the_reference_maps_and_shade_through_texrects(fra
         dh = np.abs(pos.cpu().numpy()[..., 3].astype(np.float64) - wpos[..., 3]).max(axis=1)
         rng = np.ptp(pool[rects["slot"]].reshape(len(rects), -1), axis=1)
         assert (dh <= 1e-5 * rng + 1e-3).all(), (k, dh.max())
+    cache.close()
+
+
+@pytest.mark.gpu
+def test_device_bookkeeping_takes_the_reference_decisions(frames, ref, port, gpu):
+    """k_plan_frame (32 lanes, tables in device memory) against the reference's GetHeightMapForQuad:
+    the 30-frame flight (owners, corners, pixel sizes, flags, counts) and the awkward lists."""
+    cache = gpu.HeightMapCache(32, 1024, 1499, extra_slots=1024)
+    host = gpu.HeightMapCache(32, 1024, 1499, extra_slots=1024)
+    p = gpu.fbm_params(4, 0.5, gpu.FAST)                        # what is generated does not matter here
+    slot_owner = {}
+    for k, f in enumerate(frames):
+        d_rects, n_gen = cache.frame_device(gpu.quads_to_device(f["quads"]), 18, p, 100)
+        rects = d_rects.cpu().numpy().view(gpu.TEXRECT_DTYPE).reshape(-1)
+        assert n_gen == f["generated"], (k, n_gen, f["generated"])
+        for q, r in zip(f["quads"], rects):
+            if r["flags"] == gpu.TEXRECT_GENERATED:
+                slot_owner[int(r["slot"])] = int(q["id"])
+        assert (np.array([slot_owner[int(s)] for s in rects["slot"]], np.uint64) == f["owners"]).all(), k
+        assert rects["corners"].tobytes() == f["corners"].tobytes() and rects["pixel_size"].tobytes() == f["pixel"].tobytes(), k
+        h_rects, h_gen = host.plan_frame(f["quads"], 100)       # one lane on the host: the same bytes
+        assert h_rects.tobytes() == rects.tobytes() and h_gen == n_gen and host.count == cache.count, k
+    assert cache.count == 1024
+    cache.close(); host.close()
+
+    cache = gpu.HeightMapCache(32, 1024, 1499, extra_slots=6000)
+
+    def plan(quads, budget):
+        d_rects, n_gen = cache.frame_device(gpu.quads_to_device(quads), 18, p, budget)
+        return d_rects.cpu().numpy().view(gpu.TEXRECT_DTYPE).reshape(-1), n_gen, cache.count
+    run_lists(ref, port, plan)
+    cache.close()
+
+
+@pytest.mark.gpu
+def test_a_failed_device_frame_leaves_the_cache_unchanged(frames, gpu):
+    cache = gpu.HeightMapCache(32, 8, 11, extra_slots=4)
+    p = gpu.default_params()
+    few = gpu.quads_to_device(frames[2]["quads"][:6])
+    r0, n0 = cache.frame_device(few, 18, p, 100)
+    with pytest.raises(gpu.PlanetGpuError, match="pool exhausted"):
+        cache.frame_device(gpu.quads_to_device(frames[2]["quads"]), 18, p, 100)
+    assert cache.count == 6
+    r1, n1 = cache.frame_device(few, 18, p, 100)
+    assert n0 == 6 and n1 == 0 and (r1[:, 0] == r0[:, 0]).all()
     cache.close()
