@@ -45,8 +45,11 @@ def check(o64, o32, g, slerp_exact):
         for got, want in ((o64, g["out64"]), (o32, g["out32"])):
             a, b = got[:, lo:hi], want[:, lo:hi]
             if name == "Slerp" and not slerp_exact:
-                assert np.isfinite(a).all()
-                assert (np.abs(a.astype(np.float64) - b) <= 1e-6 * scale).all(), name
+                # float operands a hair apart give Dot/(|a||b|) >= 1: acos is 0 or NaN and vec3.h:70-71 divides
+                # by sin(0) -- the reference's own hazard, reproduced: the same rows are non-finite
+                ok = np.isfinite(b).all(axis=1)
+                assert (np.isfinite(a).all(axis=1) == ok).all() and ok.sum() > 0.7 * len(ok), name
+                assert (np.abs(a[ok].astype(np.float64) - b[ok]) <= 1e-6 * scale[ok]).all(), name
             else:
                 assert a.tobytes() == b.tobytes(), f"{name} ({got.dtype}) is not bit-identical to vec3.h"
 

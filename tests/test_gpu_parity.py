@@ -500,6 +500,40 @@ def test_wide_quads_take_the_per_sample_reduction(gpu, port):
     assert np.abs(got.astype(np.float64) - want).max() <= REL_TOL * 8848.0 * amp_sum(0.5, 6)
 
 
+def test_fast_mode_steps_aside_where_its_shifts_would_wrap(gpu, port, golden):
+    """FAST is the lattice split by 32-bit funnel shifts and a 40-bit magic division: neither holds
+    for more than 32 octaves or dim > 8192.  The library must then run the EXACT arithmetic on the
+    GPU (never wrong heights): with max_depth 9 a depth-10 quad asks for 6 + 12*10/9 = 19 octaves, but
+    the bound over every depth a QuadID can carry (31 -> 47) is over 32; dim 8200 is past the
+    division's range.  (Beyond ~30 octaves the reference itself casts out-of-range doubles to int.)"""
+    import torch
+    deep = quads_from_bytes(golden["frame_quads"])
+    deep = deep[np.argsort((deep["id"] >> np.uint64(55)) & np.uint64(31))[-3:]].copy()     # the frame's deepest leaves (depth 10)
+    fast = gpu.default_params(precision=gpu.FAST)                   # ridged 0.55, 6 + 12*depth/max_depth octaves
+    exact = gpu.default_params(precision=gpu.EXACT)
+    got = to_np(gpu.generate_height_maps(gpu.quads_to_device(deep), 32, 9, fast))
+    want = port.generate_height_maps(deep, 32, 9, orc_params(exact))
+    assert np.isfinite(want).all()
+    assert as_bits(got).tobytes() == as_bits(want).tobytes()        # EXACT path taken: the reference's bits
+    one = gpu.quads_to_device(port.root_quads()[:1])
+    p8 = gpu.fbm_params(2, 0.5, gpu.FAST)
+    a = gpu.generate_height_maps(one, 8200, 18, p8)
+    b = gpu.generate_height_maps(one, 8200, 18, gpu.fbm_params(2, 0.5, gpu.EXACT))
+    assert torch.equal(a, b)
+    rows = [0, 1, 4099, 8199]
+    sub = to_np(a[0, rows][:, ::911])
+    xs = np.arange(0, 8200, 911)
+    q = port.root_quads()[0]["p"]
+    for ri, y in enumerate(rows):                                   # main.cpp:132-146 by hand for a few texels
+        for ci, x in enumerate(xs):
+            fx, fy = (x - 1) / (8200 - 3), (y - 1) / (8200 - 3)
+            v0, v1 = q[1] - q[0], q[3] - q[2]
+            top, bot = q[0] + v0 * fx, q[2] + v1 * fx
+            pt = top + (bot - top) * fy
+            h = port.get_height_at(pt, 0, 18, orc_params(gpu.fbm_params(2, 0.5, gpu.EXACT)))
+            assert abs(float(sub[ri, ci]) - h) <= 1e-3 * 8848.0, (x, y)
+
+
 def test_argument_validation_returns_errors(gpu, port):
     import torch
     q = gpu.quads_to_device(port.root_quads())
