@@ -255,6 +255,27 @@ def run_ours(args, rank, local_rank, world):
     k2_ms_est = nq * DIM * DIM / 39e9 * 1e3
     shade_share = int(os.environ.get("PLANET_GATHER_SHADE_SHARE", "2" if nvlink_ms > k2_ms_est else "0"))
 
+    # How K4 is driven (PLANET_GATHER_MODE):
+    #   fused  K2 pushes its finished tiles itself (planet_gpu_gather_height_maps), K3 its share
+    #   push   K2 runs unfused in chunks into this rank's slice of the gathered buffer; every finished chunk is
+    #          pushed to the peers by the library's small pusher kernel on a side stream, resident on the SMs beside
+    #          the K2 CTAs of the next chunk and beside K3 (planet_gpu_gather_begin / _push / _publish)
+    #   concurrent  ONE unfused K2 launch that publishes per-warp progress counters, and the pusher kernel following
+    #          them on the side stream from the first finished tile on (planet_gpu_gather_height_maps in that push mode)
+    gather_mode = os.environ.get("PLANET_GATHER_MODE", "fused") if world > 1 else "none"
+    # chunk sizes in K2 "waves" (one 128-sample tile for each of the 148 x 24 resident warps = 444 maps of 32^2):
+    # whole waves keep every warp equally loaded; a short first chunk starts the transfer early
+    wave = 148 * 24 * 128 // (DIM * DIM)
+    waves = [float(w) for w in os.environ.get("PLANET_GATHER_CHUNK_WAVES", "2,5").split(",")]
+    chunks, at = [], 0
+    while at < nq:
+        w = waves[min(len(chunks), len(waves) - 1)]
+        n = min(nq - at, max(1, int(round(w * wave))))
+        if nq - at - n < wave // 2:                                        # no crumb at the end
+            n = nq - at
+        chunks.append((at, n))
+        at += n
+
     def k1_quads():
         pb._check(L.planet_gpu_tessellate_uniform(pp, DEPTH, lo, nq, quads.data_ptr(), None, sp))
 
@@ -289,6 +310,28 @@ def run_ours(args, rank, local_rank, world):
             if e: e[2].record()
             k3(heights)
             if e: e[3].record(); e[4].record()
+        elif gather_mode == "push":
+            fork = torch.cuda.Event()
+            fork.record(stream)
+            k1_quads()
+            if e: e[1].record()
+            pb._check(L.planet_gpu_gather_begin(gather.handle, sp))        # next buffer; the peers have released it
+            b = L.planet_gpu_gather_last_buffer(gather.handle)
+            per = DIM * DIM * 4
+            for a, n in chunks:                                            # K2 chunk by chunk, each handed to the pusher kernel
+                pb._check(L.planet_gpu_generate_height_maps(pp, quads.data_ptr() + a * 104, n, DIM, MAX_LOD, shard_ptr[b] + a * per, sp))
+                pb._check(L.planet_gpu_gather_push(gather.handle, (lo + a) * per, n * per, sp))
+            pb._check(L.planet_gpu_gather_publish(gather.handle))          # the peers are signalled when the last push is done
+            if e: e[2].record()
+            side.wait_event(fork)
+            k1_indices()
+            join = torch.cuda.Event()
+            join.record(side)
+            k3(shard_ptr[b])                                               # under the tail of the transfer
+            stream.wait_event(join)
+            if e: e[3].record()
+            pb._check(L.planet_gpu_gather_wait(gather.handle, 1, sp))
+            if e: e[4].record()
         else:
             fork = torch.cuda.Event()
             fork.record(stream)
@@ -311,7 +354,8 @@ def run_ours(args, rank, local_rank, world):
         if e: marks.append(e)
 
     if gather is not None:
-        pb._check(L.planet_gpu_gather_set_shade_share(gather.handle, shade_share))
+        pb._check(L.planet_gpu_gather_set_shade_share(gather.handle, shade_share if gather_mode == "fused" else 0))
+        pb._check(L.planet_gpu_gather_set_push_mode(gather.handle, {"push": 1, "concurrent": 2}.get(gather_mode, 0)))
     for _ in range(warmup):
         step()
     barrier()
@@ -524,7 +568,8 @@ def run_ours(args, rank, local_rank, world):
                           f"every {shade_share}-th map is left to K3, which sends it as one 4 KB bulk copy per peer from the "
                           "shared-memory copy it shades from; arrival and release are flags written GPU to GPU, two gathered "
                           "buffers, no host barrier in the step",
-                "shade_share": shade_share,
+                "mode": gather_mode, "shade_share": shade_share if gather_mode == "fused" else 0,
+                "k2_chunks": len(chunks) if gather_mode == "push" else 1,
                 "bytes_received_per_gpu": gather_bytes_in,
                 "nvlink_floor_ms": gather_bytes_in / 660e9 * 1e3,
                 "nvlink_floor_note": "bytes every GPU must receive / 660 GB/s: what this box's NVLink sustains per direction when all "

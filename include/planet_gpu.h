@@ -157,6 +157,18 @@ int   planet_gpu_gather_shade(void *gather, const planet_gpu_params *p, const pl
  * cudaMemcpyAsync per peer on the gather's own streams, ordered behind `stream` by an event), then
  * publish (each peer is signalled as soon as its copies are done), then planet_gpu_gather_wait. */
 int   planet_gpu_gather_begin(void *gather, void *stream);
+/* who moves the bytes of planet_gpu_gather_push: the copy engines (default), or a small kernel of the
+ * library's own on one high-priority side stream (16-byte loads from the local buffer, 16-byte
+ * stores to every peer; 128 threads x 32 registers per CTA so that it is resident on the SMs BESIDE
+ * the K2 CTAs computing the next chunk -- the SMs reach ~700 GB/s all-to-all where the copy engines
+ * reach ~480, and no compute warp waits for the link as in the fused kernel) */
+/* PLANET_GATHER_PUSH_CONCURRENT changes planet_gpu_gather_height_maps instead: ONE un-chunked K2 launch
+ * that stores to this rank's buffer only and publishes, per warp, how many 512-byte tiles it has
+ * finished, and the pusher kernel on the side stream following those counters and sending the
+ * finished tiles to every peer while K2 (and then K3) compute on the same SMs; falls back to the
+ * fused kernel for batches the big FAST kernel does not take. */
+enum { PLANET_GATHER_PUSH_COPY_ENGINES = 0, PLANET_GATHER_PUSH_SM_KERNEL = 1, PLANET_GATHER_PUSH_CONCURRENT = 2 };
+int   planet_gpu_gather_set_push_mode(void *gather, int mode);
 int   planet_gpu_gather_push(void *gather, int64_t offset_bytes, int64_t size_bytes, void *stream);
 int   planet_gpu_gather_publish(void *gather);
 /* stream-ordered wait until every peer's shard of the last step has landed in this rank's buffer;

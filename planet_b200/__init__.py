@@ -77,6 +77,7 @@ def lib():
             "planet_gpu_gather_begin": (i, [vp, vp]),
             "planet_gpu_gather_push": (i, [vp, i64, i64, vp]),
             "planet_gpu_gather_publish": (i, [vp]),
+            "planet_gpu_gather_set_push_mode": (i, [vp, i]),
             "planet_gpu_gather_nccl": (i, [vp, i, vp, vp, vp]),
             "planet_gpu_gather_barrier": (i, [vp, vp]),
             "planet_gpu_gather_error": (i, [vp]),
@@ -121,7 +122,7 @@ EXPORTED_SYMBOLS = [
     "planet_gpu_generate_height_maps_gathered", "planet_gpu_gather_unique_id", "planet_gpu_gather_create",
     "planet_gpu_gather_destroy", "planet_gpu_gather_buffer", "planet_gpu_gather_last_buffer",
     "planet_gpu_gather_height_maps", "planet_gpu_gather_wait", "planet_gpu_gather_begin", "planet_gpu_gather_push",
-    "planet_gpu_gather_publish", "planet_gpu_gather_set_shade_share", "planet_gpu_gather_shade", "planet_gpu_gather_nccl",
+    "planet_gpu_gather_publish", "planet_gpu_gather_set_push_mode", "planet_gpu_gather_set_shade_share", "planet_gpu_gather_shade", "planet_gpu_gather_nccl",
     "planet_gpu_gather_barrier", "planet_gpu_gather_error", "planet_gpu_heights_at", "planet_gpu_noise", "planet_gpu_tessellate_uniform",
     "planet_gpu_quads_from_ids", "planet_gpu_patch_mesh", "planet_gpu_patch_vertex_count",
     "planet_gpu_patch_index_count", "planet_gpu_strip_index", "planet_gpu_uniform_leaf_id",

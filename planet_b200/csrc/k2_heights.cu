@@ -663,6 +663,20 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int WARPS = NTHREADS / 32;
+    // progress mode of the gather: lane 0 publishes the warp's finished-tile count (release: the tile's
+    // stores, ordered before it by the __syncwarp, are visible to whoever acquires the counter)
+    auto publish = [&](uint32_t tiles_done, bool last) {
+        if constexpr (GATHER) {
+            if (peers.progress && (last || (tiles_done & peers.progress_mask) == 0)) {
+                __syncwarp();
+                if (lane == 0) {
+                    const unsigned long long v = ((unsigned long long)peers.progress_tag << 32) | tiles_done;
+                    unsigned long long *at = peers.progress + (blockIdx.x * WARPS + warp);
+                    asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(at), "l"(v) : "memory");
+                }
+            }
+        }
+    };
     TileQuad *tq = reinterpret_cast<TileQuad *>(smem + L::TABLES) + warp * MAX_WTILE_QUADS;
     const LaneTab tab = lane_tab<REPL>(smem, lane, one_bits ^ ONE_BITS);
     const uint32_t dim2 = (uint32_t)dim * (uint32_t)dim;
@@ -678,6 +692,7 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
     const int64_t per_warp = (nwtiles + nwarps - 1) / nwarps;
     int64_t wt = ((int64_t)blockIdx.x * WARPS + warp) * per_warp;
     const int64_t wt_end = min(nwtiles, wt + per_warp);
+    const uint32_t wt_first = (uint32_t)wt;                          // (progress mode: tiles done = wt - wt_first)
     int64_t q_first = (wt * WTILE) / dim2;
     uint32_t r_base = (uint32_t)(wt * WTILE - q_first * dim2);
     int64_t q_built = -1;                                            // quad whose coefficients sit in tq[0]
@@ -797,6 +812,8 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
                     }
                 }
                 store_pair(o, value);
+                if constexpr (GATHER)
+                    if ((t & (SUB - 1)) == SUB - 1) publish((uint32_t)wt - wt_first + (uint32_t)(t / SUB) + 1u, wt + t / SUB + 1 == wt_end);
             }
             wt += run;
             r_base += (uint32_t)run * WTILE;
@@ -885,6 +902,7 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
         }
 
         wt++;
+        publish((uint32_t)wt - wt_first, wt == wt_end);
         r_base += WTILE;                                                     // the next tile of this warp
         if (small_maps) { const uint32_t dq = div_magic(r_base, magic_dim2); q_first += dq; r_base -= dq * dim2; }
         else if (r_base >= dim2) { r_base -= dim2; q_first++; }
@@ -1056,6 +1074,27 @@ bool height_maps_push_in_bulk(const planet_gpu_params *p, int64_t nquads, int di
     return ok;
 }
 
+// The tile ownership of the big FAST kernel for a batch of `total` samples -- warps in the grid, tiles
+// per warp, tiles in all -- for the pusher kernel that follows the kernel's progress counters
+// (k4_gather.cu).  False when this batch would not run on that kernel (EXACT arithmetic, the
+// small-batch kernel, unaligned output): progress mode is then not available.
+bool height_maps_progress_layout(const planet_gpu_params *p, int64_t nquads, int dim, int max_depth, const float *d_out,
+                                 int *nwarps, int64_t *per_warp, int64_t *nwtiles)
+{
+    HeightCfg cfg = make_cfg(p, max_depth);
+    const int64_t total = nquads * (int64_t)dim * dim;
+    const int max_oct = octaves_for(cfg.fixed_octaves, 31, max_depth != 0 ? max_depth : 1);
+    if (!(p->precision == PLANET_PRECISION_FAST && dim <= 8192 && fast_applicable(cfg.lacunarity, max_oct) &&
+          total > k2_small_max() && (total & 3) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0))
+        return false;
+    const int nt = k2_threads();
+    *nwtiles = (total + fast::WTILE - 1) / fast::WTILE;
+    const int grid = (int)std::min<int64_t>((*nwtiles + nt / 32 - 1) / (nt / 32), sm_count());
+    *nwarps = grid * (nt / 32);
+    *per_warp = (*nwtiles + *nwarps - 1) / *nwarps;
+    return true;
+}
+
 int launch_height_maps_gathered(const planet_gpu_params *p, const Quad *d_quads, int64_t nquads, int dim,
                                 int max_depth, float *d_out, const PeerOut &peers, cudaStream_t stream)
 {
@@ -1077,11 +1116,11 @@ int launch_height_maps_gathered(const planet_gpu_params *p, const Quad *d_quads,
         const uint64_t m1 = (one40 + dim - 1) / dim, m2 = (one40 + (uint64_t)dim * dim - 1) / ((uint64_t)dim * dim);
         int al = (reinterpret_cast<uintptr_t>(d_out) & 7) == 0;
         for (int r = 0; r < peers.n; r++) al = al && (reinterpret_cast<uintptr_t>(peers.ptr[r]) & 7) == 0;
-        const bool gather = peers.n > 0 || peers.release != nullptr, ridged = cfg.kind == PLANET_NOISE_RIDGED;
+        const bool gather = peers.n > 0 || peers.release != nullptr || peers.progress != nullptr, ridged = cfg.kind == PLANET_NOISE_RIDGED;
         uint32_t one_bits = fast::ONE_BITS;
         PeerOut peers_arg = peers;
         // tiles leave the SM as 512-byte bulk copies when every destination is 16-byte aligned
-        int bulk = gather && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && !getenv("PLANET_K2_NO_BULK");
+        int bulk = gather && !peers.progress && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && !getenv("PLANET_K2_NO_BULK");
         for (int r = 0; r < peers.n; r++) bulk = bulk && (reinterpret_cast<uintptr_t>(peers.ptr[r]) & 15) == 0;
         void *args[] = { (void *)&d_quads, &total, &dim, &cfg, (void *)&d_out, &nwtiles, &al, (void *)&m1, (void *)&m2, &one_bits, &peers_arg, &bulk };
         auto launch_fast = [&](const void *kern, int grid, int threads, size_t smem, cudaStream_t st) -> int {

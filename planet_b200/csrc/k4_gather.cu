@@ -22,11 +22,14 @@
 //     buffer first waits for the peers' releases of the step that filled it.  With two buffers
 //     nothing in a step waits on the host: no host barrier, no stream synchronisation.
 #include "planet_common.cuh"
+#include "planet_tma.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -36,6 +39,7 @@ int launch_height_maps_gathered(const planet_gpu_params *, const Quad *, int64_t
 int launch_gather_wait(const uint32_t *, uint32_t, int, int, uint32_t *, cudaStream_t);
 bool height_maps_push_in_bulk(const planet_gpu_params *, int64_t, int, int, const float *, const PeerOut &);
 bool shade_can_push(const planet_gpu_params *, const float *);
+bool height_maps_progress_layout(const planet_gpu_params *, int64_t, int, int, const float *, int *, int64_t *, int64_t *);
 int launch_shade_push(const planet_gpu_params *, const Quad *, int64_t, const double *, const float *,
                       const planet_gpu_texrect *, float, float *, float *, const PeerOut *, cudaStream_t);
 
@@ -118,6 +122,171 @@ __global__ void k_gather_wait_release(const uint32_t *flags, uint32_t step, int 
         asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(pf.ptr[threadIdx.x] + FLAG_RELEASE + rank), "r"(step) : "memory");
 }
 
+// The pushing done by a kernel of its own, beside the compute kernels: 16-byte vectors of a finished
+// range of the LOCAL buffer are loaded (L2 hits: K2 has just written them) and stored to the same
+// offset of every peer's buffer.  128 threads and 32 registers per CTA, no shared memory: one such
+// CTA fits on an SM next to a resident 768-thread K2 CTA (61 440 of the 65 536 registers, 217 of the
+// 228 KB of shared memory), so the transfer runs on the SMs that are computing the next chunk and
+// costs them ~8 issue slots per 112 bytes sent -- while no compute warp ever waits for the link.
+struct PushDst { float4 *ptr[7]; int n; };
+
+__global__ void __launch_bounds__(128, 16)
+k_push_range(const float4 *__restrict__ src, PushDst dst, size_t nvec)
+{
+    const size_t stride = (size_t)gridDim.x * 128;
+    size_t i = (size_t)blockIdx.x * 128 + threadIdx.x;
+    for (; i + stride < nvec; i += 2 * stride) {                         // two loads in flight per thread
+        const float4 a = __ldcg(src + i), b = __ldcg(src + i + stride);
+#pragma unroll
+        for (int k = 0; k < 7; k++)
+            if (k < dst.n) { __stcs(dst.ptr[k] + i, a); __stcs(dst.ptr[k] + i + stride, b); }
+    }
+    if (i < nvec) {
+        const float4 a = __ldcg(src + i);
+#pragma unroll
+        for (int k = 0; k < 7; k++)
+            if (k < dst.n) __stcs(dst.ptr[k] + i, a);
+    }
+}
+
+// The pusher that runs BESIDE one un-chunked K2 launch (PLANET_GATHER_PUSH_CONCURRENT).  K2's warps own
+// contiguous runs of 512-byte tiles and publish how many they have finished (PeerOut::progress); every
+// pusher warp looks after a fixed set of K2 warps, round robin: it acquires the counter, and sends the
+// tiles finished since its last visit -- one 16-byte vector per lane loaded from the local buffer (L2),
+// stored to the same offset of every peer's buffer -- until all its warps are done.  A counter carries
+// the step in its upper half, so one left over from an earlier step reads as "nothing yet" and one from
+// a later step (this pusher lagging behind the next K2) as "all done".
+constexpr int PUSH_MAX_OWNED = 32;     // K2 warps per pusher warp
+
+__global__ void __launch_bounds__(128, 16)
+k_push_progress(const float4 *__restrict__ src, PushDst dst, const unsigned long long *progress, uint32_t tag,
+                int nwarps, long long per_warp, long long nwtiles, long long total_vec, uint32_t *error)
+{
+    __shared__ uint32_t s_sent[4][PUSH_MAX_OWNED];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int pw = blockIdx.x * 4 + w, npw = gridDim.x * 4;
+    const int owned = pw < nwarps ? (nwarps - pw + npw - 1) / npw : 0;       // K2 warps pw, pw + npw, ...
+    for (int j = lane; j < PUSH_MAX_OWNED; j += 32) s_sent[w][j] = 0;
+    __syncwarp();
+    int open = owned;
+    unsigned long long idle_since = 0;
+    while (open > 0) {
+        open = 0;
+        bool moved = false;
+        for (int j = 0; j < owned; j++) {
+            const int gw = pw + j * npw;
+            const long long first = (long long)gw * per_warp;
+            const long long mine = min(per_warp, max(0ll, nwtiles - first));  // tiles this K2 warp owns
+            const uint32_t sent = s_sent[w][j];
+            if (sent >= (uint32_t)mine) continue;
+            // polled with a RELAXED load: an acquire load invalidates the SM's L1 every time, and L1 is the same
+            // array K2's table lookups live in (K2 ran at half speed beside a pusher that polled with acquire);
+            // the acquire fence is paid once per observed advance instead
+            unsigned long long v;
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(progress + gw) : "memory");
+            const uint32_t vt = (uint32_t)(v >> 32);
+            uint32_t done = vt == tag ? (uint32_t)v : ((int32_t)(vt - tag) > 0 ? (uint32_t)mine : 0u);
+            done = min(done, (uint32_t)mine);
+            if (done > sent) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            for (uint32_t t = sent; t < done; t++) {
+                const long long vec = (first + t) * 32 + lane;               // 32 vectors of 16 bytes per tile
+                if (vec < total_vec) {
+                    const float4 x = __ldcg(src + vec);
+#pragma unroll
+                    for (int k = 0; k < 7; k++)
+                        if (k < dst.n) __stcs(dst.ptr[k] + vec, x);
+                }
+            }
+            if (done > sent) { moved = true; __syncwarp(); if (lane == 0) s_sent[w][j] = done; __syncwarp(); }
+            if (done < (uint32_t)mine) open++;
+        }
+        if (open && !moved) {
+            // bounded like every wait in this file: 2 s without any progress of K2 and the pusher gives up
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (!idle_since) idle_since = now;
+            else if (now - idle_since > 2000000000ull) { if (lane == 0 && error) atomicExch(error, 1u); return; }
+            __nanosleep(1000);
+        } else {
+            idle_since = 0;
+        }
+    }
+}
+
+// The same pusher moving the bytes with the TMA unit instead of the load/store unit: K2's octave loop
+// keeps the SM's shared-memory pipe ~75 % busy, and 16-byte stores that wait for NVLink in that pipe
+// hold K2's table lookups up behind them (K2 ran at half speed beside k_push_progress).  Here one lane
+// per warp only issues bulk copies: finished tiles come from the local buffer into a 1 KB staging slot
+// (global -> shared, completion on an mbarrier) and leave for every peer (shared -> global), two slots
+// per warp in flight; the data never passes through a register.
+constexpr int PUSH_SLOT = 1024;        // bytes per staging slot: 2 consecutive tiles of one K2 warp (8 KB per CTA: what K2 leaves of the SM)
+
+__global__ void __launch_bounds__(128, 16)
+k_push_progress_tma(const char *__restrict__ src, PushDst dst, const unsigned long long *progress, uint32_t tag,
+                    int nwarps, long long per_warp, long long nwtiles, long long total_bytes, uint32_t *error)
+{
+    __shared__ __align__(128) unsigned char s_stage[4][2][PUSH_SLOT];
+    __shared__ __align__(8) uint64_t s_bar[4][2];
+    __shared__ uint32_t s_sent[4][PUSH_MAX_OWNED];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane != 0) return;                                                   // one issuing lane per warp; nothing here is warp-collective
+    const int pw = blockIdx.x * 4 + w, npw = gridDim.x * 4;
+    const int owned = pw < nwarps ? (nwarps - pw + npw - 1) / npw : 0;
+    for (int j = 0; j < owned; j++) s_sent[w][j] = 0;
+    tma::mbar_init(&s_bar[w][0], 1); tma::mbar_init(&s_bar[w][1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    uint32_t phase[2] = { 0, 0 };
+    int slot = 0;
+    int open = owned;
+    unsigned long long idle_since = 0;
+    while (open > 0) {
+        open = 0;
+        bool moved = false;
+        for (int j = 0; j < owned; j++) {
+            const int gw = pw + j * npw;
+            const long long first = (long long)gw * per_warp;
+            const long long mine = min(per_warp, max(0ll, nwtiles - first));
+            uint32_t sent = s_sent[w][j];
+            if (sent >= (uint32_t)mine) continue;
+            unsigned long long v;                                            // relaxed poll, see k_push_progress
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(progress + gw) : "memory");
+            const uint32_t vt = (uint32_t)(v >> 32);
+            uint32_t done = vt == tag ? (uint32_t)v : ((int32_t)(vt - tag) > 0 ? (uint32_t)mine : 0u);
+            done = min(done, (uint32_t)mine);
+            if (done > sent) { asm volatile("fence.acq_rel.gpu;" ::: "memory"); tma::fence_before_async_reads(); }
+            while (sent < done) {
+                const uint32_t ntile = min(done - sent, (uint32_t)(PUSH_SLOT / 512));
+                const long long at = (first + sent) * 512;
+                const uint32_t bytes = (uint32_t)min((long long)ntile * 512, total_bytes - at);
+                tma::wait_read<1>();                                         // the slot's previous contents have left it
+                tma::mbar_expect_tx(&s_bar[w][slot], bytes);
+                tma::load_bulk(s_stage[w][slot], src + at, bytes, &s_bar[w][slot]);
+                while (!tma::mbar_try_wait(&s_bar[w][slot], phase[slot])) { }
+                phase[slot] ^= 1;
+#pragma unroll
+                for (int k = 0; k < 7; k++)
+                    if (k < dst.n) tma::store_bulk(reinterpret_cast<char *>(dst.ptr[k]) + at, s_stage[w][slot], bytes);
+                tma::commit();
+                slot ^= 1;
+                sent += ntile;
+                moved = true;
+            }
+            s_sent[w][j] = sent;
+            if (sent < (uint32_t)mine) open++;
+        }
+        if (open && !moved) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (!idle_since) idle_since = now;
+            else if (now - idle_since > 2000000000ull) { if (error) atomicExch(error, 1u); break; }
+            __nanosleep(1000);
+        } else {
+            idle_since = 0;
+        }
+    }
+    tma::wait_all<0>();
+}
+
 struct Gather {
     int rank = 0, world = 1, nbuf = 1, device = 0;
     size_t bytes = 0, stride = 0;
@@ -128,7 +297,12 @@ struct Gather {
     int last_buffer = 0;
     // copy-engine path: one stream per peer and a ring of events that order the copies behind the
     // kernels of the caller's stream
+    int push_mode = PLANET_GATHER_PUSH_COPY_ENGINES;   // who moves the bytes of planet_gpu_gather_push
+    int sm_count = 148;
     int k3_every = 0;                   // > 0: the shade kernel pushes every k3_every-th quad (planet_gpu_gather_set_shade_share)
+    unsigned long long *progress = nullptr;   // PLANET_GATHER_PUSH_CONCURRENT: one counter per K2 warp
+    int progress_cap = 0;
+    bool carveout_set = false;
     PeerOut pending = {};               // the peers of the step whose shade-kernel share is still to be pushed
     bool shade_pending = false;
     cudaStream_t push_stream[7] = {};
@@ -226,8 +400,14 @@ void *planet_gpu_gather_create(const void *id, int rank, int world, int64_t byte
             if (check_cuda(cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return fail("peer mapping");
             g->peer_base[r] = (char *)p;
         }
+        // The side streams keep the DEFAULT priority.  Measured (profiles/r02y_*): with the pusher on a
+        // high-priority stream the K2 kernel it shares the SMs with runs at half speed for as long as the
+        // pusher is resident, whatever the pusher does (even only sleeping between polls)
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, g->device);
         for (int k = 0; k < world - 1; k++)
-            if (check_cuda(cudaStreamCreateWithFlags(&g->push_stream[k], cudaStreamNonBlocking), "push stream")) return fail("streams");
+            if (check_cuda(cudaStreamCreateWithPriority(&g->push_stream[k], cudaStreamNonBlocking, getenv("PLANET_PUSH_HIGHPRIO") ? prio_hi : prio_lo), "push stream")) return fail("streams");
         for (auto &e : g->ring)
             if (check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event")) return fail("events");
         if (nccl_barrier(g, nullptr)) return fail("barrier");            // every rank has mapped every buffer
@@ -249,6 +429,7 @@ void planet_gpu_gather_destroy(void *gather)
     if (g->world > 1) nccl_barrier(g, nullptr);
     for (auto &st : g->push_stream) if (st) cudaStreamDestroy(st);
     for (auto &e : g->ring) if (e) cudaEventDestroy(e);
+    if (g->progress) cudaFree(g->progress);
     if (g->base) cudaFree(g->base);
     if (g->comm) nccl_api().CommDestroy(g->comm);
     delete g;
@@ -292,9 +473,65 @@ int planet_gpu_gather_height_maps(void *gather, const planet_gpu_params *p, cons
         peers.rank = g->rank; peers.world = g->world;
         peers.error = g->flags(g->rank) + FLAG_ERROR;
     }
-    // part of the pushing may be left to the shade kernel (planet_gpu_gather_shade must then follow)
     g->shade_pending = false;
     peers.quad0 = first_quad;
+    // One un-chunked K2 launch that pushes nothing itself, and the pusher kernel beside it on the side stream
+    int k2_warps = 0;
+    int64_t per_warp = 0, nwtiles = 0;
+    if (g->world > 1 && g->push_mode == PLANET_GATHER_PUSH_CONCURRENT && nquads > 0 &&
+        height_maps_progress_layout(p, nquads, dim, max_depth, g->buffer(g->rank, b) + off, &k2_warps, &per_warp, &nwtiles) &&
+        (off * sizeof(float)) % 16 == 0) {
+        if (k2_warps > g->progress_cap) {
+            if (g->progress) { PLANET_CUDA(cudaStreamSynchronize(g->push_stream[0])); cudaFree(g->progress); g->progress = nullptr; g->progress_cap = 0; }
+            PLANET_CUDA(cudaMalloc(&g->progress, (size_t)k2_warps * sizeof(unsigned long long)));
+            PLANET_CUDA(cudaMemset(g->progress, 0, (size_t)k2_warps * sizeof(unsigned long long)));
+            g->progress_cap = k2_warps;
+        }
+        PeerOut local = peers;
+        local.n = 0;                                                      // K2 stores to this rank's buffer only ...
+        local.progress = g->progress;                                     // ... and says how far it is
+        local.progress_tag = step;
+        {   // how often a K2 warp publishes (every 2^k tiles; tuning knob PLANET_PUSH_EVERY, used by tools/gather_modes.py)
+            const char *e = getenv("PLANET_PUSH_EVERY");
+            int every = e ? atoi(e) : 1;
+            while (every & (every - 1)) every &= every - 1;
+            local.progress_mask = (uint32_t)(every > 0 ? every - 1 : 0);
+        }
+        PushDst dst = {};
+        dst.n = g->world - 1;
+        for (int k = 0; k < dst.n; k++) dst.ptr[k] = reinterpret_cast<float4 *>(peers.ptr[k]);
+        // the pusher may start as soon as the stream reaches this point (it only ever follows K2's counters,
+        // and K2 itself waits for the peers' release of the buffer before its first tile)
+        cudaEvent_t ev = g->ring[g->ring_at++ & 31];
+        PLANET_CUDA(cudaEventRecord(ev, stream));
+        PLANET_CUDA(cudaStreamWaitEvent(g->push_stream[0], ev, 0));
+        rc = launch_height_maps_gathered(p, (const Quad *)d_quads, nquads, dim, max_depth, g->buffer(g->rank, b) + off, local, stream);
+        if (rc) return rc;
+        // the pusher's CTAs must be able to share an SM with K2's, whichever arrives first: an SM keeps one
+        // shared-memory carve-out while anything is resident on it, and K2 needs the largest
+        if (!g->carveout_set) {
+            PLANET_CUDA(cudaFuncSetAttribute(k_push_progress, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            PLANET_CUDA(cudaFuncSetAttribute(k_push_progress_tma, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            g->carveout_set = true;
+        }
+        int pushers = std::min(g->sm_count, (k2_warps + 3) / 4);
+        if (getenv("PLANET_PUSH_CTAS")) pushers = std::max(1, std::min(pushers, atoi(getenv("PLANET_PUSH_CTAS"))));
+        const int owned = (k2_warps + pushers * 4 - 1) / (pushers * 4);
+        if (owned > PUSH_MAX_OWNED) return set_error(PLANET_E_UNSUPPORTED, "gather: %d K2 warps per pusher warp", owned);
+        const long long total_vec = (long long)nquads * (long long)texels / 4;
+        if (getenv("PLANET_PUSH_LSU"))
+            k_push_progress<<<pushers, 128, 0, g->push_stream[0]>>>(reinterpret_cast<const float4 *>(g->buffer(g->rank, b) + off), dst,
+                                                                    g->progress, step, k2_warps, per_warp, nwtiles, total_vec, g->flags(g->rank) + FLAG_ERROR);
+        else
+            k_push_progress_tma<<<pushers, 128, 0, g->push_stream[0]>>>(reinterpret_cast<const char *>(g->buffer(g->rank, b) + off), dst,
+                                                                        g->progress, step, k2_warps, per_warp, nwtiles, total_vec * 16, g->flags(g->rank) + FLAG_ERROR);
+        count_launch();
+        PLANET_CUDA(cudaGetLastError());
+        k_gather_signal<<<1, 32, 0, g->push_stream[0]>>>(g->peer_flags(), FLAG_ARRIVE + g->rank, step);
+        count_launch();
+        return check_cuda(cudaGetLastError(), "gather signal launch");
+    }
+    // part of the pushing may be left to the shade kernel (planet_gpu_gather_shade must then follow)
     if (g->world > 1 && g->k3_every > 1 && nquads > 0 && dim == p->patch_verts + 2 &&
         height_maps_push_in_bulk(p, nquads, dim, max_depth, g->buffer(g->rank, b) + off, peers) &&
         shade_can_push(p, g->buffer(g->rank, b) + off)) {
@@ -385,6 +622,19 @@ int planet_gpu_gather_push(void *gather, int64_t offset_bytes, int64_t size_byte
     cudaEvent_t ev = g->ring[g->ring_at++ & 31];
     PLANET_CUDA(cudaEventRecord(ev, (cudaStream_t)stream_));
     const char *src = reinterpret_cast<const char *>(g->buffer(g->rank, g->last_buffer)) + offset_bytes;
+    if (g->push_mode == PLANET_GATHER_PUSH_SM_KERNEL) {
+        if ((offset_bytes | size_bytes) & 15) return set_error(PLANET_E_INVALID, "gather_push: the SM pusher moves 16-byte vectors (offset %lld, size %lld)", (long long)offset_bytes, (long long)size_bytes);
+        PushDst dst = {};
+        dst.n = g->world - 1;
+        for (int k = 0; k < dst.n; k++)
+            dst.ptr[k] = reinterpret_cast<float4 *>(reinterpret_cast<char *>(g->buffer((g->rank + 1 + k) % g->world, g->last_buffer)) + offset_bytes);
+        PLANET_CUDA(cudaStreamWaitEvent(g->push_stream[0], ev, 0));
+        const size_t nvec = (size_t)size_bytes / 16;
+        const int grid = (int)std::min<size_t>((size_t)g->sm_count, (nvec + 127) / 128);
+        k_push_range<<<grid, 128, 0, g->push_stream[0]>>>(reinterpret_cast<const float4 *>(src), dst, nvec);
+        count_launch();
+        return check_cuda(cudaGetLastError(), "gather push launch");
+    }
     for (int k = 0; k < g->world - 1; k++) {
         char *dst = reinterpret_cast<char *>(g->buffer((g->rank + 1 + k) % g->world, g->last_buffer)) + offset_bytes;
         PLANET_CUDA(cudaStreamWaitEvent(g->push_stream[k], ev, 0));
@@ -398,6 +648,11 @@ int planet_gpu_gather_publish(void *gather)
 {
     Gather *g = (Gather *)gather;
     if (!g) return set_error(PLANET_E_INVALID, "gather is NULL");
+    if (g->world > 1 && g->push_mode == PLANET_GATHER_PUSH_SM_KERNEL) {      // every push sits on one stream: one signal to all peers
+        k_gather_signal<<<1, 32, 0, g->push_stream[0]>>>(g->peer_flags(), FLAG_ARRIVE + g->rank, g->step);
+        count_launch();
+        return check_cuda(cudaGetLastError(), "gather publish launch");
+    }
     for (int k = 0; k < g->world - 1; k++) {
         PeerFlags one = {};
         one.n = 1;
@@ -406,6 +661,15 @@ int planet_gpu_gather_publish(void *gather)
         count_launch();
     }
     return check_cuda(cudaGetLastError(), "gather publish launch");
+}
+
+int planet_gpu_gather_set_push_mode(void *gather, int mode)
+{
+    Gather *g = (Gather *)gather;
+    if (!g || mode < PLANET_GATHER_PUSH_COPY_ENGINES || mode > PLANET_GATHER_PUSH_CONCURRENT)
+        return set_error(PLANET_E_INVALID, "gather_set_push_mode(%d)", mode);
+    g->push_mode = mode;
+    return 0;
 }
 
 int planet_gpu_gather_wait(void *gather, int release, void *stream_)

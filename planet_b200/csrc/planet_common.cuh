@@ -123,6 +123,13 @@ struct PeerOut {
     // bulk copy per peer (the NVLink transfer is then spread over both kernels)
     int64_t quad0;      // index in the gathered buffer of the launch's first quad
     int k3_every;
+    // Progress mode (k4_gather.cu, PLANET_GATHER_PUSH_CONCURRENT): the kernel pushes nothing itself; every
+    // warp publishes, after each finished 128-sample tile, (tag << 32 | tiles done) in progress[its index
+    // in the grid] with release semantics, and a pusher kernel running BESIDE it on the same SMs sends the
+    // finished tiles on.  n == 0 then; the release wait above still guards the peers' buffers.
+    unsigned long long *progress;
+    uint32_t progress_tag;
+    uint32_t progress_mask;     // publish when (tiles done & mask) == 0 and at the warp's last tile (2^k - 1)
 };
 int validate_params(const planet_gpu_params *p);
 

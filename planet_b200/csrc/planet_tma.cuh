@@ -38,5 +38,32 @@ template <int N> __device__ __forceinline__ void wait_read() { asm volatile("cp.
 // all but the latest N groups of this thread are complete (their writes are performed)
 template <int N> __device__ __forceinline__ void wait_all() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
 
+// ---- global -> shared bulk loads, completion on an mbarrier (for kernels that only forward data) ----
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase)
+{
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(phase) : "memory");
+    return ok != 0;
+}
+// src: 16-byte aligned global address; dst: 16-byte aligned shared address; bytes % 16 == 0
+__device__ __forceinline__ void load_bulk(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes),
+                    "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+// data another thread wrote through ordinary stores (and this thread has acquired) is about to be
+// read through the async proxy
+__device__ __forceinline__ void fence_before_async_reads() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 } // namespace tma
 } // namespace planet

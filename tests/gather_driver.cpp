@@ -1,6 +1,6 @@
 // Multi-process test driver for K4 (planet_gpu_gather_*): one process per GPU, no Python, no torch.
 //
-//   gather_driver <world> <depth> <mode>      mode: fast | exact | ragged | nccl | ce | split
+//   gather_driver <world> <depth> <mode>      mode: fast | exact | ragged | nccl | ce | smpush | split | concurrent | concurrent_ragged
 //
 // The parent forks `world` ranks before any CUDA call.  Rank 0 writes the NCCL unique id to a file
 // in a scratch directory, the others read it (the C-ABI leaves the transport to the caller).  The
@@ -60,7 +60,7 @@ static int run_rank(int rank, int world, int depth, const std::string &mode, con
     // patch-range partition; `ragged` moves the boundaries off the even split
     std::vector<int64_t> lo(world + 1);
     for (int r = 0; r <= world; r++) lo[r] = Q * r / world;
-    if (mode == "ragged") for (int r = 1; r < world; r++) lo[r] += 37 * r + 1;
+    if (mode == "ragged" || mode == "concurrent_ragged") for (int r = 1; r < world; r++) lo[r] += 37 * r + 1;
     const int64_t first = lo[rank], n = lo[rank + 1] - lo[rank];
 
     void *g = planet_gpu_gather_create(world > 1 ? id : nullptr, rank, world, Q * texels * sizeof(float), 2);
@@ -99,8 +99,10 @@ static int run_rank(int rank, int world, int depth, const std::string &mode, con
         which = planet_gpu_gather_last_buffer(g);
         CUDA_OK(cudaStreamSynchronize(stream));
         cudaFree(d_pos); cudaFree(d_nrm);
-    } else if (mode == "ce") {
-        // the copy-engine path: plain K2 in four chunks, every finished chunk pushed to the peers
+    } else if (mode == "ce" || mode == "smpush") {
+        // plain K2 in four chunks, every finished chunk pushed to the peers by the copy engines (ce) or by
+        // the library's pusher kernel on its side stream (smpush)
+        if (mode == "smpush") CHECK(planet_gpu_gather_set_push_mode(g, PLANET_GATHER_PUSH_SM_KERNEL));
         for (int step = 0; step < 3; step++) {
             params.seed_offset[1] = 0.25 * step;
             CHECK(planet_gpu_gather_begin(g, stream));
@@ -115,6 +117,8 @@ static int run_rank(int rank, int world, int depth, const std::string &mode, con
         }
         which = planet_gpu_gather_last_buffer(g);
     } else {
+        // concurrent: one K2 launch publishing its progress, the pusher kernel following it on the side stream
+        if (mode == "concurrent" || mode == "concurrent_ragged") CHECK(planet_gpu_gather_set_push_mode(g, PLANET_GATHER_PUSH_CONCURRENT));
         for (int step = 0; step < 3; step++) {
             // every step computes a different terrain (seed offset), so a step satisfied by an earlier
             // step's data -- a missed release wait, a wrong buffer rotation -- fails the comparison below

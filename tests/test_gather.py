@@ -63,7 +63,7 @@ def test_unique_id_comes_from_nccl():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["fast", "exact", "nccl", "ce", "split"])
+@pytest.mark.parametrize("mode", ["fast", "exact", "nccl", "ce", "smpush", "split", "concurrent"])
 def test_world_of_one_is_the_plain_path(driver, gpu, mode):
     rc, out, err = run_driver(driver, 1, 5, mode)
     assert rc == 0, err[-2000:]
@@ -71,7 +71,7 @@ def test_world_of_one_is_the_plain_path(driver, gpu, mode):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["fast", "ragged", "exact", "nccl", "ce", "split"])
+@pytest.mark.parametrize("mode", ["fast", "ragged", "exact", "nccl", "ce", "smpush", "split", "concurrent", "concurrent_ragged"])
 def test_two_ranks_gather_the_unsharded_bytes(driver, gpu, mode):
     import torch
     if torch.cuda.device_count() < 2:
