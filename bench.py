@@ -80,8 +80,18 @@ def make_config(world):
         workload = (f"C3 (BASELINE.json configs[2]): full planet, 6 faces at depth 7 = 98304 quads x 32^2 = 100.66M vertices "
                     f"as a fixed total, fBm 8 octaves gain 0.5, patch 30 verts, split by patch range over {world} GPUs, "
                     f"finished height maps gathered on every GPU")
+    per_gpu = [b - a for a, b in (shard_range(nq, r, world) for r in range(world))]
+    # every key is emitted identically by both arms (the driver compares the two config objects), so the
+    # entries that describe one arm only say which arm they describe
     return {"workload": workload, "depth": DEPTH, "dim": DIM, "octaves": OCTAVES, "gain": GAIN, "faces": nq // QUADS_PER_FACE,
-            "quads": nq, "vertices": nq * DIM * DIM, "gpus": world}
+            "quads": nq, "vertices": nq * DIM * DIM, "gpus": world,
+            "quads_per_gpu": max(per_gpu), "vertices_per_gpu": max(per_gpu) * DIM * DIM,
+            "precision": "GPU arm: FAST arithmetic (<= 1e-5 * height_scale * sum(gain^k) from the reference; the EXACT mode is "
+                         "bit-identical and timed beside it); reference arm: the reference's own arithmetic",
+            "l2": "GPU arm: 256 MiB buffer written between timed steps (L2 flush); reference arm: every step writes the whole "
+                  "height-map batch (67 MB per face), larger than the host's last-level cache",
+            "step": "GPU arm: K1 tessellate + K2 heights + K3 shade" + ("" if world == 1 else " + K4 gather (fused into K2/K3, wait for the peers' shards)") +
+                    "; reference arm: GenerateHeightMap on every quad (the reference has no CPU displacement/normals)"}
 
 
 def measured_peaks():
@@ -491,11 +501,6 @@ def run_ours(args, rank, local_rank, world):
         k3_alg = k3_write + nq * 104 + verts_rank * 4
         traffic, traffic_src = profiled_traffic()
         config = make_config(world)
-        config.update({"quads_per_gpu": nq, "vertices_per_gpu": verts_rank, "precision": "FAST",
-                       "l2": "256 MiB buffer written between timed steps (L2 flush)",
-                       "step": "K1 tessellate + K2 heights + K3 shade" if world == 1 else
-                               "K1 quads + K2 heights with K4 fused (bulk copies to every peer over NVLink) + K3 shade with its share of "
-                               "K4 (K1's index stream beside it) + wait for the peers' shards"})
         line = {
             "metric": METRIC, "value": total_verts / (ms_step * 1e-3), "unit": "vertices/s",
             "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step,

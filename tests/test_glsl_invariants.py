@@ -128,9 +128,12 @@ def test_k3_flat_height_map_normal_is_the_interpolated_normal_and_positions_lie_
         all_slerp = not any(b.any() for b in r["branch"])
         if all_slerp:                                                              # on the sphere of radius R + h
             assert np.abs(np.linalg.norm(world, axis=-1) - (R + 1234.5)).max() <= 8.0, k
-        assert np.abs(world - ev).max() <= 8 * 2.0 ** -23 * np.abs(quads[k]["p"] - cam).max() + 1e-5 * np.linalg.norm(quads[k]["p"][3] - quads[k]["p"][0])
+        tol = 8 * 2.0 ** -23 * np.abs(quads[k]["p"] - cam).max() + 1e-5 * np.linalg.norm(quads[k]["p"][3] - quads[k]["p"][0])
+        assert np.abs(world - ev).max() <= tol
         # the four corner vertices are the endpoints of interpolate: P[i] + N[i] * h (slots of UV = (0,0),(1,0),(0,1),(1,1))
         for i, (ux, uy) in enumerate(((0, 0), (1, 0), (0, 1), (1, 1))):
             slot = int(np.flatnonzero((uv3[:, 0] == ux) & (uv3[:, 1] == uy) & skirtless)[0])
             want = draws[k][3 * i:3 * i + 3].astype(np.float64) + draws[k][12 + 3 * i:15 + 3 * i].astype(np.float64) * 1234.5
-            assert np.abs(pos[k, slot, :3] - want).max() <= 4 * 2.0 ** -23 * np.abs(want).max() + 1e-3, (k, i)
+            # (in the slerp branch y = 1/sin(theta) - 1/(cos(gamma) tan(theta)) cancels to ~1 fp32 ulp of 1/sin(theta),
+            #  times half the chord: the shader's own rounding, a fraction of a metre on a 1000 km quad)
+            assert np.abs(pos[k, slot, :3] - want).max() <= tol, (k, i)
