@@ -525,14 +525,42 @@ void ref_vec3_ops_f64(const double *a, const double *b, const double *t, long n,
  * stdout: int64 leaf count, the leaf Quads (104 B each), int64 map count, the maps (w*h floats).
  * tests/test_real_caller.py compares them with what the CPU generator produced in the
  * reference's real main() (golden frame_quads / frame_height_maps).
- *   usage: ref_gpu_caller [frames] [cpu]   (further frames fly 20 km east per frame, reusing the cache;
+ *   usage: ref_gpu_caller [frames] [cpu|lod]   (further frames fly 20 km east per frame, reusing the cache;
  *                                           "cpu": the same program with the reference's CPU generator
  *                                           installed instead -- the other side of the comparison on a box
- *                                           that has no /root/reference and no golden for later frames)
+ *                                           that has no /root/reference and no golden for later frames;
+ *                                           "lod": the second half of INTEGRATION.md's minimum edit as well --
+ *                                           the six ProcessQuad calls of RenderPlanet (main.cpp:604-624) replaced
+ *                                           by ONE planet_gpu_select_lod, the reference's own per-leaf
+ *                                           GetHeightMapForQuad loop (main.cpp:652-660, :682) behind it)
  */
 #ifdef PLANET_REAL_CALLER
 #define PLANET_HOST_NO_TYPES
 #include "../planet_b200/host/planet_host.h"
+#include <cuda_runtime_api.h>
+
+/* RenderPlanet with its quadtree recursion on the GPU: leaves from planet_gpu_select_lod into the
+ * reference's planet.quads, then the reference's own cache lookups in the reference's order.  (Draw
+ * submission, main.cpp:662-679, is presentation and not needed to see what was uploaded.) */
+static bool render_planet_gpu_lod(Planet &planet, const CameraInfo &cam, planet_gpu_quad *d_leaves, int64_t capacity)
+{
+    planet_gpu_params params;
+    planet_gpu_default_params(&params);
+    params.radius = planet.radius;
+    const double cam_pos[3] = { cam.position.x, cam.position.y, cam.position.z };
+    int64_t n = 0;
+    if (planet_gpu_select_lod(&params, cam_pos, planet.max_lod, d_leaves, capacity, &n, nullptr) != PLANET_OK) {
+        fprintf(stderr, "[ERROR] planet_gpu_select_lod: %s\n", planet_gpu_last_error());
+        return false;
+    }
+    ListResize(planet.quads, (int)n);
+    if (cudaMemcpy(planet.quads.data, d_leaves, sizeof(Quad) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+    int generations_per_frame = 100;                                   /* main.cpp:652-653 */
+    for (int i = 0; i < planet.quads.num; ++i)                         /* main.cpp:655-660 */
+        GetHeightMapForQuad(planet, planet.quads.data[i], generations_per_frame);
+    planet.render_tick++;                                              /* main.cpp:682 */
+    return true;
+}
 
 static void write_all(const void *p, size_t n) { if (fwrite(p, 1, n, stdout) != n) exit(4); }
 
@@ -540,7 +568,9 @@ int main(int argc, char **argv)
 {
     const int frames = argc > 1 ? atoi(argv[1]) : 1;
     const double radius = 6371000.0;                                   /* main.cpp:821 */
-    const bool cpu = argc > 2 && !strcmp(argv[2], "cpu");
+    const bool cpu = argc > 2 && !strcmp(argv[2], "cpu"), lod = argc > 2 && !strcmp(argv[2], "lod");
+    planet_gpu_quad *d_leaves = nullptr;
+    const int64_t capacity = 1 << 16;
     HeightMapGenerator hmap_gen = cpu ? g_gen                          /* main.cpp:843 as it is */
                                       : CreateGpuHeightMapGenerator(); /* instead of main.cpp:843 */
     if (!hmap_gen.GenerateHeightMap || !hmap_gen.GetHeightAt) return 3;
@@ -553,7 +583,12 @@ int main(int argc, char **argv)
         cam_info.rotation = Mat3Identity();
         InitCameraInfo(cam_info, DegToRad(50.0f), 800.0f / 600.0f, 1.0f, 20000000.0f);      /* main.cpp:1072-1075 */
         fakegl::reset_frame();
-        RenderPlanet(planet, cam_info);                                /* main.cpp:1087 */
+        if (lod) {
+            if (!d_leaves && cudaMalloc((void **)&d_leaves, sizeof(planet_gpu_quad) * capacity) != cudaSuccess) return 5;
+            if (!render_planet_gpu_lod(planet, cam_info, d_leaves, capacity)) return 6;
+        } else {
+            RenderPlanet(planet, cam_info);                            /* main.cpp:1087 */
+        }
         int64_t n = planet.quads.num;
         write_all(&n, sizeof n);
         write_all(planet.quads.data, (size_t)n * sizeof(Quad));

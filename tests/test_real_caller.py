@@ -85,3 +85,18 @@ def test_reference_flight_of_eight_frames_gpu_generator_vs_cpu_generator(gpu):
         assert qa.tobytes() == qb.tobytes()
         assert (as_bits(ma) == as_bits(mb)).all()
     assert a == b
+
+
+@pytest.mark.gpu
+def test_reference_cache_loop_behind_gpu_lod_selection(gpu):
+    """Both halves of INTEGRATION.md's minimum edit: the GPU generator installed through InitPlanet AND
+    RenderPlanet's ProcessQuad recursion (main.cpp:604-624) replaced by one planet_gpu_select_lod, the
+    reference's own GetHeightMapForQuad loop (main.cpp:652-660) running behind it.  Leaves and uploaded maps
+    of an 8-frame flight are byte-identical to the untouched reference with its CPU generator."""
+    need_exe()
+    a = subprocess.run([EXE, "8", "lod"], capture_output=True, check=True).stdout
+    b = subprocess.run([EXE, "8", "cpu"], capture_output=True, check=True).stdout
+    for k, ((qa, ma), (qb, mb)) in enumerate(zip(parse_frames(a, 8), parse_frames(b, 8))):
+        assert qa.tobytes() == qb.tobytes(), k
+        assert (as_bits(ma) == as_bits(mb)).all(), k
+    assert a == b
