@@ -47,7 +47,9 @@ static struct Staging {
     void *d_out = nullptr;    size_t d_out_cap = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;           // D2H of finished chunks overlaps the next chunk's kernel
-    cudaEvent_t chunk_done[8] = {};
+    cudaStream_t up_stream = nullptr;             // H2D of the quads behind the first chunk's
+    cudaEvent_t chunk_done[16] = {};
+    cudaEvent_t quads_up = nullptr;
 } g_stage;
 
 int set_error(int code, const char *fmt, ...)
@@ -152,7 +154,9 @@ static int stage_stream()
     if (!g_stage.stream) PLANET_CUDA(cudaStreamCreateWithFlags(&g_stage.stream, cudaStreamNonBlocking));
     if (!g_stage.copy_stream) {
         PLANET_CUDA(cudaStreamCreateWithFlags(&g_stage.copy_stream, cudaStreamNonBlocking));
+        PLANET_CUDA(cudaStreamCreateWithFlags(&g_stage.up_stream, cudaStreamNonBlocking));
         for (auto &e : g_stage.chunk_done) PLANET_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        PLANET_CUDA(cudaEventCreateWithFlags(&g_stage.quads_up, cudaEventDisableTiming));
     }
     return 0;
 }
@@ -211,7 +215,9 @@ void planet_gpu_shutdown(void)
     if (g_stage.stream) cudaStreamDestroy(g_stage.stream);
     if (g_stage.copy_stream) {
         cudaStreamDestroy(g_stage.copy_stream);
+        if (g_stage.up_stream) cudaStreamDestroy(g_stage.up_stream);
         for (auto &e : g_stage.chunk_done) if (e) cudaEventDestroy(e);
+        if (g_stage.quads_up) { cudaEventDestroy(g_stage.quads_up); g_stage.quads_up = nullptr; }
     }
     g_stage = Staging();
     release_lod_scratch();
@@ -309,13 +315,42 @@ static int host_pipeline(const planet_gpu_params *p, const planet_gpu_quad *h_qu
     // pinned buffers.  Callers that want full PCIe rate pass cudaHostRegister'ed memory.
     // The output (dim*dim*4 bytes per quad) dominates the PCIe traffic, so large batches run as
     // a pipeline: kernel on chunk c while chunk c-1 drains to the host on the copy stream.
-    const int chunks = nquads >= 4096 ? 8 : nquads >= 256 ? 4 : 1;
+    // Chunk boundaries.  What the caller waits for is the PCIe drain (67 MB at ~55 GB/s for a C2 batch against
+    // 0.43 ms of K2), so the first bytes should start crossing as early as possible and the link must
+    // never run dry afterwards: the first chunk is ONE wave of the height-map kernel (a 128-sample tile for
+    // each of its resident warps, ~20 us), then 2, 4, 8, 8, ... waves -- every chunk's copy is at least as
+    // long as the next chunk's kernel.  Whole waves keep every warp of a chunk equally loaded.  The quads
+    // are uploaded in two copies, the first chunk's ahead of the rest.
     const size_t per_quad = (size_t)dim * dim;
+    int device = 0, sms = 148;
+    cudaGetDevice(&device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int64_t wave_quads = std::max<int64_t>(1, ((int64_t)sms * 24 * 128 + (int64_t)per_quad - 1) / (int64_t)per_quad);
+    int64_t bounds[17] = { 0 };
+    int chunks = 0;
+    if (nquads < 256) {
+        bounds[++chunks] = nquads;
+    } else {
+        int64_t waves = 1;
+        while (bounds[chunks] < nquads && chunks < 16) {
+            int64_t hi = std::min(nquads, bounds[chunks] + waves * wave_quads);
+            if (chunks == 15 || nquads - hi < wave_quads / 2) hi = nquads;        // last slot, or only a crumb left
+            bounds[++chunks] = hi;
+            waves = std::min<int64_t>(waves * 2, 8);
+        }
+    }
     auto enqueue = [&]() -> int {
-        PLANET_CUDA(cudaMemcpyAsync(g_stage.d_in, h_quads, in_bytes, cudaMemcpyHostToDevice, g_stage.stream));
+        const size_t first_in = (size_t)bounds[1] * sizeof(Quad);
+        PLANET_CUDA(cudaMemcpyAsync(g_stage.d_in, h_quads, first_in, cudaMemcpyHostToDevice, g_stage.stream));
+        if (in_bytes > first_in) {                                    // the other quads go up beside chunk 0, on their own stream
+            PLANET_CUDA(cudaMemcpyAsync((char *)g_stage.d_in + first_in, (const char *)h_quads + first_in, in_bytes - first_in,
+                                        cudaMemcpyHostToDevice, g_stage.up_stream));
+            PLANET_CUDA(cudaEventRecord(g_stage.quads_up, g_stage.up_stream));
+        }
         for (int c = 0; c < chunks; c++) {
-            const int64_t lo = nquads * c / chunks, hi = nquads * (c + 1) / chunks;
+            const int64_t lo = bounds[c], hi = bounds[c + 1];
             if (hi == lo) continue;
+            if (c == 1) PLANET_CUDA(cudaStreamWaitEvent(g_stage.stream, g_stage.quads_up, 0));   // chunk 1's kernel is the first to need them
             int r = launch_height_maps(p, (const Quad *)g_stage.d_in + lo, hi - lo, dim, max_depth,
                                        d_out + lo * per_quad, g_stage.stream);
             if (r) return r;
@@ -337,6 +372,7 @@ static int host_pipeline(const planet_gpu_params *p, const planet_gpu_quad *h_qu
     // buffer, which must not be touched after this call returns.
     cudaError_t e1 = cudaStreamSynchronize(g_stage.stream);
     cudaError_t e2 = chunks > 1 ? cudaStreamSynchronize(g_stage.copy_stream) : cudaSuccess;
+    if (g_stage.up_stream) cudaStreamSynchronize(g_stage.up_stream);
     if (rc) return rc;
     if (e1 != cudaSuccess) return check_cuda(e1, "height maps (host path)");
     return check_cuda(e2, "height maps D2H");

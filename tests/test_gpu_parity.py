@@ -379,6 +379,35 @@ def test_large_maps_dim_1024_and_4096(gpu, golden):
     assert bool((e4.double() - f4.double()).abs().max() <= tol)
 
 
+@pytest.mark.parametrize("dim", [128, 512, 2048])
+def test_c5_dims_between_the_probes(gpu, port, golden, dim):
+    """BASELINE config 5 sweeps dim 64..4096; 1024 and 4096 are covered above, these are the sizes
+    between: EXACT bit-identical to the oracle on whole maps (the small-batch kernel at 128 and 512,
+    the table kernel at 2048), FAST within tolerance, for a shallow and a deep leaf of the frame."""
+    quads = quads_from_bytes(golden["frame_quads"])[[0, 116 if dim < 2048 else 0]][: 2 if dim < 2048 else 1]
+    exact, fast = gpu.default_params(), gpu.default_params(precision=gpu.FAST)
+    dq = gpu.quads_to_device(quads)
+    got = to_np(gpu.generate_height_maps(dq, dim, 18, exact))
+    want = port.generate_height_maps(quads, dim, 18, orc_params(exact), nthreads=8)
+    assert as_bits(got).tobytes() == as_bits(want).tobytes()
+    f = to_np(gpu.generate_height_maps(dq, dim, 18, fast))
+    octs = 6 + 12 * int((int(quads["id"].max()) >> 55) & 31) // 18
+    assert np.abs(f.astype(np.float64) - want).max() <= REL_TOL * 8848.0 * amp_sum(0.55, octs)
+
+
+@pytest.mark.parametrize("n", [62, 126, 254])
+def test_c5_shade_at_larger_patches(gpu, port, golden, n):
+    """K3 at the C5 patch sizes it supports (dim = n + 2 = 64, 128, 256: the map of a patch must fit
+    the warp's shared-memory staging; larger patches return PLANET_E_UNSUPPORTED, tested below)."""
+    quads = quads_from_bytes(golden["frame_quads"])[[3, 60]]
+    maps = port.generate_height_maps(quads, n + 2, 18, height_params(), nthreads=4)
+    check_shade(gpu, port, quads, maps, golden["frame_cam"], n=n)
+    if n == 254:
+        import torch
+        with pytest.raises(gpu.PlanetGpuError, match="patch_verts"):
+            gpu.shade(gpu.quads_to_device(quads), torch.zeros((2, 258, 258), device="cuda"), golden["frame_cam"], gpu.default_params(patch_verts=256))
+
+
 def test_batched_api_from_four_threads_on_four_streams(gpu):
     """The batched entry points are stream-ordered and re-entrant: four host threads, each on its
     own CUDA stream, run K1 + K2 + K3 on different quad ranges and get the single-threaded bytes."""
@@ -461,7 +490,7 @@ def test_host_batch_path_equals_device_path(gpu, golden):
     assert host.tobytes() == dev.tobytes()
 
 
-@pytest.mark.parametrize("nquads", [117, 1024, 6144])           # 1, 4 and 8 pipeline chunks
+@pytest.mark.parametrize("nquads", [117, 1024, 6144, 16384])    # 1, 2, 4 and 7 pipeline chunks (1, 2, 4, 8, 8 ... waves)
 def test_terrain_host_equals_separate_calls(gpu, nquads):
     """planet_gpu_terrain_host = generate_height_maps_host + shade, byte for byte (K3 only
     overlaps the PCIe drain; it must still see every finished map)."""

@@ -94,7 +94,7 @@ def graph_time(fn, per_graph=20, reps=5):
 
 
 root = pb.tessellate_uniform(3, 0, 256, p2)
-for dim in (64, 256, 1024, 4096):
+for dim in (64, 128, 256, 512, 1024, 2048, 4096):
     for octaves in (1, 8, 16):
         for batch in (1, 4, 16, 64, 256):
             if dim * dim * batch > 1 << 26:
@@ -104,3 +104,14 @@ for dim in (64, 256, 1024, 4096):
             ms = graph_time(lambda: pb.generate_height_maps(root[:batch], dim, 18, pp, out=out))
             print(json.dumps({"config": "C5", "dim": dim, "octaves": octaves, "batch": batch, "ms": ms,
                               "us_per_patch": ms * 1e3 / batch, "gvert_s": batch * dim * dim / ms / 1e6}), flush=True)
+
+# C5, the shade kernel at the patch sizes it takes (a patch's map must fit the warp's shared-memory staging: dim <= 256)
+for dim in (64, 128, 256):
+    for batch in (1, 16, 256):
+        pp = pb.fbm_params(8, 0.5, pb.FAST, patch_verts=dim - 2)
+        maps = pb.generate_height_maps(root[:batch], dim, 18, pp)
+        nv = pb.patch_vertex_count(dim - 2)
+        pos = torch.empty((batch, nv, 4), dtype=torch.float32, device="cuda"); nrm = torch.empty_like(pos)
+        ms = graph_time(lambda: pb.shade(root[:batch], maps, (0.0, 0.0, -6371010.0), pp, pos=pos, nrm=nrm))
+        print(json.dumps({"config": "C5 K3", "dim": dim, "batch": batch, "ms": ms, "us_per_patch": ms * 1e3 / batch,
+                          "gvert_s": batch * nv / ms / 1e6, "GBs_written": batch * nv * 32 / ms / 1e6}), flush=True)
