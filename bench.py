@@ -470,6 +470,14 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize()
         if i >= 3:
             e2e_t.append(time.perf_counter() - t0)
+    # what the PCIe link alone does with the step's output: one D2H copy of the whole batch into the same pinned buffer
+    d2h_t = []
+    for i in range(2 + 5):
+        a, b_ = ev(), ev()
+        a.record(); h_out.copy_(local_maps, non_blocking=True); b_.record()
+        torch.cuda.synchronize()
+        if i >= 2: d2h_t.append(a.elapsed_time(b_))
+    d2h_ms = float(np.mean(d2h_t))
     sampler.stop_flag = True
     sampler.join()
     e2e_ms = 1e3 * float(np.mean(e2e_t))
@@ -531,7 +539,12 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": total_verts / (e2e_ms * 1e-3), "unit": "vertices/s",
                     "h2d_bytes_per_step": nq * 104, "d2h_bytes_per_step": nq * DIM * DIM * 4,
                     "ms_per_step": e2e_ms, "bytes_are": "per GPU",
-                    "path": "planet_gpu_terrain_host: pinned host quads -> K2 -> pinned host heights (8-chunk pipeline) + K3 on the resident maps"},
+                    "path": "planet_gpu_terrain_host: pinned host quads -> K2 -> pinned host heights (pipelined in chunks of 1, 2, 4, 8, 8 ... "
+                            "kernel waves) + K3 on the resident maps",
+                    "pcie_floor": {"d2h_copy_of_the_output_alone_ms": d2h_ms, "GBs": nq * DIM * DIM * 4 / (d2h_ms * 1e-3) / 1e9,
+                                   "frac": d2h_ms / e2e_ms,
+                                   "what": "one cudaMemcpyAsync of this rank's height maps to the same pinned buffer, measured on rank 0 in this run: the part of "
+                                           "e2e that is the PCIe link; frac = that time / e2e time"}},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
