@@ -473,6 +473,7 @@ def run_ours(args, rank, local_rank, world):
     # what the PCIe link alone does with the step's output: one D2H copy of the whole batch into the same pinned buffer
     d2h_t = []
     for i in range(2 + 5):
+        barrier()                                                          # all ranks copy at once, as in the e2e step
         a, b_ = ev(), ev()
         a.record(); h_out.copy_(local_maps, non_blocking=True); b_.record()
         torch.cuda.synchronize()
@@ -543,8 +544,8 @@ def run_ours(args, rank, local_rank, world):
                             "kernel waves) + K3 on the resident maps",
                     "pcie_floor": {"d2h_copy_of_the_output_alone_ms": d2h_ms, "GBs": nq * DIM * DIM * 4 / (d2h_ms * 1e-3) / 1e9,
                                    "frac": d2h_ms / e2e_ms,
-                                   "what": "one cudaMemcpyAsync of this rank's height maps to the same pinned buffer, measured on rank 0 in this run: the part of "
-                                           "e2e that is the PCIe link; frac = that time / e2e time"}},
+                                   "what": "one cudaMemcpyAsync of this rank's height maps to the same pinned buffer, all ranks copying at the same time, "
+                                           "rank 0's figure: the part of e2e that is the PCIe link / the host's memory path; frac = that time / e2e time"}},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
