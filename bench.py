@@ -286,6 +286,10 @@ def run_ours(args, rank, local_rank, world):
         chunks.append((at, n))
         at += n
 
+    k1_beside = world == 1 and os.environ.get("PLANET_K1_BESIDE", "1") != "0"
+    side1 = torch.cuda.Stream(device=dev) if k1_beside else None
+    side1_p = C.c_void_p(side1.cuda_stream) if k1_beside else None
+
     def k1_quads():
         pb._check(L.planet_gpu_tessellate_uniform(pp, DEPTH, lo, nq, quads.data_ptr(), None, sp))
 
@@ -313,7 +317,24 @@ def run_ours(args, rank, local_rank, world):
         """One step; with `marks`, CUDA events on the launching stream around every kernel."""
         e = [ev() for _ in range(5)] if marks is not None else None
         if e: e[0].record()
-        if gather is None:
+        if gather is None and k1_beside:
+            # K1 in its two independent halves: the quads (K2 needs them) on the main stream, the merged index
+            # stream -- nothing but HBM writes -- by the slim kernel on a side stream, resident on the SMs
+            # BESIDE K2, which keeps their arithmetic busy and never touches HBM
+            fork = torch.cuda.Event()
+            fork.record(stream)
+            side1.wait_event(fork)
+            pb._check(L.planet_gpu_merged_indices_beside(pp, nq, indices.data_ptr(), side1_p))
+            join = torch.cuda.Event()
+            join.record(side1)
+            k1_quads()
+            if e: e[1].record()
+            k2(heights)
+            if e: e[2].record()
+            k3(heights)
+            stream.wait_event(join)                                         # the step is over when the index stream is too
+            if e: e[3].record(); e[4].record()
+        elif gather is None:
             k1()
             if e: e[1].record()
             k2(heights)
@@ -420,7 +441,7 @@ def run_ours(args, rank, local_rank, world):
         k2(plain)
 
     # ---- N = 1 extras: EXACT-mode K2, full-size parity figures, K1 at a size L2 cannot absorb ----
-    ms_k2_exact, fast_err, exact_maps_host, k1_c3_ms = None, None, None, None
+    ms_k2_exact, fast_err, exact_maps_host, k1_c3_ms, k1_c2_ms = None, None, None, None, None
     if world == 1:
         p_exact = pb.fbm_params(octaves=OCTAVES, gain=GAIN, precision=pb.EXACT)
         ppe = C.byref(p_exact)
@@ -438,6 +459,15 @@ def run_ours(args, rank, local_rank, world):
         # FAST against the bit-exact mode on all 16.8 M samples, with the bound the tests use
         fast_err = float(np.abs(heights.cpu().numpy().astype(np.float64) - exact_maps_host).max())
         del scratch
+        # K1 (quads + merged index stream, one launch) alone at C2 size, L2 flushed before each
+        t2 = []
+        for i in range(3 + 10):
+            flush.zero_()
+            a, b_ = ev(), ev()
+            a.record(); k1(); b_.record(); torch.cuda.synchronize()
+            if i >= 3:
+                t2.append(a.elapsed_time(b_))
+        k1_c2_ms = float(np.mean(t2))
         # K1 at C3 size: 98 304 quads, 811 MB written -- six times the 126 MB L2
         q3 = 6 * QUADS_PER_FACE
         quads3 = torch.empty((q3, 13), dtype=torch.int64, device=dev)
@@ -515,7 +545,9 @@ def run_ours(args, rank, local_rank, world):
             "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config,
-            "ms": ({"k1_tessellate": ms_k1, "k2_heights": ms_k2, "k3_shade": ms_k3, "k2_heights_exact_mode": ms_k2_exact} if world == 1 else
+            "ms": (({"k1_quads": ms_k1, "k2_heights_with_k1_index_stream_beside_it": ms_k2, "k3_shade": ms_k3,
+                     "k1_tessellate_alone": k1_c2_ms, "k2_heights_exact_mode": ms_k2_exact} if k1_beside else
+                    {"k1_tessellate": ms_k1, "k2_heights": ms_k2, "k3_shade": ms_k3, "k2_heights_exact_mode": ms_k2_exact}) if world == 1 else
                    {"k1_quads": ms_k1, "k2_heights_with_gather": ms_k2, "k3_shade_with_gather_and_k1_indices_beside_it": ms_k3,
                     "wait_for_peers": ms_wait}),
             "parity": {"fast_vs_exact_max_abs_m": fast_err, "tolerance_m": fast_tol},
@@ -527,10 +559,13 @@ def run_ours(args, rank, local_rank, world):
                          "frac_of_nominal": k2_tf / nominal_tf, "flop_per_vertex": FLOP_PER_VERTEX,
                          "vertices_per_launch": verts_rank, "ms": ms_k2},
             "roofline_k1": {"kernel": "k_tessellate_bulk", "bound": "hbm",
-                            "achieved": k1_bytes / (ms_k1 * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": k1_bytes / (ms_k1 * 1e-3) / 1e9 / hbm_peak, "bytes": k1_bytes, "ms": ms_k1,
+                            "achieved": k1_bytes / ((k1_c2_ms or ms_k1) * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": k1_bytes / ((k1_c2_ms or ms_k1) * 1e-3) / 1e9 / hbm_peak, "bytes": k1_bytes, "ms": k1_c2_ms or ms_k1,
                             "peak_source": peak_src,
-                            "note": "write-only; at this size part of the stream is still in the 126 MB L2 when the kernel ends"},
+                            "note": "the one-launch K1 (quads + index stream) timed alone, L2 flushed before; write-only, and at this size part of "
+                                    "the stream is still in the 126 MB L2 when the kernel ends.  Inside the step the index stream runs as "
+                                    "k_index_stream_slim beside K2 (ms.k2_heights_with_k1_index_stream_beside_it)" if k1_beside else
+                                    "write-only; at this size part of the stream is still in the 126 MB L2 when the kernel ends"},
             # bytes that reach HBM: the two float4 streams written + the quads read.  At N = 1 the 67 MB of
             # height maps K2 wrote in the same step are L2 hits (L2 is flushed between steps, not between
             # K2 and K3); frac follows from bytes_hbm, bytes_algorithmic is printed beside it

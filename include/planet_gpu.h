@@ -200,6 +200,12 @@ int planet_gpu_noise(const double *d_xyz, int64_t n, int kind, double lacunarity
 int planet_gpu_tessellate_uniform(const planet_gpu_params *p, int depth, int64_t first,
                                   int64_t nquads, planet_gpu_quad *d_quads, uint32_t *d_indices,
                                   void *stream);
+/* The merged strip index buffer of `nquads` patches alone (d_indices[q*ni + k] = q*nv + strip[k],
+ * main.cpp:427-474 rebased) by a kernel small enough to be resident BESIDE the height-map kernel:
+ * issue it on a second stream next to planet_gpu_generate_height_maps -- K2 keeps the SMs'
+ * arithmetic busy and never touches HBM, the index stream is nothing but HBM writes.  Same bytes as
+ * planet_gpu_tessellate_uniform(..., NULL, d_indices, ...). */
+int planet_gpu_merged_indices_beside(const planet_gpu_params *p, int64_t nquads, uint32_t *d_indices, void *stream);
 /* corners of arbitrary quads from their QuadIDs (main.cpp:19-65 encoding) */
 int planet_gpu_quads_from_ids(const planet_gpu_params *p, const uint64_t *d_ids, int64_t n,
                               planet_gpu_quad *d_quads, void *stream);

@@ -84,6 +84,7 @@ def lib():
             "planet_gpu_heights_at": (i, [pp, vp, i64, i, i, vp, vp]),
             "planet_gpu_noise": (i, [vp, i64, i, d, f, i, i, vp, vp]),
             "planet_gpu_tessellate_uniform": (i, [pp, i, i64, i64, vp, vp, vp]),
+            "planet_gpu_merged_indices_beside": (i, [pp, i64, vp, vp]),
             "planet_gpu_quads_from_ids": (i, [pp, vp, i64, vp, vp]),
             "planet_gpu_patch_mesh": (i, [i, vp, vp, vp]),
             "planet_gpu_patch_vertex_count": (i, [i]),
@@ -123,7 +124,7 @@ EXPORTED_SYMBOLS = [
     "planet_gpu_gather_destroy", "planet_gpu_gather_buffer", "planet_gpu_gather_last_buffer",
     "planet_gpu_gather_height_maps", "planet_gpu_gather_wait", "planet_gpu_gather_begin", "planet_gpu_gather_push",
     "planet_gpu_gather_publish", "planet_gpu_gather_set_push_mode", "planet_gpu_gather_set_shade_share", "planet_gpu_gather_shade", "planet_gpu_gather_nccl",
-    "planet_gpu_gather_barrier", "planet_gpu_gather_error", "planet_gpu_heights_at", "planet_gpu_noise", "planet_gpu_tessellate_uniform",
+    "planet_gpu_gather_barrier", "planet_gpu_gather_error", "planet_gpu_heights_at", "planet_gpu_noise", "planet_gpu_tessellate_uniform", "planet_gpu_merged_indices_beside",
     "planet_gpu_quads_from_ids", "planet_gpu_patch_mesh", "planet_gpu_patch_vertex_count",
     "planet_gpu_patch_index_count", "planet_gpu_strip_index", "planet_gpu_uniform_leaf_id",
     "planet_gpu_max_lod", "planet_gpu_max_skirt_size",
@@ -221,6 +222,16 @@ def tessellate_uniform(depth, first=0, nquads=None, params=None, with_indices=Fa
     _check(lib().planet_gpu_tessellate_uniform(C.byref(params), depth, first, nquads, quads.data_ptr(),
                                                idx.data_ptr() if idx is not None else None, _stream(stream)))
     return (quads, idx) if with_indices else quads
+
+
+def merged_indices_beside(nquads, params=None, out=None, stream=None):
+    """The merged strip index buffer alone, by the kernel small enough to run beside K2 (issue it on a side stream)."""
+    torch = _torch()
+    params = params or default_params()
+    if out is None:
+        out = torch.empty(nquads * patch_index_count(params.patch_verts), dtype=torch.int32, device="cuda")
+    _check(lib().planet_gpu_merged_indices_beside(C.byref(params), nquads, out.data_ptr(), _stream(stream)))
+    return out
 
 
 def quads_from_ids(ids, params=None, stream=None):

@@ -303,6 +303,29 @@ k_tessellate_bulk(int depth, int64_t first, int64_t nquads, double radius, Quad 
     if (threadIdx.x == 0) tma::wait_all<0>();
 }
 
+// The merged index stream by a kernel small enough to live BESIDE the height-map kernel: K2 keeps
+// an SM's arithmetic busy and never touches HBM, the index stream is nothing but HBM writes, so the
+// two belong on the same SMs at the same time.  A resident 768-thread K2 CTA leaves 4 096
+// registers and ~10 KB of shared memory per SM: this kernel takes 128 threads x <= 32 registers and
+// no shared memory (the 8 KB strip of one patch is read through L1), one 16-byte store per thread
+// per step, (quad, vector) advanced incrementally so there is no division in the loop.
+__global__ void __launch_bounds__(128, 16)
+k_index_stream_slim(int64_t nquads, int nv, int nvec, uint4 *__restrict__ out, const uint4 *__restrict__ strip)
+{
+    const uint32_t stride = gridDim.x * 128u;
+    const uint32_t dq = stride / (uint32_t)nvec, dk = stride - dq * (uint32_t)nvec;
+    const uint32_t t = blockIdx.x * 128u + threadIdx.x;
+    uint32_t q = t / (uint32_t)nvec, k = t - q * (uint32_t)nvec;
+    uint4 *dst = out + t;
+    for (; q < (uint32_t)nquads; dst += stride) {
+        const uint4 sv = __ldg(strip + k);
+        const uint32_t base = q * (uint32_t)nv;                          // idx[q][k] = q*nv + strip[k]
+        __stcs(dst, make_uint4(sv.x + base, sv.y + base, sv.z + base, sv.w + base));
+        q += dq; k += dk;
+        if (k >= (uint32_t)nvec) { k -= (uint32_t)nvec; q++; }
+    }
+}
+
 // the reference's static patch: vertices (main.cpp:402-425) and indices (:427-474)
 __global__ void k_patch_mesh(int n, float *__restrict__ verts, uint32_t *__restrict__ indices)
 {
@@ -438,6 +461,30 @@ int launch_tessellate_uniform(const planet_gpu_params *p, int depth, int64_t fir
     }
     count_launch();
     return check_cuda(cudaGetLastError(), "tessellate launch");
+}
+
+// the merged strip indices of `nquads` patches by the slim kernel (see k_index_stream_slim)
+int launch_index_stream_beside(const planet_gpu_params *p, int64_t nquads, uint32_t *d_indices, cudaStream_t stream)
+{
+    if (nquads == 0) return 0;
+    const int n = p->patch_verts;
+    const int nv = n * n + 4 * n, ni = 2 * n * n + 8 * n - 4;
+    if ((uint64_t)nquads * (uint64_t)nv > 0xFFFFFFFFull)
+        return set_error(PLANET_E_INVALID, "merged vertex count %lld x %d exceeds uint32 indices", (long long)nquads, nv);
+    if ((ni & 3) || (reinterpret_cast<uintptr_t>(d_indices) & 15) || (uint64_t)nquads * (uint64_t)(ni / 4) > 0xFFFFFFFFull)
+        return launch_tessellate_uniform(p, 0, 0, nquads, nullptr, d_indices, stream);   // shapes the 16-byte stream cannot take
+    const uint32_t *strip = cached_strip(n, ni, stream);
+    static bool carveout[64] = {};                                       // it must fit on an SM whose carve-out K2 has set
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!carveout[dev & 63]) {
+        PLANET_CUDA(cudaFuncSetAttribute(k_index_stream_slim, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        carveout[dev & 63] = true;
+    }
+    k_index_stream_slim<<<sm_count_k1(), 128, 0, stream>>>(nquads, nv, ni / 4, reinterpret_cast<uint4 *>(d_indices),
+                                                           reinterpret_cast<const uint4 *>(strip));
+    count_launch();
+    return check_cuda(cudaGetLastError(), "index stream launch");
 }
 
 int launch_quads_from_ids(const planet_gpu_params *p, const uint64_t *d_ids, int64_t n, Quad *d_quads,

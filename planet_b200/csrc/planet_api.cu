@@ -22,6 +22,7 @@ int launch_height_at_seam(const planet_gpu_params *, const double *, int, int, f
 int launch_noise(const double *, int64_t, int, double, float, int, int, float *, cudaStream_t);
 int launch_tessellate_uniform(const planet_gpu_params *, int, int64_t, int64_t, Quad *, uint32_t *, cudaStream_t);
 int launch_quads_from_ids(const planet_gpu_params *, const uint64_t *, int64_t, Quad *, cudaStream_t);
+int launch_index_stream_beside(const planet_gpu_params *, int64_t, uint32_t *, cudaStream_t);
 int launch_patch_mesh(int, float *, uint32_t *, cudaStream_t);
 int launch_shade(const planet_gpu_params *, const Quad *, int64_t, const double *, const float *,
                  const planet_gpu_texrect *, float, float *, float *, cudaStream_t);
@@ -489,6 +490,16 @@ int planet_gpu_tessellate_uniform(const planet_gpu_params *p, int depth, int64_t
                          (long long)(first + nquads), (long long)leaves);
     if (nquads > 0 && !d_quads && !d_indices) return set_error(PLANET_E_INVALID, "both d_quads and d_indices are NULL");
     return launch_tessellate_uniform(p, depth, first, nquads, (Quad *)d_quads, d_indices, (cudaStream_t)stream);
+}
+
+int planet_gpu_merged_indices_beside(const planet_gpu_params *p, int64_t nquads, uint32_t *d_indices, void *stream)
+{
+    if (!ensure_init()) return PLANET_E_NO_DEVICE;
+    int rc = validate_params(p);
+    if (rc) return rc;
+    if (nquads < 0 || (nquads > 0 && !d_indices)) return set_error(PLANET_E_INVALID, "NULL buffer");
+    if ((reinterpret_cast<uintptr_t>(d_indices) & 7) != 0) return set_error(PLANET_E_INVALID, "index buffer must be 8-byte aligned");
+    return launch_index_stream_beside(p, nquads, d_indices, (cudaStream_t)stream);
 }
 
 int planet_gpu_quads_from_ids(const planet_gpu_params *p, const uint64_t *d_ids, int64_t n,

@@ -379,6 +379,26 @@ def test_large_maps_dim_1024_and_4096(gpu, golden):
     assert bool((e4.double() - f4.double()).abs().max() <= tol)
 
 
+@pytest.mark.parametrize("n,nq", [(30, 16384), (30, 7), (12, 333), (5, 40), (44, 100)])
+def test_index_stream_beside_k2_writes_the_same_indices(gpu, n, nq):
+    """planet_gpu_merged_indices_beside (the slim kernel that shares the SMs with K2; n = 5 has ni % 4 != 0 and
+    takes the general path) against K1's own index stream, alone and while K2 runs on another stream."""
+    import torch
+    p = gpu.fbm_params(8, 0.5, gpu.FAST, patch_verts=n)
+    _, want = gpu.tessellate_uniform(7, first=0, nquads=nq, params=p, with_indices=True)
+    assert torch.equal(gpu.merged_indices_beside(nq, p), want)
+    quads = gpu.tessellate_uniform(7, first=0, nquads=max(nq, 2048), params=p)
+    side = torch.cuda.Stream()
+    out = torch.full_like(want, -1)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        gpu.merged_indices_beside(nq, p, out=out, stream=side)
+    maps = gpu.generate_height_maps(quads, n + 2, 18, p)                    # main stream, at the same time
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
+    assert torch.equal(maps, gpu.generate_height_maps(quads, n + 2, 18, p))
+
+
 @pytest.mark.parametrize("dim", [128, 512, 2048])
 def test_c5_dims_between_the_probes(gpu, port, golden, dim):
     """BASELINE config 5 sweeps dim 64..4096; 1024 and 4096 are covered above, these are the sizes
