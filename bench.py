@@ -286,7 +286,10 @@ def run_ours(args, rank, local_rank, world):
         chunks.append((at, n))
         at += n
 
-    k1_beside = world == 1 and os.environ.get("PLANET_K1_BESIDE", "1") != "0"
+    # PLANET_K1_BESIDE=1: K1's index stream by the slim kernel on a side stream beside K2.  Measured neutral at C2
+    # (step 0.5672 -> 0.5637 ms: the stream leaves the critical path, K2 beside it runs 1.6 % slower, and what stays
+    # in front of K2 is the quads kernel's fp64 latency, 0.020 ms), so the default step keeps its three kernels in a row
+    k1_beside = world == 1 and os.environ.get("PLANET_K1_BESIDE", "0") != "0"
     side1 = torch.cuda.Stream(device=dev) if k1_beside else None
     side1_p = C.c_void_p(side1.cuda_stream) if k1_beside else None
 

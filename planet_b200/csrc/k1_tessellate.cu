@@ -56,29 +56,25 @@ __device__ Quad quad_from_id(uint64_t id, double radius)
         d3 s = exact::add(exact::add(exact::add(q.p[0], q.p[1]), q.p[2]), q.p[3]);
         d3 mid = exact::mul(exact::normalize(s), radius);
         // 3x3 grid g0..g8 = p0, V(0,1), p1, V(0,2), mid, V(1,3), p2, V(2,3), p3; child c takes
-        // (0,1,3,4) (1,2,4,5) (3,4,6,7) (4,5,7,8): only the two midpoints it touches are needed
-        d3 n0, n1, n2, n3;
-        if (child == 0) {
-            n0 = q.p[0];
-            n1 = exact::mul(exact::normalize(exact::add(q.p[0], q.p[1])), radius);
-            n2 = exact::mul(exact::normalize(exact::add(q.p[0], q.p[2])), radius);
-            n3 = mid;
-        } else if (child == 1) {
-            n0 = exact::mul(exact::normalize(exact::add(q.p[0], q.p[1])), radius);
-            n1 = q.p[1];
-            n2 = mid;
-            n3 = exact::mul(exact::normalize(exact::add(q.p[1], q.p[3])), radius);
-        } else if (child == 2) {
-            n0 = exact::mul(exact::normalize(exact::add(q.p[0], q.p[2])), radius);
-            n1 = mid;
-            n2 = q.p[2];
-            n3 = exact::mul(exact::normalize(exact::add(q.p[2], q.p[3])), radius);
-        } else {
-            n0 = mid;
-            n1 = exact::mul(exact::normalize(exact::add(q.p[1], q.p[3])), radius);
-            n2 = exact::mul(exact::normalize(exact::add(q.p[2], q.p[3])), radius);
-            n3 = q.p[3];
-        }
+        // (0,1,3,4) (1,2,4,5) (3,4,6,7) (4,5,7,8): only the two midpoints it touches are needed.
+        // Which two is a SELECT on the child index, not a branch: the lanes of a warp are consecutive
+        // leaves, i.e. all four children at the deepest levels, and four divergent paths of two
+        // normalisations each made those levels cost 9 normalisations instead of 3.
+        //   first midpoint  m1 = V(0,1) V(0,1) V(0,2) V(1,3)   for child 0 1 2 3
+        //   second midpoint m2 = V(0,2) V(1,3) V(2,3) V(2,3)
+        auto pick = [](bool c, const d3 &a, const d3 &b) { return d3{ c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z }; };
+        const bool hi = (child & 2) != 0, odd = (child & 1) != 0;
+        const d3 a1 = pick(hi && odd, q.p[1], q.p[0]);                    // 0 0 0 1
+        const d3 b1 = pick(hi, pick(odd, q.p[3], q.p[2]), q.p[1]);        // 1 1 2 3
+        const d3 a2 = pick(hi, q.p[2], pick(odd, q.p[1], q.p[0]));        // 0 1 2 2
+        const d3 b2 = pick(hi || odd, q.p[3], q.p[2]);                    // 2 3 3 3
+        const d3 m1 = exact::mul(exact::normalize(exact::add(a1, b1)), radius);
+        const d3 m2 = exact::mul(exact::normalize(exact::add(a2, b2)), radius);
+        // child 0: (p0, m1, m2, mid)  1: (m1, p1, mid, m2)  2: (m1, mid, p2, m2)  3: (mid, m1, m2, p3)
+        const d3 n0 = child == 0 ? q.p[0] : child == 3 ? mid : m1;
+        const d3 n1 = child == 0 ? m1 : child == 1 ? q.p[1] : child == 2 ? mid : m1;
+        const d3 n2 = child == 0 ? m2 : child == 1 ? mid : child == 2 ? q.p[2] : m2;
+        const d3 n3 = child == 0 ? mid : child == 3 ? q.p[3] : m2;
         q.p[0] = n0; q.p[1] = n1; q.p[2] = n2; q.p[3] = n3;
     }
     q.id = id;
