@@ -628,6 +628,16 @@ def run_ours(args, rank, local_rank, world):
                 "mode": gather_mode, "shade_share": shade_share if gather_mode == "fused" else 0,
                 "k2_chunks": len(chunks) if gather_mode == "push" else 1,
                 "bytes_received_per_gpu": gather_bytes_in,
+                # roofline of the fused compute + transfer step as B200_PROFILING.md defines it: the slower of the compute
+                # alone and the bytes that must cross NVLink at the measured per-direction rate (758 GB/s of payload: 900 raw
+                # minus the 18.75 % protocol share ncu counts for these writes, profiles/r02zf_fused_gather_nvlink_bytes.txt;
+                # the guide's measured peer copy is 770)
+                "roofline_k4": {"bound": "nvlink" if gather_bytes_in / 758e9 * 1e3 > compute_ms else "compute",
+                                "bytes_received_per_gpu": gather_bytes_in, "peak": 758.0, "unit": "GB/s",
+                                "transfer_alone_ms": gather_bytes_in / 758e9 * 1e3, "compute_alone_ms": compute_ms,
+                                "target_ms": max(gather_bytes_in / 758e9 * 1e3, compute_ms), "achieved_ms": ms_step,
+                                "frac": max(gather_bytes_in / 758e9 * 1e3, compute_ms) / ms_step,
+                                "peak_source": "ncu nvltx__bytes: payload / wire bytes of the kernel's own peer writes x 900 GB/s nominal"},
                 "nvlink_floor_ms": gather_bytes_in / 660e9 * 1e3,
                 "nvlink_floor_note": "bytes every GPU must receive / 660 GB/s: what this box's NVLink sustains per direction when all "
                                      "GPUs push to all peers with no arithmetic in the way (profiles/r02l_push_only_8gpu.txt; one "
