@@ -142,7 +142,8 @@ int   planet_gpu_gather_height_maps(void *gather, const planet_gpu_params *p, co
                                     int64_t nquads, int64_t first_quad, int dim, int max_depth, void *stream);
 /* Spreading the NVLink transfer over K2 AND K3: with every >= 2, planet_gpu_gather_height_maps leaves
  * every `every`-th map to the shade kernel, which stages each map in shared memory anyway and sends
- * those as one 4 KB bulk copy per peer (0 = off: K2 pushes everything).  planet_gpu_gather_shade is
+ * those as one 4 KB bulk copy per peer (0 = off: K2 pushes everything; -1 .. -7: that many maps in every 8 go to the
+ * shade kernel, for shares other than 1/every).  planet_gpu_gather_shade is
  * planet_gpu_shade for the quads of the preceding gather_height_maps, reading their maps from the
  * gathered buffer; when a share was left to it, it pushes it and signals the peers (so it MUST
  * follow every gather_height_maps while a share is set). */

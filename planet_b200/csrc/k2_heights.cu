@@ -774,7 +774,7 @@ k_height_maps_fast(const Quad *__restrict__ quads, int64_t total, int dim, Heigh
             // (fused gather) maps left to the shade kernel's push are only stored locally
             bool push_this_quad = true;
             if constexpr (GATHER)
-                if (stage_bufs && peers.k3_every > 0)
+                if (stage_bufs && peers.k3_every != 0)
                     push_this_quad = !shade_pushes_quad(peers.quad0 + q_first, peers.k3_every);
 #pragma unroll 1
             for (int t = 0; t < run * SUB; t++, r += 32 * S, o += 32 * S) {

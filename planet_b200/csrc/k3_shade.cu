@@ -340,7 +340,7 @@ int launch_shade_push(const planet_gpu_params *p, const Quad *d_quads, int64_t n
     if (const char *e = getenv("PLANET_K3_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));   // tuning knob
     int grid = (int)std::min<int64_t>((nquads + warps - 1) / warps, (int64_t)sms * per_sm);
     float4 *pos = reinterpret_cast<float4 *>(d_pos4), *nrm = reinterpret_cast<float4 *>(d_nrm4);
-    if (peers && peers->n > 0 && peers->k3_every > 0) {
+    if (peers && peers->n > 0 && peers->k3_every != 0) {
         if (d_rects || !stage) return set_error(PLANET_E_UNSUPPORTED, "shade kernel cannot push this map layout");
         shade::k_shade<true, false, true><<<grid, warps * 32, smem, stream>>>(
             d_quads, nquads, n, cam[0], cam[1], cam[2], d_heights, nullptr, max_skirt, pos, nrm, (int)per_warp, *peers);

@@ -532,7 +532,7 @@ int planet_gpu_gather_height_maps(void *gather, const planet_gpu_params *p, cons
         return check_cuda(cudaGetLastError(), "gather signal launch");
     }
     // part of the pushing may be left to the shade kernel (planet_gpu_gather_shade must then follow)
-    if (g->world > 1 && g->k3_every > 1 && nquads > 0 && dim == p->patch_verts + 2 &&
+    if (g->world > 1 && (g->k3_every > 1 || g->k3_every < 0) && nquads > 0 && dim == p->patch_verts + 2 &&
         height_maps_push_in_bulk(p, nquads, dim, max_depth, g->buffer(g->rank, b) + off, peers) &&
         shade_can_push(p, g->buffer(g->rank, b) + off)) {
         peers.k3_every = g->k3_every;
@@ -557,7 +557,7 @@ int planet_gpu_gather_height_maps(void *gather, const planet_gpu_params *p, cons
 int planet_gpu_gather_set_shade_share(void *gather, int every)
 {
     Gather *g = (Gather *)gather;
-    if (!g || every < 0 || every == 1) return set_error(PLANET_E_INVALID, "gather_set_shade_share(%d): 0 (off) or >= 2", every);
+    if (!g || every < -7 || every == 1) return set_error(PLANET_E_INVALID, "gather_set_shade_share(%d): 0 (off), >= 2 (one map in `every`) or -1 .. -7 (that many maps in 8)", every);
     g->k3_every = every;
     return 0;
 }

@@ -98,8 +98,10 @@ HeightCfg make_cfg(const planet_gpu_params *p, int max_depth);
 // Fused gather: is quad q (index in the gathered buffer) one of the 1-in-`every` whose map the shade
 // kernel pushes instead of the height-map kernel?  The q >> 2 term rotates the residue so that the
 // pushing does not always fall on the same warp of the shade kernel's 4-warp CTAs.
+// every >= 2: one map in `every`; every in [-7, -1]: -every maps in 8 (finer shares above one half)
 __host__ __device__ inline bool shade_pushes_quad(int64_t q, int every)
 {
+    if (every < 0) return (int)(((q >> 3) + q) & 7) < -every;
     return every > 0 && ((q >> 2) + q) % every == every - 1;
 }
 

@@ -1,6 +1,6 @@
 // Multi-process test driver for K4 (planet_gpu_gather_*): one process per GPU, no Python, no torch.
 //
-//   gather_driver <world> <depth> <mode>      mode: fast | exact | ragged | nccl | ce | smpush | split | concurrent | concurrent_ragged
+//   gather_driver <world> <depth> <mode>      mode: fast | exact | ragged | nccl | ce | smpush | split | split5of8 | concurrent | concurrent_ragged
 //
 // The parent forks `world` ranks before any CUDA call.  Rank 0 writes the NCCL unique id to a file
 // in a scratch directory, the others read it (the C-ABI leaves the transport to the caller).  The
@@ -82,14 +82,14 @@ static int run_rank(int rank, int world, int depth, const std::string &mode, con
         std::vector<int64_t> off(world), size(world);
         for (int r = 0; r < world; r++) { off[r] = lo[r] * texels * 4; size[r] = (lo[r + 1] - lo[r]) * texels * 4; }
         CHECK(planet_gpu_gather_nccl(g, 0, off.data(), size.data(), stream));
-    } else if (mode == "split") {
+    } else if (mode == "split" || mode == "split5of8") {
         // the NVLink transfer spread over K2 and K3: every 4th map travels from the shade kernel
         float *d_pos = nullptr, *d_nrm = nullptr;
         const int nv = planet_gpu_patch_vertex_count(params.patch_verts);
         CUDA_OK(cudaMalloc((void **)&d_pos, sizeof(float) * 4 * nv * n));
         CUDA_OK(cudaMalloc((void **)&d_nrm, sizeof(float) * 4 * nv * n));
         const double cam[3] = { 0.0, 0.0, -6371010.0 };
-        CHECK(planet_gpu_gather_set_shade_share(g, 4));
+        CHECK(planet_gpu_gather_set_shade_share(g, mode == "split" ? 4 : -5));      // every 4th map / 5 maps in 8
         for (int step = 0; step < 3; step++) {
             params.seed_offset[1] = 0.25 * step;
             CHECK(planet_gpu_gather_height_maps(g, &params, d_quads, n, first, dim, max_lod, stream));

@@ -71,7 +71,7 @@ def test_world_of_one_is_the_plain_path(driver, gpu, mode):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["fast", "ragged", "exact", "nccl", "ce", "smpush", "split", "concurrent", "concurrent_ragged"])
+@pytest.mark.parametrize("mode", ["fast", "ragged", "exact", "nccl", "ce", "smpush", "split", "split5of8", "concurrent", "concurrent_ragged"])
 def test_two_ranks_gather_the_unsharded_bytes(driver, gpu, mode):
     import torch
     if torch.cuda.device_count() < 2:

@@ -68,11 +68,12 @@ def timed(n=12):
 
 
 KNOBS = ("PLANET_PUSH_LSU", "PLANET_PUSH_EVERY", "PLANET_PUSH_CTAS")
-MODES = [("fused0", 0, 0, {}), ("fused2", 0, 2, {}),
-         ("concurrent_tma", 2, 0, {}), ("concurrent_tma_every2", 2, 0, {"PLANET_PUSH_EVERY": "2"}),
-         ("concurrent_tma_every4", 2, 0, {"PLANET_PUSH_EVERY": "4"}),
-         ("concurrent_lsu", 2, 0, {"PLANET_PUSH_LSU": "1"}), ("concurrent_lsu_every4", 2, 0, {"PLANET_PUSH_LSU": "1", "PLANET_PUSH_EVERY": "4"}),
-         ("concurrent_tma_74ctas", 2, 0, {"PLANET_PUSH_CTAS": "74"})]
+MODES = [("fused0", 0, 0, {}), ("fused2", 0, 2, {}), ("fused_3of8_to_k3", 0, -3, {}), ("fused_5of8_to_k3", 0, -5, {}), ("fused_6of8_to_k3", 0, -6, {}),
+         ("concurrent_tma", 2, 0, {}), ("concurrent_lsu", 2, 0, {"PLANET_PUSH_LSU": "1"})]
+if os.environ.get("PLANET_MODES_ALL"):
+    MODES += [("concurrent_tma_every2", 2, 0, {"PLANET_PUSH_EVERY": "2"}), ("concurrent_tma_every4", 2, 0, {"PLANET_PUSH_EVERY": "4"}),
+              ("concurrent_lsu_every4", 2, 0, {"PLANET_PUSH_LSU": "1", "PLANET_PUSH_EVERY": "4"}),
+              ("concurrent_tma_74ctas", 2, 0, {"PLANET_PUSH_CTAS": "74"})]
 res = {"rank": rank, "world": world, "quads_per_gpu": nq}
 for name, mode, share, env in MODES:
     for k in KNOBS:
