@@ -202,7 +202,9 @@ __host__ __device__ inline void probe_leaf(const State &st, const Shape &sh, con
     const uint64_t id = quads[i].id;
     const int own = find<LANES>(st.ids, sh.map_max, id, id);
     int par = -1;
-    if (own < 0 && quad_depth(id) > 0) { const uint64_t pid = parent_of(id); par = find<LANES>(st.ids, sh.map_max, pid, pid); }
+    // the parent is probed even when the leaf itself is cached: the leaf's entry may be evicted earlier in
+    // this frame, and its turn then needs the parent (found by the randomised lists of tests/test_cache.py)
+    if (quad_depth(id) > 0) { const uint64_t pid = parent_of(id); par = find<LANES>(st.ids, sh.map_max, pid, pid); }
     if (Lanes<LANES>::lane() == 0) { sc.own[i] = own; sc.par[i] = par; }
 }
 

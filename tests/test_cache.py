@@ -121,6 +121,50 @@ def test_plan_frame_on_lists_that_are_not_a_leaf_set(ref, port):
     cache.close()
 
 
+def random_lists(port, seed, frames=24):
+    """Seeded random quad lists over a universe of 2 304 ids (two faces at depth 5 plus their depth-4 parents and the
+    roots): sizes 50..700, budgets 0..300, duplicates and parent/child mixes included, enough distinct ids to keep the
+    1 024-entry cache evicting."""
+    rng = np.random.default_rng(seed)
+    universe = np.concatenate([port.uniform_quads(0, 5), port.uniform_quads(1, 5), port.uniform_quads(0, 4),
+                               np.concatenate([port.uniform_quads(f, 0) for f in range(6)])])
+    out = []
+    for _ in range(frames):
+        n = int(rng.integers(50, 700))
+        hot = rng.integers(0, len(universe) - n)                       # a window (locality, like a camera) + scattered ids
+        idx = np.concatenate([np.arange(hot, hot + n // 2), rng.integers(0, len(universe), n - n // 2)])
+        rng.shuffle(idx)
+        out.append((universe[idx], int(rng.choice([0, 1, 7, 100, 300]))))
+    return out
+
+
+def run_random(ref, port, plan, seed):
+    ref.reset_cache()
+    tex_owner, slot_owner = {}, {}
+    for k, (quads, budget) in enumerate(random_lists(port, seed)):
+        want, want_count = ref.cache_lookup(quads, budget)
+        rects, n_gen, count = plan(quads, budget)
+        gen = want[:, 7] != 0
+        assert n_gen == int(gen.sum()) and count == want_count, (seed, k)
+        assert ((rects["flags"] == pb.TEXRECT_GENERATED) == gen).all(), (seed, k)
+        for q, t, r, g in zip(quads, want[:, 0], rects, gen):
+            if g:
+                tex_owner[int(t)] = int(q["id"]); slot_owner[int(r["slot"])] = int(q["id"])
+        assert [tex_owner[int(t)] for t in want[:, 0]] == [slot_owner[int(s)] for s in rects["slot"]], (seed, k)
+        assert rects["corners"].tobytes() == want[:, 1:5].tobytes() and rects["pixel_size"].tobytes() == want[:, 5:7].tobytes(), (seed, k)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_plan_frame_on_random_lists(ref, port, seed):
+    cache = pb.HeightMapCache(32, 1024, 1499, extra_slots=4000)
+
+    def plan(quads, budget):
+        rects, n_gen = cache.plan_frame(quads, budget)
+        return rects, n_gen, cache.count
+    run_random(ref, port, plan, seed)
+    cache.close()
+
+
 def test_a_failed_frame_leaves_the_cache_unchanged(frames):
     cache = pb.HeightMapCache(32, 8, 11, extra_slots=4)
     few = frames[2]["quads"][:6]
@@ -235,4 +279,17 @@ def test_a_failed_device_frame_leaves_the_cache_unchanged(frames, gpu):
     assert cache.count == 6
     r1, n1 = cache.frame_device(few, 18, p, 100)
     assert n0 == 6 and n1 == 0 and (r1[:, 0] == r0[:, 0]).all()
+    cache.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [1, 4])
+def test_device_bookkeeping_on_random_lists(ref, port, gpu, seed):
+    cache = gpu.HeightMapCache(32, 1024, 1499, extra_slots=4000)
+    p = gpu.fbm_params(1, 0.5, gpu.FAST)
+
+    def plan(quads, budget):
+        d_rects, n_gen = cache.frame_device(gpu.quads_to_device(quads), 18, p, budget)
+        return d_rects.cpu().numpy().view(gpu.TEXRECT_DTYPE).reshape(-1), n_gen, cache.count
+    run_random(ref, port, plan, seed)
     cache.close()
