@@ -179,6 +179,21 @@ def test_select_lod_other_cameras_against_the_reference(gpu, ref):
         assert got.tobytes() == want.tobytes(), cam
 
 
+def test_select_lod_on_random_cameras(gpu, ref):
+    """24 seeded cameras from 1 m above the sphere to 3 radii out, anywhere around the planet (and a few inside
+    it): the leaves of the reference's RenderPlanet, in its order, byte for byte."""
+    rng = np.random.default_rng(20261019)
+    R = 6371000.0
+    for k in range(24):
+        d = rng.normal(size=3); d /= np.linalg.norm(d)
+        alt = float(np.exp(rng.uniform(0.0, np.log(3.0 * R)))) if k % 6 else -float(rng.uniform(1.0, 0.5 * R))
+        cam = d * (R + alt)
+        want, _, _ = ref.render_frame(cam)
+        got = gpu.quads_to_host(gpu.select_lod(cam))
+        assert len(got) == len(want), (k, cam, len(got), len(want))
+        assert got.tobytes() == want.tobytes(), (k, cam)
+
+
 def test_select_lod_fallback_paths(gpu, golden):
     """The device-wide sort (more leaves than one CTA sorts) and the per-level launch path."""
     import os, subprocess, sys
