@@ -135,6 +135,22 @@ def test_quads_from_ids_deepest_path_and_invalid_id(gpu, golden, port):
     assert int(got[-1]["id"]) == 0                                # invalid id (main.cpp:35) -> zero quad
 
 
+def test_quads_from_ids_on_random_paths(gpu, port):
+    """400 seeded QuadIDs, every root, depths 0..27, random child paths (all four children at every level within a
+    warp: the walk selects its two midpoints without branching) against the restatement of main.cpp:546-547, 581-594."""
+    rng = np.random.default_rng(7)
+    ids = []
+    for _ in range(400):
+        qid = port.make_root_id(int(rng.integers(0, 6)))
+        for _ in range(int(rng.integers(0, 28))):
+            qid = port.make_child_id(qid, int(rng.integers(0, 4)))
+        ids.append(qid)
+    ids = np.array(ids, np.uint64)
+    got = gpu.quads_to_host(gpu.quads_from_ids(ids))
+    for k, i in enumerate(ids):
+        assert got[k].tobytes() == port.quad_from_id(i).tobytes(), hex(int(i))
+
+
 def test_patch_mesh_bit_exact(gpu, golden, port):
     v, i = gpu.patch_mesh(30)
     assert to_np(v).tobytes() == golden["patch_vertex_buffer"].tobytes()
@@ -643,6 +659,25 @@ def check_shade(gpu, port, quads, maps, cam, n=30):
 def test_shade_default_frame(gpu, port, golden):
     """All 117 leaf quads (depths 0..10: both the slerp and the linear branch of interpolate)."""
     check_shade(gpu, port, quads_from_bytes(golden["frame_quads"]), golden["frame_height_maps"], golden["frame_cam"])
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14, 15, 16])
+def test_shade_on_random_quads_cameras_and_patch_sizes(gpu, port, seed):
+    """Seeded sweep over what K3 is given: quads from random ids at depths 0..14 (both branches of interpolate, the
+    threshold in between), a camera anywhere from the surface to two radii out, patch sizes 2..61, noisy maps."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.choice([2, 5, 12, 30, 31, 44, 61]))
+    quads = []
+    for _ in range(int(rng.integers(3, 20))):
+        qid = port.make_root_id(int(rng.integers(0, 6)))
+        for _ in range(int(rng.integers(0, 15))):
+            qid = port.make_child_id(qid, int(rng.integers(0, 4)))
+        quads.append(port.quad_from_id(qid))
+    quads = np.array(quads)
+    d = rng.normal(size=3); d /= np.linalg.norm(d)
+    cam = d * 6371000.0 * float(rng.uniform(1.0000015, 3.0))
+    maps = port.generate_height_maps(quads, n + 2, 18, height_params(kind=FBM, gain=0.6, fixed_octaves=int(rng.integers(1, 7))), nthreads=4)
+    check_shade(gpu, port, quads, maps, cam, n=n)
 
 
 def test_shade_other_patch_size_and_camera(gpu, port):
