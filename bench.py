@@ -17,6 +17,12 @@ the SM as bulk copies to every peer over NVLink while the kernel computes; arriv
 GPU to GPU, no host barrier inside a step).  Compute without the gather and the plain NCCL
 collective are extra keys.
 
+Environment knobs (experiments; the defaults are what the numbers in DESIGN.md were measured with):
+    PLANET_GATHER_MODE=fused|push|concurrent   how K4 is driven at N > 1
+    PLANET_GATHER_SHADE_SHARE=k                K3's share of the pushes: 0, every k-th map (k >= 2) or -m = m maps in 8
+    PLANET_GATHER_CHUNK_WAVES=a,b              chunk sizes of the `push` mode, in K2 waves
+    PLANET_K1_BESIDE=1                         N = 1: K1's index stream by the slim kernel on a side stream beside K2
+
 `value` counts height-map vertices (32^2 per quad, border included -- SURVEY.md 8d) per second
 with inputs resident in HBM; `e2e` is the same metric through the reference-facing host-buffer
 call (quads in pinned host memory, height maps back to pinned host memory).  `--impl reference`
