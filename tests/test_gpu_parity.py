@@ -839,6 +839,11 @@ def test_k1_k3_write_exactly_their_outputs(gpu, n, nq):
     strip = np.array([L.planet_gpu_strip_index(k, n) for k in range(ni)], np.uint32)
     want = strip[None, :] + (np.arange(nq, dtype=np.uint32) * nv)[:, None]
     assert (to_np(wi).view(np.uint32).reshape(nq, ni) == want).all()
+    # the index stream alone, by the kernel that runs beside K2: same bytes, nothing outside its window
+    bs, ws = _window(torch, nq * ni, torch.int32, pad=4100)
+    gpu._check(L.planet_gpu_merged_indices_beside(C.byref(p), nq, ws.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert _intact(bs, 4100, nq * ni) and torch.equal(ws, wi)
     quads = wq.view(nq, 13)
     heights = gpu.generate_height_maps(quads, dim, 18, gpu.fbm_params(4, 0.5, gpu.FAST, patch_verts=n))
     bp, wp = _window(torch, nq * nv * 4, torch.float32, pad=4100)
