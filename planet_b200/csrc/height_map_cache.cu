@@ -38,6 +38,7 @@
 // reference had already drawn with a texture before deleting it, here shading follows generation.
 #include "planet_common.cuh"
 
+#include <cstddef>
 #include <cstring>
 #include <vector>
 
@@ -195,11 +196,21 @@ __host__ __device__ inline void window(planet_gpu_texrect &r, int dim_i, int qua
     r.pixel_size[0] = r.pixel_size[1] = ((dim / 2.0f - 1.0f) / (float)(dim_i - 3)) / dim;
 }
 
+// the ids of the frame's leaves: inside the 104-byte quads (stride 104) or a packed copy (stride 8)
+struct LeafIds {
+    const unsigned char *base; size_t stride;
+    __host__ __device__ uint64_t operator[](int64_t i) const { return *reinterpret_cast<const uint64_t *>(base + (size_t)i * stride); }
+};
+__host__ __device__ inline LeafIds ids_in(const planet_gpu_quad *quads)
+{
+    return LeafIds{ reinterpret_cast<const unsigned char *>(quads) + offsetof(planet_gpu_quad, id), sizeof(planet_gpu_quad) };
+}
+
 // phase 1 for one leaf: where the leaf and its parent sit in the table as the frame starts
 template <int LANES>
-__host__ __device__ inline void probe_leaf(const State &st, const Shape &sh, const planet_gpu_quad *quads, int64_t i, const Scratch &sc)
+__host__ __device__ inline void probe_leaf(const State &st, const Shape &sh, const LeafIds &leaf, int64_t i, const Scratch &sc)
 {
-    const uint64_t id = quads[i].id;
+    const uint64_t id = leaf[i];
     const int own = find<LANES>(st.ids, sh.map_max, id, id);
     int par = -1;
     // the parent is probed even when the leaf itself is cached: the leaf's entry may be evicted earlier in
@@ -211,7 +222,7 @@ __host__ __device__ inline void probe_leaf(const State &st, const Shape &sh, con
 // phase 2: the frame's leaves in order (main.cpp:655-660 calling :191-278).  All lanes of the
 // cooperating group execute this with identical control flow; lane 0 writes.
 template <int LANES>
-__host__ __device__ inline void resolve_frame(State st, const Shape &sh, const planet_gpu_quad *quads, int64_t n, int budget,
+__host__ __device__ inline void resolve_frame(State st, const Shape &sh, const LeafIds &leaf, int64_t n, int budget,
                                               const Scratch &sc, planet_gpu_texrect *rects)
 {
     const bool writer = Lanes<LANES>::lane() == 0;
@@ -225,7 +236,7 @@ __host__ __device__ inline void resolve_frame(State st, const Shape &sh, const p
     const uint32_t tick = (uint32_t)st.hdr[H_TICK];
 
     for (int64_t i = 0; i < n && !error; i++) {
-        const uint64_t id = quads[i].id;
+        const uint64_t id = leaf[i];
         planet_gpu_texrect r;
         r.flags = PLANET_TEXRECT_HIT;
         window(r, sh.dim, -1);
@@ -285,27 +296,48 @@ __host__ __device__ inline void resolve_frame(State st, const Shape &sh, const p
 // ---- the device frame -----------------------------------------------------------------
 constexpr int PLAN_THREADS = 1024;
 
+// With `in_smem` the whole frame runs out of shared memory: the state blob (40 KB at the reference's
+// 1 024 / 1 499), the per-leaf scratch and a packed copy of the leaf ids are staged there, phase 2's
+// chain of dependent table reads costs shared-memory latency instead of an L2 round trip each
+// (one warp walking 141 leaves: 100-160 us out of global memory, the longest kernel of the frame),
+// and the new state is written to `next` in one coalesced pass at the end.  States too large for
+// shared memory take the same code path on the global copy.
 __global__ void __launch_bounds__(PLAN_THREADS)
 k_plan_frame(const int32_t *__restrict__ cur, int32_t *__restrict__ next, Shape sh, const planet_gpu_quad *__restrict__ quads,
-             int64_t n, int budget, Scratch sc, planet_gpu_texrect *__restrict__ rects, Quad *__restrict__ miss_quads)
+             int64_t n, int budget, Scratch sc_global, planet_gpu_texrect *__restrict__ rects, Quad *__restrict__ miss_quads, int in_smem)
 {
-    // the frame works on a copy; the host makes it current when the frame went through
+    extern __shared__ __align__(16) int32_t s_plan[];
     const size_t words = state_words(sh);
-    for (size_t w = threadIdx.x; w < words; w += PLAN_THREADS) next[w] = cur[w];
+    int32_t *work = in_smem ? s_plan : next;
+    for (size_t w = threadIdx.x; w < words; w += PLAN_THREADS) work[w] = cur[w];
+    Scratch sc = sc_global;
+    LeafIds leaf = ids_in(quads);
+    if (in_smem) {
+        int32_t *at = s_plan + ((words + 1) & ~(size_t)1);                     // keep the id copy 8-byte aligned
+        uint64_t *s_ids = reinterpret_cast<uint64_t *>(at);
+        for (int64_t i = threadIdx.x; i < n; i += PLAN_THREADS) s_ids[i] = quads[i].id;
+        leaf = LeafIds{ reinterpret_cast<const unsigned char *>(s_ids), sizeof(uint64_t) };
+        at += 2 * n;
+        sc = Scratch{ at, at + n, at + 2 * n, at + 3 * n, at + 4 * n };
+    }
     __syncthreads();
-    const State st = state_at(next, sh);
+    const State st = state_at(work, sh);
     const int warp = threadIdx.x >> 5;
-    for (int64_t i = warp; i < n; i += PLAN_THREADS / 32) probe_leaf<32>(st, sh, quads, i, sc);
+    for (int64_t i = warp; i < n; i += PLAN_THREADS / 32) probe_leaf<32>(st, sh, leaf, i, sc);
     __syncthreads();
-    if (warp == 0) resolve_frame<32>(st, sh, quads, n, budget, sc, rects);
+    if (warp == 0) resolve_frame<32>(st, sh, leaf, n, budget, sc, rects);
     __syncthreads();
-    // the K2 batch: the missing quads, compacted (13 eight-byte words each)
+    // the K2 batch: the missing quads, compacted (13 eight-byte words each), and their pool slots
     const int n_gen = st.hdr[H_ERROR] ? 0 : st.hdr[H_NGEN];
     const uint64_t *src = reinterpret_cast<const uint64_t *>(quads);
     uint64_t *dst = reinterpret_cast<uint64_t *>(miss_quads);
     for (int w = threadIdx.x; w < n_gen * 13; w += PLAN_THREADS) {
         const int k = w / 13, part = w - k * 13;
         dst[w] = src[(size_t)sc.miss_src[k] * 13 + part];
+    }
+    if (in_smem) {
+        for (int k = threadIdx.x; k < n_gen; k += PLAN_THREADS) sc_global.miss_slot[k] = sc.miss_slot[k];   // k_scatter_maps reads them
+        for (size_t w = threadIdx.x; w < words; w += PLAN_THREADS) next[w] = work[w];
     }
 }
 
@@ -337,6 +369,7 @@ struct Cache {
     size_t leaf_cap = 0;
     float *d_miss_maps = nullptr; size_t miss_cap = 0;
     int32_t *h_hdr = nullptr;                // pinned: the two integers a frame reads back
+    size_t plan_smem_set = 0;
 };
 
 static void fresh_state(const Shape &sh, int32_t *blob)
@@ -404,7 +437,14 @@ static int frame_on_device(Cache *c, const planet_gpu_params *p, const planet_gp
     if (rc) return rc;
     const Scratch sc = scratch_at(c->d_scratch, c->leaf_cap);
     int32_t *cur = c->d_state[c->current], *next = c->d_state[c->current ^ 1];
-    k_plan_frame<<<1, PLAN_THREADS, 0, stream>>>(cur, next, c->sh, d_quads, n, budget, sc, d_rects, c->d_miss_quads);
+    // the frame out of shared memory when state + ids + scratch fit (they do unless the cache or the frame is huge)
+    const size_t smem = (((state_words(c->sh) + 1) & ~(size_t)1) + 7 * (size_t)n) * sizeof(int32_t);
+    const int in_smem = smem <= 200 * 1024;
+    if (in_smem && smem > 48 * 1024 && smem > c->plan_smem_set) {
+        PLANET_CUDA(cudaFuncSetAttribute(k_plan_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        c->plan_smem_set = 200 * 1024;
+    }
+    k_plan_frame<<<1, PLAN_THREADS, in_smem ? smem : 0, stream>>>(cur, next, c->sh, d_quads, n, budget, sc, d_rects, c->d_miss_quads, in_smem);
     count_launch();
     PLANET_CUDA(cudaGetLastError());
     PLANET_CUDA(cudaMemcpyAsync(c->h_hdr, next, H_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
@@ -481,8 +521,9 @@ int planet_gpu_cache_plan_frame(void *cache, const planet_gpu_quad *h_quads, int
     c->h_scratch.resize((size_t)n * 5 + 1);
     const Scratch sc = scratch_at(c->h_scratch.data(), (size_t)n);
     const State st = state_at(next, c->sh);
-    for (int64_t i = 0; i < n; i++) probe_leaf<1>(st, c->sh, h_quads, i, sc);
-    resolve_frame<1>(st, c->sh, h_quads, n, generations_per_frame, sc, h_rects);
+    const LeafIds leaf = ids_in(h_quads);
+    for (int64_t i = 0; i < n; i++) probe_leaf<1>(st, c->sh, leaf, i, sc);
+    resolve_frame<1>(st, c->sh, leaf, n, generations_per_frame, sc, h_rects);
     if (st.hdr[H_ERROR]) return pool_exhausted(c);
     c->current ^= 1;
     c->count = st.hdr[H_COUNT];
