@@ -219,77 +219,107 @@ __host__ __device__ inline void probe_leaf(const State &st, const Shape &sh, con
     if (Lanes<LANES>::lane() == 0) { sc.own[i] = own; sc.par[i] = par; }
 }
 
-// phase 2: the frame's leaves in order (main.cpp:655-660 calling :191-278).  All lanes of the
-// cooperating group execute this with identical control flow; lane 0 writes.
+// What the bookkeeping decides per leaf, packed into one word: the pool slot to sample (24 bits), the
+// PLANET_TEXRECT_* kind (2 bits) and, for a parent fallback, the child's quadrant (2 bits).  The texrect
+// itself (six float divisions) is built from it afterwards, in parallel, off the sequential path.
+__host__ __device__ inline int32_t pack_result(int slot, int kind, int quadrant) { return slot | (kind << 24) | (quadrant << 26); }
+__host__ __device__ inline planet_gpu_texrect rect_of(int32_t res, int dim)
+{
+    planet_gpu_texrect r;
+    r.slot = res & 0xFFFFFF;
+    r.flags = (res >> 24) & 3;
+    window(r, dim, r.flags == PLANET_TEXRECT_PARENT ? (res >> 26) & 3 : -1);
+    return r;
+}
+
+// the walking state of one frame (identical in every lane of the cooperating group)
+struct Walk { int budget, count, n_free, n_gen, n_inserted, n_evicted, error; uint32_t tick; };
+
 template <int LANES>
-__host__ __device__ inline void resolve_frame(State st, const Shape &sh, const LeafIds &leaf, int64_t n, int budget,
-                                              const Scratch &sc, planet_gpu_texrect *rects)
+__host__ __device__ inline Walk begin_frame(const State &st, int budget)
+{
+    // textures deleted last frame are gone now: their slots return to the stack
+    Walk w;
+    w.n_free = st.hdr[H_NFREE];
+    const int n_deferred = st.hdr[H_NDEFERRED];
+    for (int j = Lanes<LANES>::lane(); j < n_deferred; j += LANES) st.free_slots[w.n_free + j] = st.deferred[j];
+    w.n_free += n_deferred;
+    Lanes<LANES>::sync();
+    w.budget = budget; w.count = st.hdr[H_COUNT]; w.n_gen = w.n_inserted = w.n_evicted = w.error = 0;
+    w.tick = (uint32_t)st.hdr[H_TICK];
+    return w;
+}
+
+// GetHeightMapForQuad (main.cpp:191-278) for leaf i against what the frame has changed so far.  All
+// lanes of the cooperating group execute this with identical control flow; lane 0 writes.
+template <int LANES>
+__host__ __device__ inline void resolve_leaf(const State &st, const Shape &sh, const LeafIds &leaf, int64_t i, const Scratch &sc,
+                                             Walk &w, int32_t *res)
 {
     const bool writer = Lanes<LANES>::lane() == 0;
-    // textures deleted last frame are gone now: their slots return to the stack
-    int n_free = st.hdr[H_NFREE];
-    const int n_deferred = st.hdr[H_NDEFERRED];
-    for (int j = Lanes<LANES>::lane(); j < n_deferred; j += LANES) st.free_slots[n_free + j] = st.deferred[j];
-    n_free += n_deferred;
-    Lanes<LANES>::sync();
-    int count = st.hdr[H_COUNT], n_gen = 0, n_inserted = 0, n_evicted = 0, error = 0;
-    const uint32_t tick = (uint32_t)st.hdr[H_TICK];
-
-    for (int64_t i = 0; i < n && !error; i++) {
-        const uint64_t id = leaf[i];
-        planet_gpu_texrect r;
-        r.flags = PLANET_TEXRECT_HIT;
-        window(r, sh.dim, -1);
-        // the leaf itself: the start-of-frame probe if that slot still holds it, else this frame's insertions
-        int index = sc.own[i];
-        if (index >= 0 && st.ids[index] != id) index = -1;
-        if (index < 0 && n_inserted) index = find_inserted<LANES>(st, sc.inserted, n_inserted, id);
-        if (index < 0) {
-            if (budget <= 0 && quad_depth(id) > 0) {                         // main.cpp:208: budget spent -> try the parent's map
-                const uint64_t pid = parent_of(id);
-                int p = sc.par[i];
-                if (p >= 0 && st.ids[p] != pid) p = -1;
-                if (p < 0 && n_inserted) p = find_inserted<LANES>(st, sc.inserted, n_inserted, pid);
-                if (p >= 0) {
-                    index = p;
-                    r.flags = PLANET_TEXRECT_PARENT;
-                    window(r, sh.dim, (int)((id >> (2 * (quad_depth(id) - 1))) & 3));   // GetChildIndex, main.cpp:51-55
-                }
+    const uint64_t id = leaf[i];
+    int kind = PLANET_TEXRECT_HIT, quadrant = 0;
+    // the leaf itself: the start-of-frame probe if that slot still holds it, else this frame's insertions
+    int index = sc.own[i];
+    if (index >= 0 && st.ids[index] != id) index = -1;
+    if (index < 0 && w.n_inserted) index = find_inserted<LANES>(st, sc.inserted, w.n_inserted, id);
+    if (index < 0) {
+        if (w.budget <= 0 && quad_depth(id) > 0) {                           // main.cpp:208: budget spent -> try the parent's map
+            const uint64_t pid = parent_of(id);
+            int p = sc.par[i];
+            if (p >= 0 && st.ids[p] != pid) p = -1;
+            if (p < 0 && w.n_inserted) p = find_inserted<LANES>(st, sc.inserted, w.n_inserted, pid);
+            if (p >= 0) {
+                index = p;
+                kind = PLANET_TEXRECT_PARENT;
+                quadrant = (int)((id >> (2 * (quad_depth(id) - 1))) & 3);   // GetChildIndex, main.cpp:51-55
             }
-            if (budget > 0 || index < 0) {                                   // main.cpp:239: generate
-                budget--;
-                if (count == sh.cache_max) {                                 // main.cpp:247-266
-                    const int victim = oldest<LANES>(st, sh.map_max, tick);
-                    if (writer) { st.deferred[n_evicted] = st.slot_of[victim]; st.ids[victim] = 0; }
-                    n_evicted++;
-                    count--;
-                    Lanes<LANES>::sync();
-                }
-                if (n_free == 0) { error = ERR_POOL_EXHAUSTED; break; }
-                const int slot = st.free_slots[--n_free];
-                index = find<LANES>(st.ids, sh.map_max, id, 0);              // main.cpp:268: first empty slot of the probe sequence
-                if (writer) {
-                    st.ids[index] = id; st.slot_of[index] = slot;
-                    sc.inserted[n_inserted] = index;
-                    sc.miss_src[n_gen] = (int32_t)i; sc.miss_slot[n_gen] = slot;
-                }
-                n_inserted++; n_gen++; count++;
-                r.flags = PLANET_TEXRECT_GENERATED;
-                window(r, sh.dim, -1);                                       // a generated map is the quad's own
+        }
+        if (w.budget > 0 || index < 0) {                                     // main.cpp:239: generate
+            w.budget--;
+            if (w.count == sh.cache_max) {                                   // main.cpp:247-266
+                const int victim = oldest<LANES>(st, sh.map_max, w.tick);
+                if (writer) { st.deferred[w.n_evicted] = st.slot_of[victim]; st.ids[victim] = 0; }
+                w.n_evicted++;
+                w.count--;
                 Lanes<LANES>::sync();
             }
+            if (w.n_free == 0) { w.error = ERR_POOL_EXHAUSTED; return; }
+            const int slot = st.free_slots[--w.n_free];
+            index = find<LANES>(st.ids, sh.map_max, id, 0);                  // main.cpp:268: first empty slot of the probe sequence
+            if (writer) {
+                st.ids[index] = id; st.slot_of[index] = slot;
+                sc.inserted[w.n_inserted] = index;
+                sc.miss_src[w.n_gen] = (int32_t)i; sc.miss_slot[w.n_gen] = slot;
+            }
+            w.n_inserted++; w.n_gen++; w.count++;
+            kind = PLANET_TEXRECT_GENERATED;                                 // a generated map is the quad's own
+            Lanes<LANES>::sync();
         }
-        if (writer) {
-            st.last_tick[index] = tick;                                      // main.cpp:275
-            r.slot = st.slot_of[index];
-            rects[i] = r;
-        }
-        Lanes<LANES>::sync();
     }
     if (writer) {
-        st.hdr[H_COUNT] = count; st.hdr[H_TICK] = (int32_t)(tick + 1);       // main.cpp:682
-        st.hdr[H_NFREE] = n_free; st.hdr[H_NDEFERRED] = n_evicted;
-        st.hdr[H_NGEN] = n_gen; st.hdr[H_ERROR] = error;
+        st.last_tick[index] = w.tick;                                        // main.cpp:275
+        res[i] = pack_result(st.slot_of[index], kind, quadrant);
+    }
+    Lanes<LANES>::sync();
+}
+
+// A hit in a frame that cannot evict (count + start-of-frame misses <= cache_max): nothing the frame
+// does can take the entry away before the leaf's turn, and a hit changes nothing but its own tick --
+// so all hits of such a frame are resolved at once, in any order, and only the misses are walked.
+__host__ __device__ inline void touch_hit(const State &st, int index, uint32_t tick, int32_t *res_i)
+{
+    st.last_tick[index] = tick;
+    *res_i = pack_result(st.slot_of[index], PLANET_TEXRECT_HIT, 0);
+}
+
+template <int LANES>
+__host__ __device__ inline void end_frame(const State &st, const Walk &w)
+{
+    if (Lanes<LANES>::lane() == 0) {
+        st.hdr[H_COUNT] = w.count; st.hdr[H_TICK] = (int32_t)(w.tick + 1);   // main.cpp:682
+        st.hdr[H_NFREE] = w.n_free; st.hdr[H_NDEFERRED] = w.n_evicted;
+        st.hdr[H_NGEN] = w.n_gen; st.hdr[H_ERROR] = w.error;
     }
 }
 
@@ -297,20 +327,29 @@ __host__ __device__ inline void resolve_frame(State st, const Shape &sh, const L
 constexpr int PLAN_THREADS = 1024;
 
 // With `in_smem` the whole frame runs out of shared memory: the state blob (40 KB at the reference's
-// 1 024 / 1 499), the per-leaf scratch and a packed copy of the leaf ids are staged there, phase 2's
-// chain of dependent table reads costs shared-memory latency instead of an L2 round trip each
-// (one warp walking 141 leaves: 100-160 us out of global memory, the longest kernel of the frame),
-// and the new state is written to `next` in one coalesced pass at the end.  States too large for
-// shared memory take the same code path on the global copy.
+// 1 024 / 1 499), the per-leaf scratch and a packed copy of the leaf ids are staged there and the new
+// state is written to `next` in one coalesced pass at the end.  States too large for shared memory
+// take the same code path on the global copy.
+//   phase 1, all warps   probes (leaf and parent) against the start-of-frame table
+//   phase 2, warp 0      counts the start-of-frame misses; if the frame cannot evict, lists them in order
+//   phase 3, all threads (only then) every hit resolved at once
+//   phase 4, warp 0      walks the misses in order -- or, if evictions are possible, every leaf.  One warp
+//                        running dependent code retires an instruction every ~5 cycles, so what stays
+//                        on this path is only what depends on the frame's earlier decisions (the first
+//                        version walked all leaves and built their texrects here: 90-160 us for 141 leaves)
+//   phase 5, all threads texrects from the packed results, the K2 batch, the state write-back
 __global__ void __launch_bounds__(PLAN_THREADS)
 k_plan_frame(const int32_t *__restrict__ cur, int32_t *__restrict__ next, Shape sh, const planet_gpu_quad *__restrict__ quads,
-             int64_t n, int budget, Scratch sc_global, planet_gpu_texrect *__restrict__ rects, Quad *__restrict__ miss_quads, int in_smem)
+             int64_t n, int budget, Scratch sc_global, int32_t *res_global, planet_gpu_texrect *__restrict__ rects,
+             Quad *__restrict__ miss_quads, int in_smem)
 {
     extern __shared__ __align__(16) int32_t s_plan[];
+    __shared__ int s_fast, s_nmiss;
     const size_t words = state_words(sh);
     int32_t *work = in_smem ? s_plan : next;
     for (size_t w = threadIdx.x; w < words; w += PLAN_THREADS) work[w] = cur[w];
     Scratch sc = sc_global;
+    int32_t *res = res_global, *miss_pos = res_global + n;
     LeafIds leaf = ids_in(quads);
     if (in_smem) {
         int32_t *at = s_plan + ((words + 1) & ~(size_t)1);                     // keep the id copy 8-byte aligned
@@ -319,16 +358,44 @@ k_plan_frame(const int32_t *__restrict__ cur, int32_t *__restrict__ next, Shape 
         leaf = LeafIds{ reinterpret_cast<const unsigned char *>(s_ids), sizeof(uint64_t) };
         at += 2 * n;
         sc = Scratch{ at, at + n, at + 2 * n, at + 3 * n, at + 4 * n };
+        res = at + 5 * n; miss_pos = at + 6 * n;
     }
     __syncthreads();
     const State st = state_at(work, sh);
-    const int warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int64_t i = warp; i < n; i += PLAN_THREADS / 32) probe_leaf<32>(st, sh, leaf, i, sc);
     __syncthreads();
-    if (warp == 0) resolve_frame<32>(st, sh, leaf, n, budget, sc, rects);
+    if (warp == 0) {                                                         // the misses, in order
+        int nm = 0;
+        for (int64_t base = 0; base < n; base += 32) {
+            const int64_t i = base + lane;
+            const bool miss = i < n && sc.own[i] < 0;
+            const unsigned m = __ballot_sync(0xffffffffu, miss);
+            if (miss) miss_pos[nm + __popc(m & ((1u << lane) - 1))] = (int32_t)i;
+            nm += __popc(m);
+        }
+        if (lane == 0) { s_nmiss = nm; s_fast = st.hdr[H_COUNT] + nm <= sh.cache_max; }
+    }
     __syncthreads();
+    const bool fast = s_fast != 0;
+    if (fast) {
+        const uint32_t tick = (uint32_t)st.hdr[H_TICK];
+        for (int64_t i = threadIdx.x; i < n; i += PLAN_THREADS)
+            if (sc.own[i] >= 0) touch_hit(st, sc.own[i], tick, res + i);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        Walk w = begin_frame<32>(st, budget);
+        if (fast) for (int k = 0; k < s_nmiss && !w.error; k++) resolve_leaf<32>(st, sh, leaf, miss_pos[k], sc, w, res);
+        else      for (int64_t i = 0; i < n && !w.error; i++) resolve_leaf<32>(st, sh, leaf, i, sc, w, res);
+        end_frame<32>(st, w);
+    }
+    __syncthreads();
+    const bool failed = st.hdr[H_ERROR] != 0;
+    if (!failed)
+        for (int64_t i = threadIdx.x; i < n; i += PLAN_THREADS) rects[i] = rect_of(res[i], sh.dim);
     // the K2 batch: the missing quads, compacted (13 eight-byte words each), and their pool slots
-    const int n_gen = st.hdr[H_ERROR] ? 0 : st.hdr[H_NGEN];
+    const int n_gen = failed ? 0 : st.hdr[H_NGEN];
     const uint64_t *src = reinterpret_cast<const uint64_t *>(quads);
     uint64_t *dst = reinterpret_cast<uint64_t *>(miss_quads);
     for (int w = threadIdx.x; w < n_gen * 13; w += PLAN_THREADS) {
@@ -420,7 +487,7 @@ static int ensure_device(Cache *c, int64_t n)
         cudaFree(c->d_scratch); cudaFree(c->d_miss_quads); cudaFree(c->d_quads); cudaFree(c->d_rects);   // cudaFree(nullptr) is a no-op
         c->d_scratch = nullptr; c->d_miss_quads = nullptr; c->d_quads = nullptr; c->d_rects = nullptr; c->leaf_cap = 0;
         const size_t want = (size_t)n + 1024;
-        PLANET_CUDA(cudaMalloc(&c->d_scratch, want * 5 * sizeof(int32_t)));
+        PLANET_CUDA(cudaMalloc(&c->d_scratch, want * 7 * sizeof(int32_t)));
         PLANET_CUDA(cudaMalloc(&c->d_miss_quads, want * sizeof(Quad)));
         PLANET_CUDA(cudaMalloc(&c->d_quads, want * sizeof(planet_gpu_quad)));
         PLANET_CUDA(cudaMalloc(&c->d_rects, want * sizeof(planet_gpu_texrect)));
@@ -438,13 +505,14 @@ static int frame_on_device(Cache *c, const planet_gpu_params *p, const planet_gp
     const Scratch sc = scratch_at(c->d_scratch, c->leaf_cap);
     int32_t *cur = c->d_state[c->current], *next = c->d_state[c->current ^ 1];
     // the frame out of shared memory when state + ids + scratch fit (they do unless the cache or the frame is huge)
-    const size_t smem = (((state_words(c->sh) + 1) & ~(size_t)1) + 7 * (size_t)n) * sizeof(int32_t);
+    const size_t smem = (((state_words(c->sh) + 1) & ~(size_t)1) + 9 * (size_t)n) * sizeof(int32_t);
     const int in_smem = smem <= 200 * 1024;
     if (in_smem && smem > 48 * 1024 && smem > c->plan_smem_set) {
         PLANET_CUDA(cudaFuncSetAttribute(k_plan_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         c->plan_smem_set = 200 * 1024;
     }
-    k_plan_frame<<<1, PLAN_THREADS, in_smem ? smem : 0, stream>>>(cur, next, c->sh, d_quads, n, budget, sc, d_rects, c->d_miss_quads, in_smem);
+    k_plan_frame<<<1, PLAN_THREADS, in_smem ? smem : 0, stream>>>(cur, next, c->sh, d_quads, n, budget, sc, c->d_scratch + 5 * c->leaf_cap,
+                                                                  d_rects, c->d_miss_quads, in_smem);
     count_launch();
     PLANET_CUDA(cudaGetLastError());
     PLANET_CUDA(cudaMemcpyAsync(c->h_hdr, next, H_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
@@ -518,12 +586,24 @@ int planet_gpu_cache_plan_frame(void *cache, const planet_gpu_quad *h_quads, int
     // the same three phases as k_plan_frame, one lane
     int32_t *cur = c->h_state[c->current].data(), *next = c->h_state[c->current ^ 1].data();
     memcpy(next, cur, words * sizeof(int32_t));
-    c->h_scratch.resize((size_t)n * 5 + 1);
+    c->h_scratch.resize((size_t)n * 6 + 1);
     const Scratch sc = scratch_at(c->h_scratch.data(), (size_t)n);
     const State st = state_at(next, c->sh);
     const LeafIds leaf = ids_in(h_quads);
+    int32_t *res = c->h_scratch.data() + 5 * (size_t)n;
     for (int64_t i = 0; i < n; i++) probe_leaf<1>(st, c->sh, leaf, i, sc);
-    resolve_frame<1>(st, c->sh, leaf, n, generations_per_frame, sc, h_rects);
+    int n_miss = 0;
+    for (int64_t i = 0; i < n; i++) n_miss += sc.own[i] < 0;
+    const bool fast = st.hdr[H_COUNT] + n_miss <= c->sh.cache_max;           // the frame cannot evict
+    if (fast)
+        for (int64_t i = 0; i < n; i++)
+            if (sc.own[i] >= 0) touch_hit(st, sc.own[i], (uint32_t)st.hdr[H_TICK], res + i);
+    Walk w = begin_frame<1>(st, generations_per_frame);
+    for (int64_t i = 0; i < n && !w.error; i++)
+        if (!fast || sc.own[i] < 0) resolve_leaf<1>(st, c->sh, leaf, i, sc, w, res);
+    end_frame<1>(st, w);
+    if (!w.error)
+        for (int64_t i = 0; i < n; i++) h_rects[i] = rect_of(res[i], c->sh.dim);
     if (st.hdr[H_ERROR]) return pool_exhausted(c);
     c->current ^= 1;
     c->count = st.hdr[H_COUNT];
