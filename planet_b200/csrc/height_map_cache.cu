@@ -10,15 +10,19 @@
 // slot table, last-used ticks, free-slot stack) lives in device memory, and a whole frame is:
 //
 //   k_plan_frame (one CTA)  leaf quads (device, straight from K0) -> texrects + the miss list
-//     phase 1, all warps   one warp per leaf probes the id table as it stood at the start of the
-//                          frame for the leaf and for its parent (a 32-wide compare per step);
-//     phase 2, one warp    walks the leaves in order and resolves them against what the frame has
-//                          changed so far: a probe result is still good if the table slot still
-//                          holds the id (an eviction earlier in the frame empties it), ids inserted
-//                          this frame are looked up in the frame's insertion list; a miss spends
-//                          budget, falls back to the parent or generates; an eviction is ONE
-//                          packed-key maximum over the table (age, then lowest slot) by the warp;
-//     phase 3, all warps   the missing quads are compacted into the K2 batch.
+//     all threads          an exact index over the id table is built for the frame (the reference
+//                          answers "is this id cached?" with a scan of all 1 499 slots); one thread per
+//                          leaf then finds where the leaf and its parent sit as the frame starts;
+//     all threads          in a frame that cannot evict (count + misses <= cache size) every hit is
+//                          resolved at once: nothing can take its entry away before its turn;
+//     one warp             walks what is left -- the misses, or every leaf if evictions are possible
+//                          -- in the reference's order, against what the frame has changed so far:
+//                          a miss spends budget, falls back to the parent or generates; an
+//                          eviction is ONE packed-key maximum over the table (age, then lowest
+//                          slot) by the warp; the empty slot an insertion takes is the first of the
+//                          reference's own probe sequence;
+//     all threads          texrects from the packed per-leaf results; the missing quads compacted
+//                          into the K2 batch; the new state written back.
 //   K2                     ONE batched launch generates every miss (main.cpp:244 once per quad);
 //   k_scatter_maps         moves the finished maps to their pool slots;
 //   K3 (shade_cached)      reads each quad's map through its texrect.
@@ -79,7 +83,8 @@ __host__ __device__ inline State state_at(void *blob, const Shape &s)
 // per-leaf scratch of one frame
 struct Scratch {
     int32_t *own, *par;        // [n] phase-1 probe results (table index or -1)
-    int32_t *inserted;         // [n] table indices filled this frame, in order
+    int32_t *index2;           // [index2_size] the frame's exact index over the id table, see Index2
+    int32_t index2_size;       // a power of two >= 2 * (map_max + n)
     int32_t *miss_src;         // [n] leaf index of the k-th generated map
     int32_t *miss_slot;        // [n] its pool slot
 };
@@ -138,17 +143,41 @@ __host__ __device__ inline int find(const uint64_t *ids, int map_max, uint64_t k
     return -1;
 }
 
-// an id among the table slots filled earlier in this frame (there are at most n of them)
-template <int LANES>
-__host__ __device__ inline int find_inserted(const State &st, const int32_t *inserted, int n_inserted, uint64_t want)
+// "Is this id anywhere in the table, and where?"  The reference answers with a scan of all map_max
+// slots (an eviction leaves no tombstone, so a probe cannot stop at an empty slot).  Here the frame
+// builds, once and in parallel, an exact index over the table -- open addressing on a multiplicative
+// hash, entry = table slot + 1 -- and every such question afterwards is one or two probes, in the
+// parallel pre-pass and on the sequential path alike.  Insertions of the frame are added to it; an
+// eviction needs nothing: a stale entry points at a slot that no longer holds the id, fails the
+// compare and the probe moves on.  (Which EMPTY slot an insertion takes is still the reference's own
+// probe sequence, find(key, 0): that order decides later LRU ties.)
+__host__ __device__ inline uint32_t hash2(uint64_t id, int size)
 {
-    for (int base = 0; base < n_inserted; base += LANES) {
-        const int j = base + Lanes<LANES>::lane();
-        const unsigned hit = Lanes<LANES>::ballot(j < n_inserted && st.ids[inserted[j]] == want);
-        if (hit) return inserted[base + first_bit(hit)];
-    }
-    return -1;
+    return (((uint32_t)id ^ (uint32_t)(id >> 32)) * 2654435761u ^ (uint32_t)(id >> 40)) & (uint32_t)(size - 1);
 }
+__host__ __device__ inline int lookup2(const State &st, const Scratch &sc, uint64_t id)
+{
+    for (uint32_t h = hash2(id, sc.index2_size);; h = (h + 1) & (uint32_t)(sc.index2_size - 1)) {
+        const int e = sc.index2[h];
+        if (e == 0) return -1;
+        if (st.ids[e - 1] == id) return e - 1;
+    }
+}
+// single writer (the sequential path, or the host)
+__host__ __device__ inline void insert2(const Scratch &sc, uint64_t id, int slot)
+{
+    uint32_t h = hash2(id, sc.index2_size);
+    while (sc.index2[h] != 0) h = (h + 1) & (uint32_t)(sc.index2_size - 1);
+    sc.index2[h] = slot + 1;
+}
+#ifdef __CUDACC__
+// many writers (the parallel build)
+__device__ inline void insert2_atomic(const Scratch &sc, uint64_t id, int slot)
+{
+    uint32_t h = hash2(id, sc.index2_size);
+    while (atomicCAS(&sc.index2[h], 0, slot + 1) != 0) h = (h + 1) & (uint32_t)(sc.index2_size - 1);
+}
+#endif
 
 // the entry main.cpp:249-261 evicts: the largest tick age (signed, as there), the lowest table
 // index among equals -- one packed key (age << 32 | ~index), one maximum
@@ -207,16 +236,13 @@ __host__ __device__ inline LeafIds ids_in(const planet_gpu_quad *quads)
 }
 
 // phase 1 for one leaf: where the leaf and its parent sit in the table as the frame starts
-template <int LANES>
-__host__ __device__ inline void probe_leaf(const State &st, const Shape &sh, const LeafIds &leaf, int64_t i, const Scratch &sc)
+__host__ __device__ inline void probe_leaf(const State &st, const LeafIds &leaf, int64_t i, const Scratch &sc)
 {
     const uint64_t id = leaf[i];
-    const int own = find<LANES>(st.ids, sh.map_max, id, id);
-    int par = -1;
+    sc.own[i] = lookup2(st, sc, id);
     // the parent is probed even when the leaf itself is cached: the leaf's entry may be evicted earlier in
     // this frame, and its turn then needs the parent (found by the randomised lists of tests/test_cache.py)
-    if (quad_depth(id) > 0) { const uint64_t pid = parent_of(id); par = find<LANES>(st.ids, sh.map_max, pid, pid); }
-    if (Lanes<LANES>::lane() == 0) { sc.own[i] = own; sc.par[i] = par; }
+    sc.par[i] = quad_depth(id) > 0 ? lookup2(st, sc, parent_of(id)) : -1;
 }
 
 // What the bookkeeping decides per leaf, packed into one word: the pool slot to sample (24 bits), the
@@ -233,7 +259,7 @@ __host__ __device__ inline planet_gpu_texrect rect_of(int32_t res, int dim)
 }
 
 // the walking state of one frame (identical in every lane of the cooperating group)
-struct Walk { int budget, count, n_free, n_gen, n_inserted, n_evicted, error; uint32_t tick; };
+struct Walk { int budget, count, n_free, n_gen, n_evicted, error; uint32_t tick; };
 
 template <int LANES>
 __host__ __device__ inline Walk begin_frame(const State &st, int budget)
@@ -245,7 +271,7 @@ __host__ __device__ inline Walk begin_frame(const State &st, int budget)
     for (int j = Lanes<LANES>::lane(); j < n_deferred; j += LANES) st.free_slots[w.n_free + j] = st.deferred[j];
     w.n_free += n_deferred;
     Lanes<LANES>::sync();
-    w.budget = budget; w.count = st.hdr[H_COUNT]; w.n_gen = w.n_inserted = w.n_evicted = w.error = 0;
+    w.budget = budget; w.count = st.hdr[H_COUNT]; w.n_gen = w.n_evicted = w.error = 0;
     w.tick = (uint32_t)st.hdr[H_TICK];
     return w;
 }
@@ -259,16 +285,15 @@ __host__ __device__ inline void resolve_leaf(const State &st, const Shape &sh, c
     const bool writer = Lanes<LANES>::lane() == 0;
     const uint64_t id = leaf[i];
     int kind = PLANET_TEXRECT_HIT, quadrant = 0;
-    // the leaf itself: the start-of-frame probe if that slot still holds it, else this frame's insertions
+    // the leaf itself: the start-of-frame probe if that slot still holds it, else the table as it is now
+    // (an entry evicted earlier in the frame, or one inserted by an earlier leaf of the frame)
     int index = sc.own[i];
-    if (index >= 0 && st.ids[index] != id) index = -1;
-    if (index < 0 && w.n_inserted) index = find_inserted<LANES>(st, sc.inserted, w.n_inserted, id);
+    if (index < 0 || st.ids[index] != id) index = w.n_gen || w.n_evicted ? lookup2(st, sc, id) : -1;
     if (index < 0) {
         if (w.budget <= 0 && quad_depth(id) > 0) {                           // main.cpp:208: budget spent -> try the parent's map
             const uint64_t pid = parent_of(id);
             int p = sc.par[i];
-            if (p >= 0 && st.ids[p] != pid) p = -1;
-            if (p < 0 && w.n_inserted) p = find_inserted<LANES>(st, sc.inserted, w.n_inserted, pid);
+            if (p < 0 || st.ids[p] != pid) p = w.n_gen || w.n_evicted ? lookup2(st, sc, pid) : -1;
             if (p >= 0) {
                 index = p;
                 kind = PLANET_TEXRECT_PARENT;
@@ -289,10 +314,10 @@ __host__ __device__ inline void resolve_leaf(const State &st, const Shape &sh, c
             index = find<LANES>(st.ids, sh.map_max, id, 0);                  // main.cpp:268: first empty slot of the probe sequence
             if (writer) {
                 st.ids[index] = id; st.slot_of[index] = slot;
-                sc.inserted[w.n_inserted] = index;
+                insert2(sc, id, index);
                 sc.miss_src[w.n_gen] = (int32_t)i; sc.miss_slot[w.n_gen] = slot;
             }
-            w.n_inserted++; w.n_gen++; w.count++;
+            w.n_gen++; w.count++;
             kind = PLANET_TEXRECT_GENERATED;                                 // a generated map is the quad's own
             Lanes<LANES>::sync();
         }
@@ -327,16 +352,18 @@ __host__ __device__ inline void end_frame(const State &st, const Walk &w)
 constexpr int PLAN_THREADS = 1024;
 
 // With `in_smem` the whole frame runs out of shared memory: the state blob (40 KB at the reference's
-// 1 024 / 1 499), the per-leaf scratch and a packed copy of the leaf ids are staged there and the new
-// state is written to `next` in one coalesced pass at the end.  States too large for shared memory
-// take the same code path on the global copy.
-//   phase 1, all warps   probes (leaf and parent) against the start-of-frame table
+// 1 024 / 1 499), the frame's index over it, the per-leaf scratch and a packed copy of the leaf ids are
+// staged there and the new state is written to `next` in one coalesced pass at the end.  States too
+// large for shared memory take the same code path on the global copy.
+//   phase 0, all threads the state copy; the exact index over the id table, built with atomicCAS
+//   phase 1, all threads one thread per leaf: where the leaf and its parent sit as the frame starts
 //   phase 2, warp 0      counts the start-of-frame misses; if the frame cannot evict, lists them in order
 //   phase 3, all threads (only then) every hit resolved at once
 //   phase 4, warp 0      walks the misses in order -- or, if evictions are possible, every leaf.  One warp
 //                        running dependent code retires an instruction every ~5 cycles, so what stays
 //                        on this path is only what depends on the frame's earlier decisions (the first
-//                        version walked all leaves and built their texrects here: 90-160 us for 141 leaves)
+//                        version walked all leaves, scanned the table for every absent id and built the
+//                        texrects here: 90-160 us for 141 leaves)
 //   phase 5, all threads texrects from the packed results, the K2 batch, the state write-back
 __global__ void __launch_bounds__(PLAN_THREADS)
 k_plan_frame(const int32_t *__restrict__ cur, int32_t *__restrict__ next, Shape sh, const planet_gpu_quad *__restrict__ quads,
@@ -357,13 +384,17 @@ k_plan_frame(const int32_t *__restrict__ cur, int32_t *__restrict__ next, Shape 
         for (int64_t i = threadIdx.x; i < n; i += PLAN_THREADS) s_ids[i] = quads[i].id;
         leaf = LeafIds{ reinterpret_cast<const unsigned char *>(s_ids), sizeof(uint64_t) };
         at += 2 * n;
-        sc = Scratch{ at, at + n, at + 2 * n, at + 3 * n, at + 4 * n };
-        res = at + 5 * n; miss_pos = at + 6 * n;
+        sc = Scratch{ at, at + n, at + 6 * n, sc_global.index2_size, at + 2 * n, at + 3 * n };
+        res = at + 4 * n; miss_pos = at + 5 * n;
     }
+    for (int h = threadIdx.x; h < sc.index2_size; h += PLAN_THREADS) sc.index2[h] = 0;
     __syncthreads();
     const State st = state_at(work, sh);
+    for (int k = threadIdx.x; k < sh.map_max; k += PLAN_THREADS)
+        if (st.ids[k] != 0) insert2_atomic(sc, st.ids[k], k);
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int64_t i = warp; i < n; i += PLAN_THREADS / 32) probe_leaf<32>(st, sh, leaf, i, sc);
+    for (int64_t i = threadIdx.x; i < n; i += PLAN_THREADS) probe_leaf(st, leaf, i, sc);
     __syncthreads();
     if (warp == 0) {                                                         // the misses, in order
         int nm = 0;
@@ -437,6 +468,8 @@ struct Cache {
     float *d_miss_maps = nullptr; size_t miss_cap = 0;
     int32_t *h_hdr = nullptr;                // pinned: the two integers a frame reads back
     size_t plan_smem_set = 0;
+    int32_t *d_index2 = nullptr; size_t index2_cap = 0;
+    std::vector<int32_t> h_index2;
 };
 
 static void fresh_state(const Shape &sh, int32_t *blob)
@@ -448,9 +481,17 @@ static void fresh_state(const Shape &sh, int32_t *blob)
     st.hdr[H_NFREE] = sh.pool_slots;
 }
 
-static Scratch scratch_at(int32_t *base, size_t n)
+// size of the frame's index: a power of two, at most half full after every leaf of the frame was inserted
+static int index2_size_for(const Shape &sh, int64_t n)
 {
-    return Scratch{ base, base + n, base + 2 * n, base + 3 * n, base + 4 * n };
+    int size = 1024;
+    while ((int64_t)size < 2 * ((int64_t)sh.map_max + n)) size <<= 1;
+    return size;
+}
+// own | par | miss_src | miss_slot | (res | miss_pos)   -- six arrays of n; the index lives elsewhere
+static Scratch scratch_at(int32_t *base, size_t n, int32_t *index2, int index2_size)
+{
+    return Scratch{ base, base + n, index2, index2_size, base + 2 * n, base + 3 * n };
 }
 
 static int latch(Cache *c, int mode)
@@ -487,7 +528,7 @@ static int ensure_device(Cache *c, int64_t n)
         cudaFree(c->d_scratch); cudaFree(c->d_miss_quads); cudaFree(c->d_quads); cudaFree(c->d_rects);   // cudaFree(nullptr) is a no-op
         c->d_scratch = nullptr; c->d_miss_quads = nullptr; c->d_quads = nullptr; c->d_rects = nullptr; c->leaf_cap = 0;
         const size_t want = (size_t)n + 1024;
-        PLANET_CUDA(cudaMalloc(&c->d_scratch, want * 7 * sizeof(int32_t)));
+        PLANET_CUDA(cudaMalloc(&c->d_scratch, want * 6 * sizeof(int32_t)));
         PLANET_CUDA(cudaMalloc(&c->d_miss_quads, want * sizeof(Quad)));
         PLANET_CUDA(cudaMalloc(&c->d_quads, want * sizeof(planet_gpu_quad)));
         PLANET_CUDA(cudaMalloc(&c->d_rects, want * sizeof(planet_gpu_texrect)));
@@ -502,16 +543,23 @@ static int frame_on_device(Cache *c, const planet_gpu_params *p, const planet_gp
 {
     int rc = ensure_device(c, n);
     if (rc) return rc;
-    const Scratch sc = scratch_at(c->d_scratch, c->leaf_cap);
+    const int index2_size = index2_size_for(c->sh, n);
+    if ((size_t)index2_size > c->index2_cap) {
+        cudaFree(c->d_index2);
+        c->d_index2 = nullptr; c->index2_cap = 0;
+        PLANET_CUDA(cudaMalloc(&c->d_index2, (size_t)index2_size * sizeof(int32_t)));
+        c->index2_cap = (size_t)index2_size;
+    }
+    const Scratch sc = scratch_at(c->d_scratch, c->leaf_cap, c->d_index2, index2_size);
     int32_t *cur = c->d_state[c->current], *next = c->d_state[c->current ^ 1];
-    // the frame out of shared memory when state + ids + scratch fit (they do unless the cache or the frame is huge)
-    const size_t smem = (((state_words(c->sh) + 1) & ~(size_t)1) + 9 * (size_t)n) * sizeof(int32_t);
+    // the frame out of shared memory when state + ids + scratch + index fit (they do unless the cache or the frame is huge)
+    const size_t smem = (((state_words(c->sh) + 1) & ~(size_t)1) + 8 * (size_t)n + (size_t)index2_size) * sizeof(int32_t);
     const int in_smem = smem <= 200 * 1024;
     if (in_smem && smem > 48 * 1024 && smem > c->plan_smem_set) {
         PLANET_CUDA(cudaFuncSetAttribute(k_plan_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         c->plan_smem_set = 200 * 1024;
     }
-    k_plan_frame<<<1, PLAN_THREADS, in_smem ? smem : 0, stream>>>(cur, next, c->sh, d_quads, n, budget, sc, c->d_scratch + 5 * c->leaf_cap,
+    k_plan_frame<<<1, PLAN_THREADS, in_smem ? smem : 0, stream>>>(cur, next, c->sh, d_quads, n, budget, sc, c->d_scratch + 4 * c->leaf_cap,
                                                                   d_rects, c->d_miss_quads, in_smem);
     count_launch();
     PLANET_CUDA(cudaGetLastError());
@@ -563,7 +611,7 @@ void planet_gpu_cache_destroy(void *cache)
     Cache *c = (Cache *)cache;
     if (!c) return;
     cudaFree(c->d_state[0]); cudaFree(c->d_state[1]); cudaFree(c->d_pool); cudaFree(c->d_scratch);
-    cudaFree(c->d_miss_quads); cudaFree(c->d_quads); cudaFree(c->d_rects); cudaFree(c->d_miss_maps);
+    cudaFree(c->d_miss_quads); cudaFree(c->d_quads); cudaFree(c->d_rects); cudaFree(c->d_miss_maps); cudaFree(c->d_index2);
     if (c->h_hdr) cudaFreeHost(c->h_hdr);
     delete c;
 }
@@ -586,12 +634,15 @@ int planet_gpu_cache_plan_frame(void *cache, const planet_gpu_quad *h_quads, int
     // the same three phases as k_plan_frame, one lane
     int32_t *cur = c->h_state[c->current].data(), *next = c->h_state[c->current ^ 1].data();
     memcpy(next, cur, words * sizeof(int32_t));
-    c->h_scratch.resize((size_t)n * 6 + 1);
-    const Scratch sc = scratch_at(c->h_scratch.data(), (size_t)n);
+    c->h_scratch.resize((size_t)n * 5 + 1);
+    c->h_index2.assign((size_t)index2_size_for(c->sh, n), 0);
+    const Scratch sc = scratch_at(c->h_scratch.data(), (size_t)n, c->h_index2.data(), (int)c->h_index2.size());
     const State st = state_at(next, c->sh);
     const LeafIds leaf = ids_in(h_quads);
-    int32_t *res = c->h_scratch.data() + 5 * (size_t)n;
-    for (int64_t i = 0; i < n; i++) probe_leaf<1>(st, c->sh, leaf, i, sc);
+    int32_t *res = c->h_scratch.data() + 4 * (size_t)n;
+    for (int k = 0; k < c->sh.map_max; k++)
+        if (st.ids[k] != 0) insert2(sc, st.ids[k], k);
+    for (int64_t i = 0; i < n; i++) probe_leaf(st, leaf, i, sc);
     int n_miss = 0;
     for (int64_t i = 0; i < n; i++) n_miss += sc.own[i] < 0;
     const bool fast = st.hdr[H_COUNT] + n_miss <= c->sh.cache_max;           // the frame cannot evict
