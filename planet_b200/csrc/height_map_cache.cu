@@ -153,7 +153,16 @@ __host__ __device__ inline int find(const uint64_t *ids, int map_max, uint64_t k
 // probe sequence, find(key, 0): that order decides later LRU ties.)
 __host__ __device__ inline uint32_t hash2(uint64_t id, int size)
 {
-    return (((uint32_t)id ^ (uint32_t)(id >> 32)) * 2654435761u ^ (uint32_t)(id >> 40)) & (uint32_t)(size - 1);
+    // the TOP bits of a multiplicative hash: a QuadID keeps its path in the low bits and root / depth in
+    // bits 55..63, and a shallow quad's low bits are all zero -- the low bits of a product only see the
+    // low bits of its input (taking those made the probe chains hundreds of entries long)
+#ifdef __CUDA_ARCH__
+    const int shift = __clz(size) + 1;
+#else
+    const int shift = __builtin_clz((unsigned)size) + 1;
+#endif
+    const uint32_t x = (uint32_t)id * 0x9E3779B1u ^ (uint32_t)(id >> 32) * 0x85EBCA77u;
+    return (x * 2654435761u) >> shift;
 }
 __host__ __device__ inline int lookup2(const State &st, const Scratch &sc, uint64_t id)
 {
