@@ -120,25 +120,36 @@ __device__ __forceinline__ void lod_group(const unsigned char *s_perm, const flo
         bool near = __dmul_rn(length_sq(exact::sub(p, cam)), 2.0) < d;
         split = __any_sync(0xffffffffu, near);
     }
-    if (!live || lane != 0) return;
+    if (!live) return;                                                // (warp-uniform: one frontier quad per warp)
 
     if (!split) {                                                     // main.cpp:541-543, 573-577
-        int idx = atomicAdd(n_leaves, 1);
-        if (idx < capacity) { leaves[idx] = q; keys[idx] = dfs_key(q.id); }
+        if (lane == 0) {
+            int idx = atomicAdd(n_leaves, 1);
+            if (idx < capacity) { leaves[idx] = q; keys[idx] = dfs_key(q.id); }
+        }
         return;
     }
-    // main.cpp:581-592: 3x3 grid p0, V(0,1), p1, V(0,2), mid, V(1,3), p2, V(2,3), p3
-    int idx = atomicAdd(n_next, 4);
+    // main.cpp:581-592: 3x3 grid p0, V(0,1), p1, V(0,2), mid, V(1,3), p2, V(2,3), p3.  The four edge
+    // midpoints are four independent fp64 normalisations (a division chain each): lanes 0..3 take one
+    // each instead of lane 0 running all four, and lane c then writes child c.
+    int idx = 0;
+    if (lane == 0) idx = atomicAdd(n_next, 4);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
     if (idx + 3 >= capacity) return;
-    d3 v01 = exact::mul(exact::normalize(exact::add(q.p[0], q.p[1])), radius);
-    d3 v02 = exact::mul(exact::normalize(exact::add(q.p[0], q.p[2])), radius);
-    d3 v13 = exact::mul(exact::normalize(exact::add(q.p[1], q.p[3])), radius);
-    d3 v23 = exact::mul(exact::normalize(exact::add(q.p[2], q.p[3])), radius);
-    Quad c;
-    c.p[0] = q.p[0]; c.p[1] = v01; c.p[2] = v02; c.p[3] = mid; c.id = make_child_id(q.id, 0); next[idx + 0] = c;
-    c.p[0] = v01; c.p[1] = q.p[1]; c.p[2] = mid; c.p[3] = v13; c.id = make_child_id(q.id, 1); next[idx + 1] = c;
-    c.p[0] = v02; c.p[1] = mid; c.p[2] = q.p[2]; c.p[3] = v23; c.id = make_child_id(q.id, 2); next[idx + 2] = c;
-    c.p[0] = mid; c.p[1] = v13; c.p[2] = v23; c.p[3] = q.p[3]; c.id = make_child_id(q.id, 3); next[idx + 3] = c;
+    const int e = lane & 3;                                           // edge: V(0,1) V(0,2) V(1,3) V(2,3)
+    const d3 ea = e < 2 ? q.p[0] : e == 2 ? q.p[1] : q.p[2];
+    const d3 eb = e == 0 ? q.p[1] : e == 1 ? q.p[2] : q.p[3];
+    const d3 ev = exact::mul(exact::normalize(exact::add(ea, eb)), radius);
+    const d3 v01 = shfl_d3(ev, 0), v02 = shfl_d3(ev, 1), v13 = shfl_d3(ev, 2), v23 = shfl_d3(ev, 3);
+    if (lane < 4) {
+        Quad c;
+        c.id = make_child_id(q.id, (uint64_t)lane);
+        if (lane == 0)      { c.p[0] = q.p[0]; c.p[1] = v01; c.p[2] = v02; c.p[3] = mid; }
+        else if (lane == 1) { c.p[0] = v01; c.p[1] = q.p[1]; c.p[2] = mid; c.p[3] = v13; }
+        else if (lane == 2) { c.p[0] = v02; c.p[1] = mid; c.p[2] = q.p[2]; c.p[3] = v23; }
+        else                { c.p[0] = mid; c.p[1] = v13; c.p[2] = v23; c.p[3] = q.p[3]; }
+        next[idx + lane] = c;
+    }
 }
 
 // All levels in ONE cooperative launch: a grid-wide barrier separates the levels.
@@ -165,6 +176,36 @@ k_lod_all_levels(Quad *fa, Quad *fb, int max_lod, double radius, double cam_x, d
                       &counters[0], &counters[2 + level]);
         }
         grid.sync();
+        Quad *t = fa; fa = fb; fb = t;
+    }
+}
+
+// The same walk by ONE CTA of 32 warps, a block barrier between the levels instead of a grid barrier
+// (~0.2 us instead of ~2 us, at every one of the dozen levels a frame descends): the frontier of a
+// usual frame is a few dozen quads per level, one or two rounds of 32 warps.  A level wider than
+// `one_cta_max` gives up (counters[30] = 1) and the host runs the grid-wide kernel instead.
+template <int ONE_CTA_THREADS>
+__global__ void __launch_bounds__(ONE_CTA_THREADS)
+k_lod_one_cta(Quad *fa, Quad *fb, int max_lod, double radius, double cam_x, double cam_y, double cam_z,
+              HeightCfg cfg, Quad *leaves, uint64_t *keys, int capacity, int *counters, int one_cta_max)
+{
+    __shared__ unsigned char s_perm[256];
+    __shared__ float s_grad[48];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_perm[i] = g_perm[i];
+    for (int i = threadIdx.x; i < 48; i += blockDim.x) s_grad[i] = (&g_grad[0][0])[i];
+    __syncthreads();
+    const d3 cam = { cam_x, cam_y, cam_z };
+    const int groups = ONE_CTA_THREADS >> 5;
+    int level = 0;
+    for (int lod = max_lod; lod >= 0; lod--, level++) {
+        const int n = min(((volatile int *)counters)[1 + level], capacity);   // written before the last barrier
+        if (n == 0) break;
+        if (n > one_cta_max) { if (threadIdx.x == 0) counters[30] = 1; return; }
+        for (int base = 0; base < n; base += groups)
+            lod_group(s_perm, s_grad, fa, base + (threadIdx.x >> 5), n, lod, max_lod, radius, cam, cfg, leaves, keys, fb, capacity,
+                      &counters[0], &counters[2 + level]);
+        __threadfence_block();
+        __syncthreads();
         Quad *t = fa; fa = fb; fb = t;
     }
 }
@@ -307,22 +348,40 @@ int launch_select_lod(const planet_gpu_params *p, const double *cam, int max_lod
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (coop && cap <= (1 << 16) && max_lod + 3 <= 31 && !getenv("PLANET_K0_LEVEL_LAUNCHES")) {
         const int six = 6;
-        PLANET_CUDA(cudaMemcpyAsync(counters + 1, &six, sizeof(int), cudaMemcpyHostToDevice, stream));
-        int grid = sms;                                               // 148 CTAs x 8 warps = 1 184 quads per pass
         double cx = cam[0], cy = cam[1], cz = cam[2], radius = p->radius;
         int ml = max_lod, capi = cap;
-        void *args[] = { &fa, &fb, &ml, &radius, &cx, &cy, &cz, &cfg, &leaves, &keys, &capi, &counters };
-        PLANET_CUDA(cudaLaunchCooperativeKernel((void *)lod::k_lod_all_levels, dim3(grid), dim3(256), args, 0, stream));
         int block_sort_max = lod::BS_THREADS * lod::BS_ITEMS;
         if (const char *e = getenv("PLANET_K0_BLOCK_SORT_MAX")) block_sort_max = std::min(block_sort_max, atoi(e));   // test knob
-        lod::k_block_sort_gather<<<1, lod::BS_THREADS, 0, stream>>>(leaves, keys, counters, cap, block_sort_max, d_out);
-        count_launch(2);
-        PLANET_CUDA(cudaGetLastError());
+        // frontier width up to which ONE CTA walks the levels (block barriers); test knob: 0 forces the grid-wide kernel
+        int one_cta_max = 256;
+        if (const char *e = getenv("PLANET_K0_ONE_CTA_MAX")) one_cta_max = atoi(e);
         int h[32];
-        PLANET_CUDA(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, stream));
-        PLANET_CUDA(cudaStreamSynchronize(stream));
+        for (int attempt = one_cta_max > 0 ? 0 : 1; attempt < 2; attempt++) {
+            if (attempt == 1 && one_cta_max > 0) {                        // the one-CTA walk gave up: start over, grid-wide
+                PLANET_CUDA(cudaMemsetAsync(counters, 0, 32 * sizeof(int), stream));
+                rc = launch_tessellate_uniform(p, 0, 0, 6, fa, nullptr, stream);
+                if (rc) return rc;
+            }
+            PLANET_CUDA(cudaMemcpyAsync(counters + 1, &six, sizeof(int), cudaMemcpyHostToDevice, stream));
+            if (attempt == 0) {
+                static const int one_cta_threads = [] { const char *e = getenv("PLANET_K0_ONE_CTA_THREADS"); return e ? atoi(e) : 512; }();
+                if (one_cta_threads == 1024)     lod::k_lod_one_cta<1024><<<1, 1024, 0, stream>>>(fa, fb, ml, radius, cx, cy, cz, cfg, leaves, keys, capi, counters, one_cta_max);
+                else if (one_cta_threads == 768) lod::k_lod_one_cta<768><<<1, 768, 0, stream>>>(fa, fb, ml, radius, cx, cy, cz, cfg, leaves, keys, capi, counters, one_cta_max);
+                else                             lod::k_lod_one_cta<512><<<1, 512, 0, stream>>>(fa, fb, ml, radius, cx, cy, cz, cfg, leaves, keys, capi, counters, one_cta_max);
+            } else {
+                int grid = sms;                                           // 148 CTAs x 8 warps = 1 184 quads per pass
+                void *args[] = { &fa, &fb, &ml, &radius, &cx, &cy, &cz, &cfg, &leaves, &keys, &capi, &counters };
+                PLANET_CUDA(cudaLaunchCooperativeKernel((void *)lod::k_lod_all_levels, dim3(grid), dim3(256), args, 0, stream));
+            }
+            lod::k_block_sort_gather<<<1, lod::BS_THREADS, 0, stream>>>(leaves, keys, counters, cap, block_sort_max, d_out);
+            count_launch(2);
+            PLANET_CUDA(cudaGetLastError());
+            PLANET_CUDA(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, stream));
+            PLANET_CUDA(cudaStreamSynchronize(stream));
+            if (!(attempt == 0 && h[30])) break;
+        }
         int64_t worst = h[0];
-        for (int l = 1; l < 31; l++) worst = std::max<int64_t>(worst, h[l]);
+        for (int l = 1; l < 30; l++) worst = std::max<int64_t>(worst, h[l]);
         if (count) *count = h[0];
         if (worst > cap) {
             if (count) *count = worst;
