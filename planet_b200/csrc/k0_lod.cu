@@ -180,36 +180,6 @@ k_lod_all_levels(Quad *fa, Quad *fb, int max_lod, double radius, double cam_x, d
     }
 }
 
-// The same walk by ONE CTA of 32 warps, a block barrier between the levels instead of a grid barrier
-// (~0.2 us instead of ~2 us, at every one of the dozen levels a frame descends): the frontier of a
-// usual frame is a few dozen quads per level, one or two rounds of 32 warps.  A level wider than
-// `one_cta_max` gives up (counters[30] = 1) and the host runs the grid-wide kernel instead.
-template <int ONE_CTA_THREADS>
-__global__ void __launch_bounds__(ONE_CTA_THREADS)
-k_lod_one_cta(Quad *fa, Quad *fb, int max_lod, double radius, double cam_x, double cam_y, double cam_z,
-              HeightCfg cfg, Quad *leaves, uint64_t *keys, int capacity, int *counters, int one_cta_max)
-{
-    __shared__ unsigned char s_perm[256];
-    __shared__ float s_grad[48];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_perm[i] = g_perm[i];
-    for (int i = threadIdx.x; i < 48; i += blockDim.x) s_grad[i] = (&g_grad[0][0])[i];
-    __syncthreads();
-    const d3 cam = { cam_x, cam_y, cam_z };
-    const int groups = ONE_CTA_THREADS >> 5;
-    int level = 0;
-    for (int lod = max_lod; lod >= 0; lod--, level++) {
-        const int n = min(((volatile int *)counters)[1 + level], capacity);   // written before the last barrier
-        if (n == 0) break;
-        if (n > one_cta_max) { if (threadIdx.x == 0) counters[30] = 1; return; }
-        for (int base = 0; base < n; base += groups)
-            lod_group(s_perm, s_grad, fa, base + (threadIdx.x >> 5), n, lod, max_lod, radius, cam, cfg, leaves, keys, fb, capacity,
-                      &counters[0], &counters[2 + level]);
-        __threadfence_block();
-        __syncthreads();
-        Quad *t = fa; fa = fb; fb = t;
-    }
-}
-
 __global__ void __launch_bounds__(256)
 k_lod_level(const Quad *__restrict__ frontier, int n, int lod, int max_lod, double radius,
             double cam_x, double cam_y, double cam_z, HeightCfg cfg, Quad *__restrict__ leaves,
@@ -348,40 +318,25 @@ int launch_select_lod(const planet_gpu_params *p, const double *cam, int max_lod
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (coop && cap <= (1 << 16) && max_lod + 3 <= 31 && !getenv("PLANET_K0_LEVEL_LAUNCHES")) {
         const int six = 6;
+        PLANET_CUDA(cudaMemcpyAsync(counters + 1, &six, sizeof(int), cudaMemcpyHostToDevice, stream));
+        int grid = sms;                                               // 148 CTAs x 8 warps = 1 184 quads per pass
         double cx = cam[0], cy = cam[1], cz = cam[2], radius = p->radius;
         int ml = max_lod, capi = cap;
+        void *args[] = { &fa, &fb, &ml, &radius, &cx, &cy, &cz, &cfg, &leaves, &keys, &capi, &counters };
+        // (One CTA walking the levels with block barriers instead of grid barriers was measured too: 93-113 us
+        //  per frame's selection at 512 / 768 / 1 024 threads against 91 us for this kernel -- a level costs the
+        //  latency of its fp64 chains and 6-octave samples, not its barrier, and one CTA needs more rounds.)
+        PLANET_CUDA(cudaLaunchCooperativeKernel((void *)lod::k_lod_all_levels, dim3(grid), dim3(256), args, 0, stream));
         int block_sort_max = lod::BS_THREADS * lod::BS_ITEMS;
         if (const char *e = getenv("PLANET_K0_BLOCK_SORT_MAX")) block_sort_max = std::min(block_sort_max, atoi(e));   // test knob
-        // frontier width up to which ONE CTA walks the levels (block barriers); test knob: 0 forces the grid-wide kernel
-        int one_cta_max = 256;
-        if (const char *e = getenv("PLANET_K0_ONE_CTA_MAX")) one_cta_max = atoi(e);
+        lod::k_block_sort_gather<<<1, lod::BS_THREADS, 0, stream>>>(leaves, keys, counters, cap, block_sort_max, d_out);
+        count_launch(2);
+        PLANET_CUDA(cudaGetLastError());
         int h[32];
-        for (int attempt = one_cta_max > 0 ? 0 : 1; attempt < 2; attempt++) {
-            if (attempt == 1 && one_cta_max > 0) {                        // the one-CTA walk gave up: start over, grid-wide
-                PLANET_CUDA(cudaMemsetAsync(counters, 0, 32 * sizeof(int), stream));
-                rc = launch_tessellate_uniform(p, 0, 0, 6, fa, nullptr, stream);
-                if (rc) return rc;
-            }
-            PLANET_CUDA(cudaMemcpyAsync(counters + 1, &six, sizeof(int), cudaMemcpyHostToDevice, stream));
-            if (attempt == 0) {
-                static const int one_cta_threads = [] { const char *e = getenv("PLANET_K0_ONE_CTA_THREADS"); return e ? atoi(e) : 512; }();
-                if (one_cta_threads == 1024)     lod::k_lod_one_cta<1024><<<1, 1024, 0, stream>>>(fa, fb, ml, radius, cx, cy, cz, cfg, leaves, keys, capi, counters, one_cta_max);
-                else if (one_cta_threads == 768) lod::k_lod_one_cta<768><<<1, 768, 0, stream>>>(fa, fb, ml, radius, cx, cy, cz, cfg, leaves, keys, capi, counters, one_cta_max);
-                else                             lod::k_lod_one_cta<512><<<1, 512, 0, stream>>>(fa, fb, ml, radius, cx, cy, cz, cfg, leaves, keys, capi, counters, one_cta_max);
-            } else {
-                int grid = sms;                                           // 148 CTAs x 8 warps = 1 184 quads per pass
-                void *args[] = { &fa, &fb, &ml, &radius, &cx, &cy, &cz, &cfg, &leaves, &keys, &capi, &counters };
-                PLANET_CUDA(cudaLaunchCooperativeKernel((void *)lod::k_lod_all_levels, dim3(grid), dim3(256), args, 0, stream));
-            }
-            lod::k_block_sort_gather<<<1, lod::BS_THREADS, 0, stream>>>(leaves, keys, counters, cap, block_sort_max, d_out);
-            count_launch(2);
-            PLANET_CUDA(cudaGetLastError());
-            PLANET_CUDA(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, stream));
-            PLANET_CUDA(cudaStreamSynchronize(stream));
-            if (!(attempt == 0 && h[30])) break;
-        }
+        PLANET_CUDA(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, stream));
+        PLANET_CUDA(cudaStreamSynchronize(stream));
         int64_t worst = h[0];
-        for (int l = 1; l < 30; l++) worst = std::max<int64_t>(worst, h[l]);
+        for (int l = 1; l < 31; l++) worst = std::max<int64_t>(worst, h[l]);
         if (count) *count = h[0];
         if (worst > cap) {
             if (count) *count = worst;

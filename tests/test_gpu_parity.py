@@ -211,16 +211,14 @@ def test_select_lod_on_random_cameras(gpu, ref):
 
 
 def test_select_lod_fallback_paths(gpu, golden):
-    """The device-wide sort (more leaves than one CTA sorts), the per-level launch path, the grid-wide kernel
-    without the one-CTA walk in front of it, and that walk giving up on a wide level."""
+    """The device-wide sort (more leaves than one CTA sorts) and the per-level launch path."""
     import os, subprocess, sys
     code = ("import sys; sys.path.insert(0, %r); import numpy as np, planet_b200 as pb; pb.init(0);"
             "g = np.load(%r); q = pb.quads_to_host(pb.select_lod(g['frame_cam'], 18));"
             "print('OK' if q.tobytes() == g['frame_quads'].tobytes() else 'BAD')")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = code % (root, os.path.join(root, "tests", "golden", "planet_golden.npz"))
-    for knob in ({"PLANET_K0_BLOCK_SORT_MAX": "64"}, {"PLANET_K0_LEVEL_LAUNCHES": "1"}, {"PLANET_K0_ONE_CTA_MAX": "0"},
-                 {"PLANET_K0_ONE_CTA_MAX": "16"}):                # the grid-wide kernel alone; the one-CTA walk giving up half way
+    for knob in ({"PLANET_K0_BLOCK_SORT_MAX": "64"}, {"PLANET_K0_LEVEL_LAUNCHES": "1"}):
         out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **knob), capture_output=True, text=True)
         assert out.stdout.strip().endswith("OK"), (knob, out.stdout, out.stderr)
 
