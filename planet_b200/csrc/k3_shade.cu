@@ -109,6 +109,103 @@ __device__ __forceinline__ float sample_bilinear(const float *tex, int dim, floa
     return fmaf(bot - top, fy, top);
 }
 
+// ---- the two inner bodies, shared by the warp-per-quad kernel and the CTA-per-chunk kernel ----
+// phase B for one column: both edge interpolants at UV.x and the column-constant part of
+// v = interpolate(p, q, UV.y) (main.cpp:310-326, 354-355), as one column record
+__device__ __forceinline__ void column_record(const V *s_corner, float ux, int n, float4 *rec)
+{
+    V p = interpolate(s_corner[0], s_corner[1], ux);                 // main.cpp:354
+    V q = interpolate(s_corner[2], s_corner[3], ux);                 // main.cpp:355
+    float3 pq = q.p - p.p;
+    float len = sqrtf(dot(pq, pq));
+    float d = dot(p.n, q.n);
+    float th2 = -1.0f, itan = 0.f, isin = 0.f;
+    if (!(1.0f - d < 0.001f)) {
+        th2 = acosf(d);
+        float theta = th2 * 0.5f;
+        itan = 1.0f / tanf(theta);
+        isin = 1.0f / sinf(theta);
+    }
+    rec[0] = make_float4(p.p.x, p.p.y, p.p.z, th2);
+    rec[1] = make_float4(p.n.x, p.n.y, p.n.z, 2.0f * (len / (float)(n - 1)));   // 2*xyscale, main.cpp:345,361 (29.0 == n-1)
+    rec[2] = make_float4(pq.x, pq.y, pq.z, 0.5f * len);                         // w: length((q.p - p.p) * 0.5)
+    rec[3] = make_float4(q.n.x - p.n.x, q.n.y - p.n.y, q.n.z - p.n.z, itan);
+    rec[4] = make_float4(isin, 0.f, 0.f, 0.f);
+}
+
+// what phase C needs of its quad
+struct QuadCtx {
+    int n, w, dim; unsigned magic_w;
+    const float *s_uv; const float4 *s_col; const float *s_h; const float *H;
+    planet_gpu_texrect rect; float skirt_size;
+    float4 *pos_q, *nrm_q;
+};
+
+// phase C for vertex slot i of the quad (main.cpp:348-367 + the fragment stage, :371-378)
+template <bool STAGE, bool RECT>
+__device__ __forceinline__ void shade_vertex(const QuadCtx &c, int i)
+{
+    const int n = c.n, w = c.w, dim = c.dim;
+    // Slot -> (row, column).  Padding the top and bottom skirt rows (n slots each) to the
+    // w slots of a body row makes the patch a (n+2) x w grid: virtual index = slot + 1,
+    // + 1 more past the top row, + 1 more past the last body row.
+    const int vi = i + 1 + (i >= n) + (i >= n + n * w);
+    const int vrow = (int)__umulhi((unsigned)vi, c.magic_w);         // vi / w, exact for vi < 2^16, w <= 256
+    const int col = vi - vrow * w;
+    const int vx = min(max(col - 1, 0), n - 1), vy = min(max(vrow - 1, 0), n - 1);
+    const float skirt = (vrow == 0 || vrow == n + 1 || col == 0 || col == w - 1) ? 1.0f : 0.0f;
+    const float t = c.s_uv[vy], omt = 1.0f - t;
+    const int row_off = (vy + 1) * dim;
+    const float4 *rec = c.s_col + vx * (COL_STRIDE / 4);
+    const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
+    const float3 pp = f3(r0.x, r0.y, r0.z), pn = f3(r1.x, r1.y, r1.z);
+    const float3 pq = f3(r2.x, r2.y, r2.z), dn = f3(r3.x, r3.y, r3.z);
+    const float th2 = r0.w;
+    // v = interpolate(p, q, UV.y)                                  // main.cpp:356
+    float3 vp, vn;
+    if (th2 < 0.0f) {                                                // interpolate_linear, main.cpp:300-308
+        // mix(a, b, t) = a + (b - a) t with the column's precomputed b - a
+        vn = normalize(f3(fmaf(dn.x, t, pn.x), fmaf(dn.y, t, pn.y), fmaf(dn.z, t, pn.z)));
+        vp = f3(fmaf(pq.x, t, pp.x), fmaf(pq.y, t, pp.y), fmaf(pq.z, t, pp.z));
+    } else {                                                         // main.cpp:314-331
+        const float3 qn = pn + dn;
+        vn = normalize(pn * sinf(omt * th2) + qn * sinf(t * th2));
+        float gamma = th2 * 0.5f - th2 * t;
+        float itan = r3.w;
+        float x = 1.0f - tanf(gamma) * itan;
+        float y = rec[4].x - itan / cosf(gamma);
+        vp = pp + pq * (0.5f * x) + vn * (y * r2.w);
+    }
+    const int ti = row_off + vx + 1;                                 // texel (vx+1, vy+1)
+    float hc, hl, hr, hu, hd;
+    if (RECT) {
+        // uv = mix(corners0, corners1, UV.xy), taps at +-pixel_size (main.cpp:339-344, 358)
+        const float ux = c.s_uv[vx];                                 // UV.x (skirt literals 0.0f / 1.0f coincide)
+        const float u = c.rect.corners[0] * (1.0f - ux) + c.rect.corners[2] * ux;
+        const float v = c.rect.corners[1] * omt + c.rect.corners[3] * t;
+        hc = sample_bilinear(c.s_h, dim, u, v);
+        hl = sample_bilinear(c.s_h, dim, u - c.rect.pixel_size[0], v);
+        hr = sample_bilinear(c.s_h, dim, u + c.rect.pixel_size[0], v);
+        hu = sample_bilinear(c.s_h, dim, u, v - c.rect.pixel_size[1]);
+        hd = sample_bilinear(c.s_h, dim, u, v + c.rect.pixel_size[1]);
+    } else if (STAGE) { hc = c.s_h[ti]; hl = c.s_h[ti - 1]; hr = c.s_h[ti + 1]; hu = c.s_h[ti - dim]; hd = c.s_h[ti + dim]; }
+    else { hc = __ldg(c.H + ti); hl = __ldg(c.H + ti - 1); hr = __ldg(c.H + ti + 1); hu = __ldg(c.H + ti - dim); hd = __ldg(c.H + ti + dim); }
+    const float height = hc - c.skirt_size * skirt;                  // main.cpp:360
+    float3 nt = normalize(f3(hl - hr, r1.w, hu - hd));               // main.cpp:339-345
+    float3 tg = normalize(cross(vn, pq));                            // main.cpp:363
+    // main.cpp:364-365 normalise bi = cross(t, n) and mat3(t, n, bi) * normal as well; t, n
+    // are unit and orthogonal by construction and |normal| = 1, so both lengths are
+    // 1 +- a few ulp and the two rsqrt/multiply groups are left out (<= 1e-6 rad)
+    float3 bi = cross(tg, vn);
+    float3 N = tg * nt.x + vn * nt.y + bi * nt.z;
+    float3 pos = f3(fmaf(vn.x, height, vp.x), fmaf(vn.y, height, vp.y), fmaf(vn.z, height, vp.z));   // :366
+    // fragment stage at the vertex: l = normalize(0,1,-1), main.cpp:374-378
+    const float inv_sqrt2 = 0.70710678118654752f;
+    float light = 0.001f + fmaxf((N.y - N.z) * inv_sqrt2, 0.0f);
+    if (c.pos_q) __stcs(c.pos_q + i, make_float4(pos.x, pos.y, pos.z, height));
+    if (c.nrm_q) __stcs(c.nrm_q + i, make_float4(N.x, N.y, N.z, sqrt_fast(light)));
+}
+
 // STAGE: height map staged in shared memory (else taps read global via L1).
 // RECT:  each quad reads its map through a texrect (pool slot + corners + pixel size) with
 //        bilinear filtering -- the cache / parent-fallback path (main.cpp:191-237, 334-346, 358).
@@ -180,28 +277,7 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
         }
         __syncwarp();
         // ---- B: per-column edge interpolants and column constants -------------------------------
-        for (int x = lane; x < n; x += 32) {
-            const float ux = s_uv[x];
-            V p = interpolate(s_corner[0], s_corner[1], ux);         // main.cpp:354
-            V q = interpolate(s_corner[2], s_corner[3], ux);         // main.cpp:355
-            float3 pq = q.p - p.p;
-            float len = sqrtf(dot(pq, pq));
-            // column-constant part of v = interpolate(p, q, UV.y), main.cpp:310-326
-            float d = dot(p.n, q.n);
-            float th2 = -1.0f, itan = 0.f, isin = 0.f;
-            if (!(1.0f - d < 0.001f)) {
-                th2 = acosf(d);
-                float theta = th2 * 0.5f;
-                itan = 1.0f / tanf(theta);
-                isin = 1.0f / sinf(theta);
-            }
-            float4 *rec = s_col + x * (COL_STRIDE / 4);
-            rec[0] = make_float4(p.p.x, p.p.y, p.p.z, th2);
-            rec[1] = make_float4(p.n.x, p.n.y, p.n.z, 2.0f * (len / (float)(n - 1)));   // 2*xyscale, main.cpp:345,361 (29.0 == n-1)
-            rec[2] = make_float4(pq.x, pq.y, pq.z, 0.5f * len);                         // w: length((q.p - p.p) * 0.5)
-            rec[3] = make_float4(q.n.x - p.n.x, q.n.y - p.n.y, q.n.z - p.n.z, itan);
-            rec[4] = make_float4(isin, 0.f, 0.f, 0.f);
-        }
+        for (int x = lane; x < n; x += 32) column_record(s_corner, s_uv[x], n, s_col + x * (COL_STRIDE / 4));
         __syncwarp();
         // ---- C: the warp walks the patch rows ----------------------------------------------------
         float skirt_size = max_skirt;                                // main.cpp:674-677
@@ -209,77 +285,81 @@ k_shade(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, dou
             int d = (int)quad_depth(quads[qi].id) - 1;
             if (d > 0) skirt_size /= (float)(2 << d);
         }
-        float4 *pos_q = pos4 ? pos4 + qi * nv : nullptr;
-        float4 *nrm_q = nrm4 ? nrm4 + qi * nv : nullptr;
+        QuadCtx ctx;
+        ctx.n = n; ctx.w = w; ctx.dim = dim; ctx.magic_w = magic_w;
+        ctx.s_uv = s_uv; ctx.s_col = s_col; ctx.s_h = s_h; ctx.H = H; ctx.rect = rect; ctx.skirt_size = skirt_size;
+        ctx.pos_q = pos4 ? pos4 + qi * nv : nullptr;
+        ctx.nrm_q = nrm4 ? nrm4 + qi * nv : nullptr;
         // The warp walks the quad's nv vertex slots 32 at a time (main.cpp:406-422 order: n top-skirt
         // slots, n rows of n+2, n bottom-skirt slots); a lane's slot gives its row and column.  For
         // the reference's n = 30 a 32-slot step is exactly one row; for other sizes lanes of one
-        // step may sit on two rows, which costs nothing since everything below is per lane.
-        for (int i0 = 0; i0 < nv; i0 += 32) {
-            const int i = i0 + lane;
-            if (i < nv) {
-                // Slot -> (row, column).  Padding the top and bottom skirt rows (n slots each) to the
-                // w slots of a body row makes the patch a (n+2) x w grid: virtual index = slot + 1,
-                // + 1 more past the top row, + 1 more past the last body row.
-                const int vi = i + 1 + (i >= n) + (i >= n + n * w);
-                const int vrow = (int)__umulhi((unsigned)vi, magic_w);        // vi / w, exact for vi < 2^16, w <= 256
-                const int c = vi - vrow * w;
-                const int vx = min(max(c - 1, 0), n - 1), vy = min(max(vrow - 1, 0), n - 1);
-                const float skirt = (vrow == 0 || vrow == n + 1 || c == 0 || c == w - 1) ? 1.0f : 0.0f;
-                const float t = s_uv[vy], omt = 1.0f - t;
-                const int row_off = (vy + 1) * dim;
-                const float4 *rec = s_col + vx * (COL_STRIDE / 4);
-                const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
-                const float3 pp = f3(r0.x, r0.y, r0.z), pn = f3(r1.x, r1.y, r1.z);
-                const float3 pq = f3(r2.x, r2.y, r2.z), dn = f3(r3.x, r3.y, r3.z);
-                const float th2 = r0.w;
-                // v = interpolate(p, q, UV.y)                      // main.cpp:356
-                float3 vp, vn;
-                if (th2 < 0.0f) {                                    // interpolate_linear, main.cpp:300-308
-                    // mix(a, b, t) = a + (b - a) t with the column's precomputed b - a
-                    vn = normalize(f3(fmaf(dn.x, t, pn.x), fmaf(dn.y, t, pn.y), fmaf(dn.z, t, pn.z)));
-                    vp = f3(fmaf(pq.x, t, pp.x), fmaf(pq.y, t, pp.y), fmaf(pq.z, t, pp.z));
-                } else {                                             // main.cpp:314-331
-                    const float3 qn = pn + dn;
-                    vn = normalize(pn * sinf(omt * th2) + qn * sinf(t * th2));
-                    float gamma = th2 * 0.5f - th2 * t;
-                    float itan = r3.w;
-                    float x = 1.0f - tanf(gamma) * itan;
-                    float y = rec[4].x - itan / cosf(gamma);
-                    vp = pp + pq * (0.5f * x) + vn * (y * r2.w);
-                }
-                const int ti = row_off + vx + 1;                     // texel (vx+1, vy+1)
-                float hc, hl, hr, hu, hd;
-                if (RECT) {
-                    // uv = mix(corners0, corners1, UV.xy), taps at +-pixel_size (main.cpp:339-344, 358)
-                    const float ux = s_uv[vx];                       // UV.x (skirt literals 0.0f / 1.0f coincide)
-                    const float u = rect.corners[0] * (1.0f - ux) + rect.corners[2] * ux;
-                    const float v = rect.corners[1] * omt + rect.corners[3] * t;
-                    hc = sample_bilinear(s_h, dim, u, v);
-                    hl = sample_bilinear(s_h, dim, u - rect.pixel_size[0], v);
-                    hr = sample_bilinear(s_h, dim, u + rect.pixel_size[0], v);
-                    hu = sample_bilinear(s_h, dim, u, v - rect.pixel_size[1]);
-                    hd = sample_bilinear(s_h, dim, u, v + rect.pixel_size[1]);
-                } else if (STAGE) { hc = s_h[ti]; hl = s_h[ti - 1]; hr = s_h[ti + 1]; hu = s_h[ti - dim]; hd = s_h[ti + dim]; }
-                else { hc = __ldg(H + ti); hl = __ldg(H + ti - 1); hr = __ldg(H + ti + 1); hu = __ldg(H + ti - dim); hd = __ldg(H + ti + dim); }
-                const float height = hc - skirt_size * skirt;        // main.cpp:360
-                float3 nt = normalize(f3(hl - hr, r1.w, hu - hd));   // main.cpp:339-345
-                float3 tg = normalize(cross(vn, pq));                // main.cpp:363
-                // main.cpp:364-365 normalise bi = cross(t, n) and mat3(t, n, bi) * normal as well; t, n
-                // are unit and orthogonal by construction and |normal| = 1, so both lengths are
-                // 1 +- a few ulp and the two rsqrt/multiply groups are left out (<= 1e-6 rad)
-                float3 bi = cross(tg, vn);
-                float3 N = tg * nt.x + vn * nt.y + bi * nt.z;
-                float3 pos = f3(fmaf(vn.x, height, vp.x), fmaf(vn.y, height, vp.y), fmaf(vn.z, height, vp.z));   // :366
-                // fragment stage at the vertex: l = normalize(0,1,-1), main.cpp:374-378
-                const float inv_sqrt2 = 0.70710678118654752f;
-                float light = 0.001f + fmaxf((N.y - N.z) * inv_sqrt2, 0.0f);
-                if (pos_q) __stcs(pos_q + i, make_float4(pos.x, pos.y, pos.z, height));
-                if (nrm_q) __stcs(nrm_q + i, make_float4(N.x, N.y, N.z, sqrt_fast(light)));
-            }
-        }
+        // step may sit on two rows, which costs nothing since everything is per lane.
+        for (int i0 = 0; i0 < nv; i0 += 32)
+            if (i0 + lane < nv) shade_vertex<STAGE, RECT>(ctx, i0 + lane);
     }
     if (PUSH) { if (lane < peers.n) tma::wait_all<0>(); }
+}
+
+// The same stage for FEW, LARGE patches (BASELINE config 5's end of the range: one 254 x 254 patch is
+// 65 532 vertices): one warp per quad leaves the chip empty there (a single 256^2 patch took 1.2 ms),
+// so here a whole CTA works on one (quad, chunk of vertex slots): the corner uniforms, the staged map
+// and the column records are built by all its threads between block barriers, and the slots of the
+// chunk are walked by all its warps.  Several CTAs share a quad; each rebuilds the column records
+// (n interpolations -- small against a chunk of a thousand vertices or more).
+constexpr int WIDE_THREADS = 256;
+constexpr int WIDE_MIN_CHUNK = 1024;       // vertex slots per work item, at least (the host sizes chunks to ~4 items per SM)
+
+template <bool STAGE>
+__global__ void __launch_bounds__(WIDE_THREADS)
+k_shade_wide(const Quad *__restrict__ quads, int64_t nquads, int n, double cam_x, double cam_y, double cam_z,
+             const float *__restrict__ heights, float max_skirt, float4 *__restrict__ pos4, float4 *__restrict__ nrm4,
+             int chunks, int chunk)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int dim = n + 2, dim2 = dim * dim, w = n + 2, nv = n * n + 4 * n;
+    const int np = (n + 31) & ~31;
+    float *s_uv = reinterpret_cast<float *>(smem);
+    unsigned char *mine = smem + np * sizeof(float);
+    V *s_corner = reinterpret_cast<V *>(mine);
+    float4 *s_col = reinterpret_cast<float4 *>(mine + 128);
+    float *s_h = reinterpret_cast<float *>(s_col) + COL_STRIDE * np;
+    const double div = __ddiv_rn(1.0, (double)(n - 1));              // main.cpp:404
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_uv[i] = __double2float_rn(__dmul_rn((double)i, div));
+    int64_t staged = -1;                                             // quad whose uniforms / map / columns are in shared memory
+    for (int64_t item = blockIdx.x; item < nquads * chunks; item += gridDim.x) {
+        const int64_t qi = item / chunks;
+        const int ch = (int)(item - qi * chunks);
+        const float *H = heights + qi * dim2;
+        if (qi != staged) {                                          // (block-uniform)
+            __syncthreads();                                         // the previous quad is fully shaded
+            if (threadIdx.x < 4) {
+                const d3 p = quads[qi].p[threadIdx.x];
+                d3 rel = { p.x - cam_x, p.y - cam_y, p.z - cam_z };  // main.cpp:668
+                d3 nd = exact::normalize(p);                         // main.cpp:669
+                V c;
+                c.p = f3((float)rel.x, (float)rel.y, (float)rel.z);
+                c.n = f3((float)nd.x, (float)nd.y, (float)nd.z);
+                s_corner[threadIdx.x] = c;
+            }
+            if (STAGE) for (int i = threadIdx.x; i < dim2; i += blockDim.x) s_h[i] = __ldcs(H + i);
+            __syncthreads();
+            for (int x = threadIdx.x; x < n; x += blockDim.x) column_record(s_corner, s_uv[x], n, s_col + x * (COL_STRIDE / 4));
+            __syncthreads();
+            staged = qi;
+        }
+        QuadCtx ctx;
+        ctx.n = n; ctx.w = w; ctx.dim = dim; ctx.magic_w = (unsigned)(((1ull << 32) + (unsigned)w - 1) / (unsigned)w);
+        ctx.s_uv = s_uv; ctx.s_col = s_col; ctx.s_h = s_h; ctx.H = H; ctx.rect = planet_gpu_texrect{};
+        ctx.skirt_size = max_skirt;                                  // main.cpp:674-677
+        {
+            int d = (int)quad_depth(quads[qi].id) - 1;
+            if (d > 0) ctx.skirt_size /= (float)(2 << d);
+        }
+        ctx.pos_q = pos4 ? pos4 + qi * nv : nullptr;
+        ctx.nrm_q = nrm4 ? nrm4 + qi * nv : nullptr;
+        const int hi = min(nv, (ch + 1) * chunk);
+        for (int i = ch * chunk + threadIdx.x; i < hi; i += blockDim.x) shade_vertex<STAGE, false>(ctx, i);
+    }
 }
 
 } // namespace shade
@@ -340,6 +420,28 @@ int launch_shade_push(const planet_gpu_params *p, const Quad *d_quads, int64_t n
     if (const char *e = getenv("PLANET_K3_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));   // tuning knob
     int grid = (int)std::min<int64_t>((nquads + warps - 1) / warps, (int64_t)sms * per_sm);
     float4 *pos = reinterpret_cast<float4 *>(d_pos4), *nrm = reinterpret_cast<float4 *>(d_nrm4);
+    // few quads, large patches: not enough warps at one per quad -- a CTA per (quad, chunk of slots) instead
+    const int nv = n * n + 4 * n;
+    const bool pushing = peers && peers->n > 0 && peers->k3_every != 0;
+    if (!pushing && !d_rects && nv >= 2 * shade::WIDE_MIN_CHUNK && nquads < (int64_t)sms * 16 && !getenv("PLANET_K3_NO_WIDE")) {
+        // chunks sized for about four work items per SM, a multiple of the CTA's 256 slots per round
+        int64_t chunk = std::max<int64_t>(shade::WIDE_MIN_CHUNK, (nquads * nv + 4 * sms - 1) / (4 * sms));
+        chunk = std::min<int64_t>((chunk + shade::WIDE_THREADS - 1) / shade::WIDE_THREADS * shade::WIDE_THREADS, nv);
+        const int chunks = (int)((nv + chunk - 1) / chunk);
+        const size_t wsmem = np * sizeof(float) + ((col_bytes + (stage ? hbytes : 0) + 15) & ~(size_t)15);
+        static size_t wide_configured[64] = {};
+        if (wsmem > 48 * 1024 && wsmem > wide_configured[dev & 63]) {
+            PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade_wide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+            PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade_wide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+            wide_configured[dev & 63] = wsmem;
+        }
+        const int wide_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, budget / wsmem));
+        const int wgrid = (int)std::min<int64_t>(nquads * chunks, (int64_t)sms * wide_per_sm);
+        if (stage) shade::k_shade_wide<true><<<wgrid, shade::WIDE_THREADS, wsmem, stream>>>(d_quads, nquads, n, cam[0], cam[1], cam[2], d_heights, max_skirt, pos, nrm, chunks, (int)chunk);
+        else       shade::k_shade_wide<false><<<wgrid, shade::WIDE_THREADS, wsmem, stream>>>(d_quads, nquads, n, cam[0], cam[1], cam[2], d_heights, max_skirt, pos, nrm, chunks, (int)chunk);
+        count_launch();
+        return check_cuda(cudaGetLastError(), "shade kernel launch");
+    }
     if (peers && peers->n > 0 && peers->k3_every != 0) {
         if (d_rects || !stage) return set_error(PLANET_E_UNSUPPORTED, "shade kernel cannot push this map layout");
         shade::k_shade<true, false, true><<<grid, warps * 32, smem, stream>>>(

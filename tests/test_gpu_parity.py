@@ -459,6 +459,22 @@ def test_c5_shade_at_larger_patches(gpu, port, golden, n):
             gpu.shade(gpu.quads_to_device(quads), torch.zeros((2, 258, 258), device="cuda"), golden["frame_cam"], gpu.default_params(patch_verts=256))
 
 
+@pytest.mark.parametrize("n,nq", [(44, 3), (62, 1), (126, 5), (254, 2)])
+def test_shade_cta_per_chunk_kernel_gives_the_warp_per_quad_bytes(gpu, golden, monkeypatch, n, nq):
+    """Few large patches are shaded by a CTA per (quad, chunk of slots) instead of a warp per quad: same
+    per-vertex code, same column records -- the outputs must be the same bytes."""
+    import torch
+    quads = gpu.quads_to_device(quads_from_bytes(golden["frame_quads"])[[1, 30, 77, 100, 116][:nq]])
+    p = gpu.fbm_params(5, 0.5, gpu.FAST, patch_verts=n)
+    maps = gpu.generate_height_maps(quads, n + 2, 18, p)
+    cam = golden["frame_cam"]
+    pos_w, nrm_w = gpu.shade(quads, maps, cam, p)
+    monkeypatch.setenv("PLANET_K3_NO_WIDE", "1")
+    pos_q, nrm_q = gpu.shade(quads, maps, cam, p)
+    assert torch.equal(pos_w, pos_q) and torch.equal(nrm_w, nrm_q)
+    assert bool(torch.isfinite(pos_w).all()) and bool((nrm_w[..., :3].norm(dim=-1) - 1).abs().max() < 1e-5)
+
+
 def test_batched_api_from_four_threads_on_four_streams(gpu):
     """The batched entry points are stream-ordered and re-entrant: four host threads, each on its
     own CUDA stream, run K1 + K2 + K3 on different quad ranges and get the single-threaded bytes."""
