@@ -428,7 +428,11 @@ int launch_shade_push(const planet_gpu_params *p, const Quad *d_quads, int64_t n
         int64_t chunk = std::max<int64_t>(shade::WIDE_MIN_CHUNK, (nquads * nv + 4 * sms - 1) / (4 * sms));
         chunk = std::min<int64_t>((chunk + shade::WIDE_THREADS - 1) / shade::WIDE_THREADS * shade::WIDE_THREADS, nv);
         const int chunks = (int)((nv + chunk - 1) / chunk);
-        const size_t wsmem = np * sizeof(float) + ((col_bytes + (stage ? hbytes : 0) + 15) & ~(size_t)15);
+        // a CTA that shades a whole quad stages its map in shared memory; CTAs that share a quad read their
+        // taps through L1 instead of each staging the whole map for a slice of it (dim 128, 256 patches:
+        // 137 -> measured faster unstaged, profiles/r02zx / r02zy C5 K3 rows)
+        const bool wstage = stage && chunks == 1;
+        const size_t wsmem = np * sizeof(float) + ((col_bytes + (wstage ? hbytes : 0) + 15) & ~(size_t)15);
         static size_t wide_configured[64] = {};
         if (wsmem > 48 * 1024 && wsmem > wide_configured[dev & 63]) {
             PLANET_CUDA(cudaFuncSetAttribute(shade::k_shade_wide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
@@ -437,7 +441,7 @@ int launch_shade_push(const planet_gpu_params *p, const Quad *d_quads, int64_t n
         }
         const int wide_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, budget / wsmem));
         const int wgrid = (int)std::min<int64_t>(nquads * chunks, (int64_t)sms * wide_per_sm);
-        if (stage) shade::k_shade_wide<true><<<wgrid, shade::WIDE_THREADS, wsmem, stream>>>(d_quads, nquads, n, cam[0], cam[1], cam[2], d_heights, max_skirt, pos, nrm, chunks, (int)chunk);
+        if (wstage) shade::k_shade_wide<true><<<wgrid, shade::WIDE_THREADS, wsmem, stream>>>(d_quads, nquads, n, cam[0], cam[1], cam[2], d_heights, max_skirt, pos, nrm, chunks, (int)chunk);
         else       shade::k_shade_wide<false><<<wgrid, shade::WIDE_THREADS, wsmem, stream>>>(d_quads, nquads, n, cam[0], cam[1], cam[2], d_heights, max_skirt, pos, nrm, chunks, (int)chunk);
         count_launch();
         return check_cuda(cudaGetLastError(), "shade kernel launch");
