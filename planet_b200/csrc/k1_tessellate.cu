@@ -401,6 +401,8 @@ static const uint32_t *cached_strip(int n, int ni, cudaStream_t stream)
     return d;
 }
 
+int launch_index_stream_beside(const planet_gpu_params *p, int64_t nquads, uint32_t *d_indices, cudaStream_t stream);
+
 int launch_tessellate_uniform(const planet_gpu_params *p, int depth, int64_t first, int64_t nquads,
                               Quad *d_quads, uint32_t *d_indices, cudaStream_t stream)
 {
@@ -440,6 +442,18 @@ int launch_tessellate_uniform(const planet_gpu_params *p, int depth, int64_t fir
             int idx_blocks = (int)std::min<int64_t>(nquads, (int64_t)sm_count_k1() * per_sm);
             k_tessellate_bulk<<<quad_blocks + idx_blocks, BULK_THREADS, bulk_smem, stream>>>(
                 depth, first, nquads, p->radius, d_quads, quad_blocks, n, nv, ni, d_indices, strip);
+        } else if ((size_t)ni * sizeof(uint32_t) > 200 * 1024) {
+            // a patch whose strip alone outgrows shared memory (n > 158): the quads by their own kernel, the
+            // indices by the kernel that reads the strip through L1 (it needs the 16-byte shape: even n)
+            if (!vec4)
+                return set_error(PLANET_E_UNSUPPORTED, "merged index buffer for patch_verts %d: the strip (%d indices) does not fit "
+                                 "shared memory and is not a whole number of 16-byte vectors", n, ni);
+            if (d_quads) {
+                int grid = (int)std::min<int64_t>((nquads + 31) / 32, (int64_t)sm_count_k1() * 16);
+                k_quads_uniform<<<grid, 32, 0, stream>>>(depth, first, nquads, p->radius, d_quads);
+                count_launch();
+            }
+            return launch_index_stream_beside(p, nquads, d_indices, stream);
         } else {
             size_t smem = (size_t)ni * sizeof(uint32_t);
             if (smem > 48 * 1024) {

@@ -430,6 +430,24 @@ def test_index_stream_beside_k2_writes_the_same_indices(gpu, n, nq):
     assert torch.equal(maps, gpu.generate_height_maps(quads, n + 2, 18, p))
 
 
+def test_k1_indices_at_c5_patch_sizes(gpu, port):
+    """Merged strip indices for the large patches of config 5: n = 126 (the strip still fits shared memory) and
+    n = 254 (it does not: the indices come from the kernel that reads the strip through L1); an odd n past
+    that limit is refused with a message, not a launch failure."""
+    import torch
+    for n in (126, 254):
+        p = gpu.default_params(patch_verts=n)
+        nv, ni = gpu.patch_vertex_count(n), gpu.patch_index_count(n)
+        quads, idx = gpu.tessellate_uniform(2, first=5, nquads=3, params=p, with_indices=True)
+        strip = port.patch_indices(n).astype(np.int64)
+        want = (np.arange(3, dtype=np.int64)[:, None] * nv + strip[None, :]).astype(np.uint32)
+        assert to_np(idx).view(np.uint32).reshape(3, ni).tobytes() == want.tobytes(), n
+        assert gpu.quads_to_host(quads).tobytes() == np.concatenate([port.uniform_quads(f, 2) for f in range(6)])[5:8].tobytes()
+    with pytest.raises(gpu.PlanetGpuError, match="does not fit"):
+        gpu.tessellate_uniform(1, first=0, nquads=1, params=gpu.default_params(patch_verts=201), with_indices=True)
+    torch.cuda.synchronize()
+
+
 @pytest.mark.parametrize("dim", [128, 512, 2048])
 def test_c5_dims_between_the_probes(gpu, port, golden, dim):
     """BASELINE config 5 sweeps dim 64..4096; 1024 and 4096 are covered above, these are the sizes
