@@ -29,3 +29,16 @@ def test_reference_arm_other_ranks_exit_without_work():
                           "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout == ""
+
+
+def test_both_arms_emit_the_same_config_object():
+    """The driver compares the two arms' `config` objects: both come from make_config(world) and
+    neither arm adds keys of its own afterwards."""
+    import bench
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert "config.update" not in src and src.count("make_config(world)") >= 2
+    for world in (1, 2, 4, 8):
+        c = bench.make_config(world)
+        assert {"workload", "depth", "dim", "octaves", "gain", "faces", "quads", "vertices", "gpus", "quads_per_gpu",
+                "vertices_per_gpu", "precision", "l2", "step"} <= set(c)
+        assert c["quads"] == (16384 if world == 1 else 98304) and c["quads_per_gpu"] * world >= c["quads"]
