@@ -137,3 +137,31 @@ def test_k3_flat_height_map_normal_is_the_interpolated_normal_and_positions_lie_
             # (in the slerp branch y = 1/sin(theta) - 1/(cos(gamma) tan(theta)) cancels to ~1 fp32 ulp of 1/sin(theta),
             #  times half the chord: the shader's own rounding, a fraction of a metre on a 1000 km quad)
             assert np.abs(pos[k, slot, :3] - want).max() <= tol, (k, i)
+
+
+def test_restatement_of_the_parent_fallback_sampling_agrees_with_the_evaluator(ref, port, golden):
+    """The other way the shader reads a map: through texrect corners that select the child's quadrant of the
+    PARENT's texture, with a larger pixel size (main.cpp:212-236, 334-346, 358) and GL_LINEAR filtering between
+    texels.  Draws of that kind are taken from the reference on a flight that exhausts the generation budget; the
+    restatement's rect path is compared with the float64 evaluation fed with the reference's own uniforms."""
+    from test_cache import camera_path
+    from oracle.bindings import height_params
+    uv3 = golden["patch_vertex_buffer"].view(np.float32).reshape(-1, 3)
+    ref.reset_cache()
+    textures, checked = {}, 0
+    for cam in camera_path()[:6]:
+        quads, maps, draws, tex = ref.render_next_frame(cam, height_params())
+        textures.update(maps)
+        fallback = np.flatnonzero(draws[:, 29] != np.float32(1.0 / 32))
+        for k in fallback[:: max(1, len(fallback) // 12)]:
+            tmap = textures[int(tex[k])]
+            r = shade_draw(uv3, draws[k], tmap)
+            pos, nrm = port.shade_patches_rect(quads[k:k + 1], cam, tmap[None], np.zeros(1, np.int32), draws[k:k + 1, 25:31])
+            assert angle(r["normal"], nrm[0, :, :3]).max() <= 1e-5
+            hrange = float(np.ptp(tmap))
+            assert np.abs(r["height"] - pos[0, :, 3]).max() <= 1e-5 * hrange + 0.05      # fp32 bilinear weights vs float64
+            rel = np.abs(quads[k]["p"] - cam).max()
+            ext = np.linalg.norm(quads[k]["p"][3] - quads[k]["p"][0])
+            assert np.abs(r["pos"] - pos[0, :, :3]).max() <= 8 * 2.0 ** -23 * rel + 1e-5 * ext + 1e-5 * hrange
+            checked += 1
+    assert checked >= 10, "the flight produced no parent-fallback draws to check"
