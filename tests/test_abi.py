@@ -26,6 +26,19 @@ def test_library_exports_every_declared_symbol():
     assert sorted(pb.EXPORTED_SYMBOLS) == names
 
 
+def test_header_is_plain_c_and_cxx():
+    """include/planet_gpu.h is the boundary a reference-side binding (C, C++, cgo, ctypes ...) compiles against:
+    plain C99, no CUDA, torch or C++ types in any signature."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "planet_gpu.h")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr])
+    import re
+    code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)       # comments may name what the signatures avoid
+    for banned in ("cudaStream_t", "torch", "std::", "#include <cuda", "at::", "c10::"):
+        assert banned not in code, banned
+
+
 def test_abi_version_and_struct_layout():
     assert pb.lib().planet_gpu_abi_version() == 1
     assert C.sizeof(pb.Params) == 72                       # planet_gpu_params
