@@ -138,3 +138,58 @@ def test_k2_octave_loop_has_not_grown():
         assert len(octave) >= 3, (name, octave)
         assert octave[0] <= (184 if fbm else 193), (name, octave)
         assert octave[-1] <= (190 if fbm else 201), (name, octave)
+
+
+def _sass_by_function():
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    lib = os.path.join(ROOT, "planet_b200", "libplanet_gpu.so")
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+    res = subprocess.run(["cuobjdump", "-res-usage", lib], capture_output=True, text=True, check=True).stdout
+    code = {c.split("\n", 1)[0].strip(): c for c in sass.split("Function : ")[1:]}
+    usage = {}
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+)", res):
+        usage[m.group(1)] = dict(reg=int(m.group(2)), stack=int(m.group(3)), shared=int(m.group(4)))
+    return code, usage
+
+
+def test_kernels_that_must_use_the_tma_unit_do_and_the_plain_k2_does_not():
+    """Read from the built library, no GPU: the index stream of K1, the fused gather of K2, K3's share of it
+    and the TMA pusher move their bytes as bulk copies (SASS UBLKCP); the single-GPU K2 carries none of it."""
+    code, _ = _sass_by_function()
+    def one(*parts):
+        names = [n for n in code if all(p in n for p in parts)]
+        assert len(names) == 1, (parts, names)
+        return code[names[0]]
+    assert "UBLKCP" in one("k_tessellate_bulk")
+    assert "UBLKCP" in one("k_height_maps_fast", "Li768ELi32ELb1ELi1E")          # <768, 32, gather, fBm>
+    assert "UBLKCP" not in one("k_height_maps_fast", "Li768ELi32ELb0ELi1E")      # <768, 32, no gather, fBm>
+    assert "UBLKCP" in one("k_shade", "Lb1ELb0ELb1E")                            # <STAGE, !RECT, PUSH>
+    assert "UBLKCP" not in one("k_shade", "Lb1ELb0ELb0E")
+    assert "UBLKCP" in one("k_push_progress_tma")
+
+
+def test_kernels_meant_to_share_an_sm_with_k2_fit_beside_it():
+    """A resident K2 CTA (768 threads x 80 registers, ~217 KB of shared memory) leaves an SM 4 096 registers and
+    ~10 KB: the pusher kernels and the slim index stream are built to fit there (128 threads x <= 32 registers,
+    <= 10 KB incl. the 1 KB the driver reserves per CTA), and their polling loads carry no fence."""
+    code, usage = _sass_by_function()
+    k2 = [u for n, u in usage.items() if "k_height_maps_fast" in n and "Li768ELi32ELb0ELi1E" in n]
+    assert len(k2) == 1 and k2[0]["reg"] <= 80
+    for key in ("k_push_progress_tma", "k_push_progressE", "k_push_range", "k_index_stream_slim"):
+        hits = [(n, u) for n, u in usage.items() if key in n]
+        assert len(hits) == 1, (key, [n for n, _ in hits])
+        name, u = hits[0]
+        assert u["reg"] <= 32 and u["shared"] <= 10 * 1024, (name, u)
+        assert 768 * 80 + 128 * max(u["reg"], 24) <= 65536
+    # the progress counters are polled with a relaxed load; the acquire fence (MEMBAR.GPU + CCTL.IVALL, an L1
+    # invalidation K2 would feel) is paid once per observed advance, not once per poll
+    for key, fences in (("k_push_progress_tma", 3), ("k_push_progressE", 1)):
+        name = [n for n in code if key in n][0]
+        lines = code[name].splitlines()
+        polls = [i for i, l in enumerate(lines) if "LDG.E.64.STRONG.GPU" in l]
+        assert len(polls) == 1, name
+        assert not any("CCTL" in l or "MEMBAR" in l for l in lines[polls[0]:polls[0] + 3]), name
+        assert sum("CCTL.IVALL" in l for l in lines) <= fences, name
